@@ -1,0 +1,67 @@
+"""ctypes binding of libgenstark_b200.so (include/genstark_b200.h).  There is no CPU fallback: if the
+library is missing it is built with nvcc, and if no CUDA device is present every compute call fails
+loudly (NativeError)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f'libgenstark_b200: {message} (status {code})')
+        self.code = code
+        self.message = message
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build()
+    L = C.CDLL(path)
+    vp, i32, i64, u64, cp = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_char_p
+    P = C.POINTER
+    sigs = {
+        'gs_ctx_create': (i32, [i32, P(vp)]),
+        'gs_ctx_destroy': (None, [vp]),
+        'gs_last_error': (cp, [vp]),
+        'gs_ctx_sync': (i32, [vp]),
+        'gs_ctx_launch_count': (u64, [vp]),
+        'gs_field_supported': (i32, [cp, C.c_size_t]),
+        'gs_field_root_of_unity': (i32, [i32, C.c_char_p]),
+        'gs_field_scalar_op': (i32, [i32, cp, cp, C.c_char_p]),
+        'gs_mat_alloc': (i32, [vp, i64, i64, P(vp)]),
+        'gs_mat_from_bytes': (i32, [vp, cp, i64, i64, P(vp)]),
+        'gs_mat_to_bytes': (i32, [vp, vp, vp]),
+        'gs_mat_shape': (i32, [vp, P(i64), P(i64)]),
+        'gs_mat_device_ptr': (vp, [vp]),
+        'gs_mat_free': (None, [vp]),
+        'gs_interpolate_roots': (i32, [vp, vp, P(vp)]),
+        'gs_eval_polys_at_roots': (i32, [vp, vp, i32, P(vp)]),
+        'gs_vec_binary': (i32, [vp, i32, vp, vp, cp, P(vp)]),
+        'gs_debug_modmul_probe': (i32, [vp, i32, i32, P(C.c_float)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    L._gs_declared = list(sigs)
+    _lib = L
+    return L
+
+
+def declared_symbols():
+    lib()
+    return list(_lib._gs_declared)
+
+
+def check(ctx, rc: int):
+    if rc != 0:
+        msg = lib().gs_last_error(ctx)
+        raise NativeError(rc, msg.decode() if msg else 'unknown error')

@@ -1,0 +1,105 @@
+// Context, device matrices and root tables shared by every entry point of libgenstark_b200.so.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "fp128.cuh"
+#include "../../include/genstark_b200.h"
+
+namespace gs {
+
+
+// ----------------------------------------------------------------------------------------------
+// host-side scalar helpers (u128) -- control path only
+static inline u128 h_root_of_unity(int log_order) {
+    // galois getRootOfUnity: smallest i >= 2 whose g = i^((p-1)/order) has exact order.
+    // The test g^(order/2) != 1 is i^((p-1)/2) != 1, independent of the order, so every order shares
+    // the same i and w_{n/2} = w_n^2.
+    const u128 pm1 = HP - 1;
+    for (u128 i = 2;; ++i) {
+        if (h_pow(i, pm1 >> 1) != 1) return h_pow(i, pm1 >> log_order);
+    }
+}
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    // root tables for w_G
+    int log_g = 24, log_lo = 12;
+    fp* tw_lo = nullptr;
+    fp* tw_hi = nullptr;
+    fp* tw_small = nullptr;     // w_1024^i
+    u128 root_g = 0;
+    // scratch arena (grow on demand)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // pinned mailbox for small device->host results
+    void* mailbox = nullptr;
+    size_t mailbox_bytes = 0;
+    int sm_count = 148;
+    unsigned long long launches = 0;   // kernels launched through this context (bench.py gpu_launches)
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        last_error = buf;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char* what) {
+        return fail(GS_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    int ensure_scratch(size_t bytes) {
+        if (bytes <= scratch_bytes) return GS_OK;
+        if (scratch) { cudaStreamSynchronize(stream); cudaFree(scratch); scratch = nullptr; scratch_bytes = 0; }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&scratch, want);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+        scratch_bytes = want;
+        return GS_OK;
+    }
+    // w_G^e on the host
+    u128 root_pow(u128 e) const { return h_pow(root_g, e); }
+    // primitive root of order 2^log_n from the same family
+    u128 root_of_order(int log_n) const { return h_pow(root_g, (u128)1 << (log_g - log_n)); }
+};
+
+#define GS_CUDA(ctx, call)                                              \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) return (ctx)->cuda_fail(_e, #call);      \
+    } while (0)
+
+struct Mat {
+    Ctx* ctx;
+    fp* data;
+    long long rows, cols;
+    bool owns;
+};
+
+static inline int ctx_init_tables(Ctx* c) {
+    const int lo_n = 1 << c->log_lo;
+    const int hi_n = 1 << (c->log_g > c->log_lo ? c->log_g - c->log_lo : 0);
+    std::vector<fp> lo(lo_n), hi(hi_n), sm(1024);
+    c->root_g = h_root_of_unity(c->log_g);
+    u128 acc = 1;
+    for (int i = 0; i < lo_n; ++i) { lo[i] = fp_from_u128(acc); acc = h_mul(acc, c->root_g); }
+    u128 step = h_pow(c->root_g, (u128)lo_n);
+    acc = 1;
+    for (int i = 0; i < hi_n; ++i) { hi[i] = fp_from_u128(acc); acc = h_mul(acc, step); }
+    u128 w1024 = c->root_of_order(10);
+    acc = 1;
+    for (int i = 0; i < 1024; ++i) { sm[i] = fp_from_u128(acc); acc = h_mul(acc, w1024); }
+    GS_CUDA(c, cudaMalloc(&c->tw_lo, lo_n * sizeof(fp)));
+    GS_CUDA(c, cudaMalloc(&c->tw_hi, hi_n * sizeof(fp)));
+    GS_CUDA(c, cudaMalloc(&c->tw_small, 1024 * sizeof(fp)));
+    GS_CUDA(c, cudaMemcpy(c->tw_lo, lo.data(), lo_n * sizeof(fp), cudaMemcpyHostToDevice));
+    GS_CUDA(c, cudaMemcpy(c->tw_hi, hi.data(), hi_n * sizeof(fp), cudaMemcpyHostToDevice));
+    GS_CUDA(c, cudaMemcpy(c->tw_small, sm.data(), 1024 * sizeof(fp), cudaMemcpyHostToDevice));
+    return GS_OK;
+}
+
+}  // namespace gs

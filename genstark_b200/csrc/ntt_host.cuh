@@ -1,0 +1,134 @@
+// Host-side planning and launch of the K1 passes (see ntt.cuh for the decomposition).
+#pragma once
+#include "core.cuh"
+#include "ntt.cuh"
+
+namespace gs {
+
+struct NttPlan {
+    int n_pass = 0;
+    int log_r[3] = {0, 0, 0};
+};
+
+// radices <= 256; as few passes over HBM as possible
+static inline NttPlan ntt_plan(int log_n, bool pruned) {
+    NttPlan p;
+    if (pruned && log_n <= 8) {
+        // the coset multiply lives in a column pass, so an LDE always has one
+        p.n_pass = 2; p.log_r[0] = (log_n + 1) / 2; p.log_r[1] = log_n / 2;
+    } else if (log_n <= 8) { p.n_pass = 1; p.log_r[0] = log_n; }
+    else if (log_n <= 16) { p.n_pass = 2; p.log_r[0] = (log_n + 1) / 2; p.log_r[1] = log_n / 2; }
+    else {
+        p.n_pass = 3;
+        p.log_r[0] = (log_n + 2) / 3; p.log_r[1] = (log_n + 1) / 3; p.log_r[2] = log_n / 3;
+    }
+    return p;
+}
+
+template <int A, int B>
+static inline cudaError_t launch_pass_t(const NttPassParams& P, dim3 grid, int threads, size_t smem, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(ntt_pass_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+    }
+    ntt_pass_kernel<A, B><<<grid, threads, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
+static inline cudaError_t launch_pass(int log_r, const NttPassParams& P, dim3 grid, int threads, size_t smem, cudaStream_t s) {
+    switch (log_r) {
+        case 0: case 1: return launch_pass_t<1, 0>(P, grid, threads, smem, s);
+        case 2: return launch_pass_t<2, 0>(P, grid, threads, smem, s);
+        case 3: return launch_pass_t<3, 0>(P, grid, threads, smem, s);
+        case 4: return launch_pass_t<4, 0>(P, grid, threads, smem, s);
+        case 5: return launch_pass_t<3, 2>(P, grid, threads, smem, s);
+        case 6: return launch_pass_t<3, 3>(P, grid, threads, smem, s);
+        case 7: return launch_pass_t<4, 3>(P, grid, threads, smem, s);
+        default: return launch_pass_t<4, 4>(P, grid, threads, smem, s);
+    }
+}
+
+static inline int pass_log_r1(int log_r) {
+    static const int t[9] = {1, 1, 2, 3, 4, 3, 3, 4, 4};
+    return t[log_r];
+}
+
+// Transform `rows` vectors.
+//   log_t : log2 of the input length per row (the size of the DFTs actually computed)
+//   log_e : log2 of the pruned leading radix (0 = plain transform; >0 = evaluate on the domain of size
+//           2^(log_t+log_e), i.e. E coset transforms written interleaved / natural order)
+//   inverse: use w^-1 and scale by 2^-log_t (only for log_e == 0)
+// src: rows x 2^log_t (row stride src_stride), dst: rows x 2^(log_t+log_e) (row stride dst_stride).
+// work: rows x 2^(log_t+log_e) scratch (may be null when a single pass suffices).
+static inline int ntt_run(Ctx* c, const fp* src, long long src_stride, fp* dst, long long dst_stride,
+                          fp* work, long long work_stride, int rows, int log_t, int log_e, bool inverse) {
+    const int log_ntot = log_t + log_e;
+    if (log_ntot > c->log_g) return c->fail(GS_E_UNSUPPORTED, "domain 2^%d exceeds root table 2^%d", log_ntot, c->log_g);
+    if (log_t < 1) {
+        // length-1 polynomials: constant on every coset
+        return c->fail(GS_E_UNSUPPORTED, "transform length must be >= 2");
+    }
+    if (log_e > 0 && log_t < 2) return c->fail(GS_E_UNSUPPORTED, "LDE needs at least 4 coefficients");
+    if (log_e > 0 && inverse) return c->fail(GS_E_UNSUPPORTED, "inverse coset transform");
+    NttPlan plan = ntt_plan(log_t, log_e > 0);
+    if (plan.n_pass > 1 && work == nullptr) return c->fail(GS_E_ARG, "work buffer required");
+    int log_m = log_t;
+    int log_npre = log_e;                     // prefixes so far (coset digit)
+    int digits[4]; int nd = 0;
+    if (log_e > 0) digits[nd++] = log_e;
+    for (int p = 0; p < plan.n_pass; ++p) {
+        const int lr = plan.log_r[p];
+        const bool fin = (p == plan.n_pass - 1);
+        log_m -= lr;
+        NttPassParams P;
+        memset(&P, 0, sizeof P);
+        P.tw_lo = c->tw_lo; P.tw_hi = c->tw_hi; P.tw_small = c->tw_small;
+        P.log_g = c->log_g; P.log_lo = c->log_lo;
+        P.inverse = inverse ? 1 : 0;
+        P.final_pass = fin ? 1 : 0;
+        P.log_ntot = log_ntot;
+        P.log_npre = log_npre;
+        P.coset_log_ntot = (p == 0 && log_e > 0) ? log_ntot : 0;
+        // source / destination of this pass
+        const bool first = (p == 0);
+        P.src = first ? src : work;
+        P.src_row_stride = first ? src_stride : work_stride;
+        if (fin) { P.dst = dst; P.dst_row_stride = dst_stride; }
+        else { P.dst = work; P.dst_row_stride = work_stride; }
+        int log_c;
+        dim3 grid;
+        if (!fin) {
+            P.log_m = log_m;
+            P.log_nsub = lr + log_m;
+            P.src_prefix_stride = (first && log_e > 0) ? 0 : (1ll << P.log_nsub);
+            log_c = 12 - lr; if (log_c > log_m) log_c = log_m; if (log_c > 5) log_c = 5;
+            grid = dim3(1u << (log_npre + log_m - log_c), rows);
+        } else {
+            P.log_m = 0;
+            // the final pass reads the first pass' source directly when it is the only pass
+            P.log_d0 = nd > 0 ? digits[0] : 0;
+            P.log_d1 = nd > 1 ? digits[1] : 0;
+            P.log_d2 = nd > 2 ? digits[2] : 0;
+            if (nd > 3) return c->fail(GS_E_UNSUPPORTED, "too many prefix digits");
+            log_c = 12 - lr; if (log_c > P.log_d0) log_c = P.log_d0; if (log_c > 4) log_c = 4;
+            if (inverse) { P.has_scale = 1; P.scale = fp_from_u128(h_inv((u128)1 << log_t)); }
+            grid = dim3(1u << (log_npre - log_c), rows);
+        }
+        P.log_c = log_c;
+        const int lr1 = pass_log_r1(lr), lr2 = lr - lr1;
+        int g1 = (1 << lr2) << log_c, g2 = (lr2 > 0) ? ((1 << lr1) << log_c) : 0;
+        int threads = g1 > g2 ? g1 : g2;
+        if (threads > 256) threads = 256;
+        if (threads < 32) threads = 32;
+        size_t smem = ((size_t)(1 << lr) + (size_t)(1 << lr) * ((1 << log_c) + 1)) * sizeof(fp);
+        cudaError_t e = launch_pass(lr, P, grid, threads, smem, c->stream);
+        if (e != cudaSuccess) return c->cuda_fail(e, "ntt_pass_kernel");
+        c->launches++;
+        digits[nd++] = lr;
+        log_npre += lr;
+    }
+    return GS_OK;
+}
+
+}  // namespace gs

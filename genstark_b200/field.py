@@ -1,0 +1,180 @@
+"""Device-backed mirror of the galois ``FiniteField`` seam.
+
+genSTARK receives this object as ``context.field`` (lib/Stark.ts:37-43) and calls ~35 of its methods;
+the ones that move O(N) data are implemented here on device-resident ``Matrix`` / ``Vector`` handles
+through libgenstark_b200.so.  Method names and argument meaning follow the reference interface so the
+call sites in lib/*.ts read the same."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+from . import _native
+from .air import P128
+
+
+class Context:
+    """One GPU + stream + root tables (gs_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _native.lib()
+        h = C.c_void_p()
+        rc = self._lib.gs_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise _native.NativeError(rc, self._lib.gs_last_error(None).decode())
+        self.handle = h
+        self.device = device
+
+    def check(self, rc: int):
+        _native.check(self.handle, rc)
+
+    def sync(self):
+        self.check(self._lib.gs_ctx_sync(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.gs_ctx_launch_count(self.handle))
+
+    def close(self):
+        if self.handle:
+            self._lib.gs_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Matrix:
+    """rows x cols field elements in HBM (galois ``Matrix``; a ``Vector`` is a 1-row matrix)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.handle = ctx, handle
+        r, c = C.c_int64(), C.c_int64()
+        ctx._lib.gs_mat_shape(handle, C.byref(r), C.byref(c))
+        self.rowCount, self.colCount = r.value, c.value
+
+    @property
+    def length(self) -> int:
+        return self.rowCount * self.colCount
+
+    elementSize = 16
+
+    def toBuffer(self) -> bytes:
+        buf = C.create_string_buffer(self.length * 16)
+        self.ctx.check(self.ctx._lib.gs_mat_to_bytes(self.ctx.handle, self.handle, buf))
+        return buf.raw
+
+    def toValues(self):
+        raw = self.toBuffer()
+        vals = [int.from_bytes(raw[i:i + 16], 'little') for i in range(0, len(raw), 16)]
+        if self.rowCount == 1:
+            return vals
+        return [vals[r * self.colCount:(r + 1) * self.colCount] for r in range(self.rowCount)]
+
+    def free(self):
+        if self.handle:
+            self.ctx._lib.gs_mat_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+Vector = Matrix
+
+
+def _enc(v: int) -> bytes:
+    return int(v).to_bytes(16, 'little')
+
+
+class GpuField:
+    """FiniteField over p128 whose vectors live on a B200."""
+
+    modulus = P128
+    elementSize = 16
+    isOptimized = True
+    one = 1
+    zero = 0
+
+    def __init__(self, ctx: Optional[Context] = None, modulus: int = P128):
+        self._lib = _native.lib()
+        if self._lib.gs_field_supported(_enc(modulus), 16) != 0:
+            raise _native.NativeError(-3, 'only the 128-bit field 2^128 - 9*2^32 + 1 has a native backend')
+        self.ctx = ctx or Context()
+
+    # scalars (host) --------------------------------------------------------------------------------
+    def _scalar(self, op, a, b) -> int:
+        out = C.create_string_buffer(16)
+        rc = self._lib.gs_field_scalar_op(op, _enc(a % P128), _enc(b), out)
+        if rc != 0:
+            raise _native.NativeError(rc, 'scalar op')
+        return int.from_bytes(out.raw, 'little')
+
+    def add(self, a, b): return self._scalar(0, a, b % P128)
+    def sub(self, a, b): return self._scalar(1, a, b % P128)
+    def mul(self, a, b): return self._scalar(2, a, b % P128)
+    def div(self, a, b): return self._scalar(3, a, b % P128)
+    def neg(self, a): return self._scalar(1, 0, a % P128)
+    def inv(self, a): return self._scalar(3, 1, a % P128)
+
+    def exp(self, b, e):
+        if e < 0:
+            b, e = self.inv(b), -e
+        return self._scalar(4, b, e % (P128 - 1) if e >= P128 - 1 else e)
+
+    def getRootOfUnity(self, order: int) -> int:
+        out = C.create_string_buffer(16)
+        rc = self._lib.gs_field_root_of_unity(order.bit_length() - 1, out)
+        if rc != 0 or order & (order - 1):
+            raise _native.NativeError(rc, 'order must be a power of two <= 2^32')
+        return int.from_bytes(out.raw, 'little')
+
+    # constructors ----------------------------------------------------------------------------------
+    def newVectorFrom(self, values: Sequence[int]) -> Matrix:
+        return self.newMatrixFrom([list(values)])
+
+    def newMatrixFrom(self, rows: Sequence[Sequence[int]]) -> Matrix:
+        r, c = len(rows), len(rows[0])
+        raw = b''.join(_enc(v) for row in rows for v in row)
+        return self._from_bytes(raw, r, c)
+
+    def _from_bytes(self, raw: bytes, rows: int, cols: int) -> Matrix:
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_mat_from_bytes(self.ctx.handle, raw, rows, cols, C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    # element-wise (K2) -------------------------------------------------------------------------------
+    def _binary(self, op: int, a: Matrix, b) -> Matrix:
+        h = C.c_void_p()
+        if isinstance(b, Matrix):
+            rc = self._lib.gs_vec_binary(self.ctx.handle, op, a.handle, b.handle, None, C.byref(h))
+        else:
+            rc = self._lib.gs_vec_binary(self.ctx.handle, op, a.handle, None, _enc(int(b) % P128), C.byref(h))
+        self.ctx.check(rc)
+        return Matrix(self.ctx, h)
+
+    def addVectorElements(self, a, b): return self._binary(0, a, b)
+    def subVectorElements(self, a, b): return self._binary(1, a, b)
+    def mulVectorElements(self, a, b): return self._binary(2, a, b)
+
+    # polynomials over roots of unity (K1) ------------------------------------------------------------
+    def interpolateRoots(self, domain, values: Matrix) -> Matrix:
+        """lib/Stark.ts:106 -- ``domain`` is implied by the length (power series of getRootOfUnity)."""
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_interpolate_roots(self.ctx.handle, values.handle, C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    def evalPolysAtRoots(self, polys: Matrix, domain) -> Matrix:
+        """lib/Stark.ts:109 -- ``domain`` may be the domain length (int) or an object with ``length``."""
+        n = domain if isinstance(domain, int) else domain.length
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_eval_polys_at_roots(self.ctx.handle, polys.handle, n.bit_length() - 1, C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    evalPolyAtRoots = evalPolysAtRoots

@@ -1,0 +1,84 @@
+/* libgenstark_b200.so -- C ABI of the B200 STARK proving hot path.
+ *
+ * Drop-in boundary for GuildOfWeavers/genSTARK.  genSTARK reaches all numeric work
+ * through two objects: the galois `FiniteField` it gets from air-assembly as `context.field`
+ * (lib/Stark.ts:37-43) and the merkle `Hash` (lib/Stark.ts:49-53).  A binding (N-API addon, see
+ * INTEGRATION.md) implements those two interfaces on top of the entry points below; `Vector` and
+ * `Matrix` become device-resident handles (gs_mat), and `gs_stark_prove` is the fused whole-prover
+ * crossing that replaces the body of Stark.prove (lib/Stark.ts:81-163).
+ *
+ * Conventions: every function returns 0 on success or a negative gs_status; the message is available
+ * from gs_last_error(ctx).  Field elements cross the boundary as canonical residues, 16 bytes,
+ * little-endian 32-bit limbs -- the bytes `Vector.toBuffer()` / `copyValue()` yield in the reference
+ * (lib/utils/serialization.ts:131-147).  Handles are owned by the caller and freed explicitly
+ * (the reference never frees: vectors live in the WASM arena, lib/Stark.ts:346-354).
+ * One CUDA stream per context; calls block until results needed on the host are there.
+ */
+#ifndef GENSTARK_B200_H
+#define GENSTARK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gs_ctx gs_ctx;     /* one device + stream + root tables              */
+typedef struct gs_mat gs_mat;     /* rows x cols field elements, row-major, in HBM  */
+
+enum gs_status {
+    GS_OK = 0,
+    GS_E_CUDA = -1,
+    GS_E_ARG = -2,
+    GS_E_UNSUPPORTED = -3,        /* e.g. a modulus other than 2^128 - 9*2^32 + 1: isOptimized=false */
+    GS_E_STARK = -4,              /* protocol failure; shim rethrows as StarkError (lib/StarkError.ts) */
+    GS_E_NOMEM = -5
+};
+
+/* ---- context -------------------------------------------------------------------------------- */
+int gs_ctx_create(int device, gs_ctx** out);
+void gs_ctx_destroy(gs_ctx* ctx);
+const char* gs_last_error(gs_ctx* ctx);
+int gs_ctx_sync(gs_ctx* ctx);
+/* number of kernels launched through this context so far */
+uint64_t gs_ctx_launch_count(gs_ctx* ctx);
+/* createPrimeField(modulus): 0 when the modulus has the native fast path (isOptimized) */
+int gs_field_supported(const uint8_t* modulus_le, size_t nbytes);
+/* field.getRootOfUnity(2^log2_order) -> 16 bytes (host) */
+int gs_field_root_of_unity(int log2_order, uint8_t out16[16]);
+/* field.add/sub/mul/div/exp on scalars (host): op 0 add, 1 sub, 2 mul, 3 div (inv(0)=0), 4 exp */
+int gs_field_scalar_op(int op, const uint8_t a16[16], const uint8_t b16[16], uint8_t out16[16]);
+
+/* ---- Vector / Matrix handles (galois newVectorFrom / newMatrixFrom / toBuffer) ---------------- */
+int gs_mat_alloc(gs_ctx* ctx, int64_t rows, int64_t cols, gs_mat** out);
+int gs_mat_from_bytes(gs_ctx* ctx, const void* le_bytes, int64_t rows, int64_t cols, gs_mat** out);
+int gs_mat_to_bytes(gs_ctx* ctx, const gs_mat* m, void* out_le_bytes);
+int gs_mat_shape(const gs_mat* m, int64_t* rows, int64_t* cols);
+void* gs_mat_device_ptr(gs_mat* m);
+void gs_mat_free(gs_mat* m);
+
+/* ---- polynomials over roots of unity (K1) ------------------------------------------------------
+ * gs_interpolate_roots : field.interpolateRoots(domain, values)   lib/Stark.ts:106,
+ *                        lib/components/CompositionPolynomial.ts:109.  values: rows x n, n = 2^k;
+ *                        the domain is the power series of getRootOfUnity(n).
+ * gs_eval_polys_at_roots: field.evalPolysAtRoots / evalPolyAtRoots  lib/Stark.ts:109,
+ *                        CompositionPolynomial.ts:110.  polys: rows x t, zero-padded to the domain of
+ *                        size 2^log2_domain >= t, natural-order output. */
+int gs_interpolate_roots(gs_ctx* ctx, const gs_mat* values, gs_mat** polys);
+int gs_eval_polys_at_roots(gs_ctx* ctx, const gs_mat* polys, int log2_domain, gs_mat** evals);
+
+/* ---- element-wise vector operations (K2) --------------------------------------------------------
+ * field.addVectorElements / subVectorElements / mulVectorElements (a, b) with b a vector of the same
+ * shape or a scalar (pass b = NULL and scalar16): op 0 add, 1 sub, 2 mul.
+ * Call sites: CompositionPolynomial.ts:98,120,136,145; LinearCombination.ts:50,63; ZeroPolynomial.ts:41-42 */
+int gs_vec_binary(gs_ctx* ctx, int op, const gs_mat* a, const gs_mat* b, const uint8_t* scalar16, gs_mat** out);
+
+/* ---- measurement helpers ------------------------------------------------------------------------ */
+/* runs blocks x 256 threads x (4*iters) dependent modular multiplications; returns kernel ms */
+int gs_debug_modmul_probe(gs_ctx* ctx, int blocks, int iters, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
