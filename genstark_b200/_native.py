@@ -46,6 +46,12 @@ def lib() -> C.CDLL:
         'gs_interpolate_roots': (i32, [vp, vp, P(vp)]),
         'gs_eval_polys_at_roots': (i32, [vp, vp, i32, P(vp)]),
         'gs_vec_binary': (i32, [vp, i32, vp, vp, cp, P(vp)]),
+        'gs_stark_create': (i32, [vp, cp, C.c_size_t, i32, i32, i32, P(vp)]),
+        'gs_stark_destroy': (None, [vp]),
+        'gs_stark_prove': (i32, [vp, cp, i32, cp, cp, cp, C.c_size_t, P(P(C.c_uint8)), P(C.c_size_t)]),
+        'gs_stark_stage_times': (cp, [vp]),
+        'gs_stark_set_debug': (i32, [vp, i32]),
+        'gs_stark_read_intermediate': (i32, [vp, i32, vp, C.c_size_t]),
         'gs_debug_modmul_probe': (i32, [vp, i32, i32, P(C.c_float)]),
     }
     for name, (res, args) in sigs.items():

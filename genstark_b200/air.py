@@ -264,3 +264,26 @@ class AirModule:
         m = copy.copy(self)
         m.extension_factor = int(extension_factor)
         return m
+
+
+AIR_BLOB_MAGIC = 0x52494147      # 'GAIR'
+
+
+def pack_air(air: AirModule) -> bytes:
+    """Flatten an AirModule for gs_stark_create (include/genstark_b200.h)."""
+    log_t = air.trace_length.bit_length() - 1
+    log_e = air.extension_factor.bit_length() - 1
+    if (1 << log_t) != air.trace_length or (1 << log_e) != air.extension_factor:
+        raise ValueError('trace length and extension factor must be powers of two')
+    out = [struct.pack('<I', AIR_BLOB_MAGIC), int(air.modulus).to_bytes(16, 'little'),
+           struct.pack('<5I', air.trace_register_count, air.constraint_count, log_t, log_e, len(air.static_registers))]
+    for reg in air.static_registers:
+        if reg.kind == 'cycle':
+            out.append(struct.pack('<2I', 0, len(reg.values)))
+            out.extend(int(v).to_bytes(16, 'little') for v in reg.values)
+        else:
+            out.append(struct.pack('<2I', 1 if reg.secret else 2, 0))
+    out.append(struct.pack(f'<{air.constraint_count}I', *air.constraint_degrees))
+    out.append(air.transition.pack())
+    out.append(air.evaluation.pack())
+    return b''.join(out)

@@ -1,13 +1,16 @@
 // extern "C" surface of libgenstark_b200.so (declared in include/genstark_b200.h).
+#include <memory>
 #include "core.cuh"
 #include "ntt_host.cuh"
 #include "pointwise.cuh"
+#include "prover.cuh"
 #include "../../include/genstark_b200.h"
 
 using namespace gs;
 
 struct gs_ctx : public Ctx {};
 struct gs_mat : public Mat {};
+struct gs_stark : public Stark { std::vector<uint8_t> proof; std::string times_json; };
 
 static thread_local std::string g_null_error;
 
@@ -204,6 +207,151 @@ int gs_debug_modmul_probe(gs_ctx* c, int blocks, int iters, float* ms_out) {
     cudaEventElapsedTime(ms_out, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     c->launches += 2;
+    return GS_OK;
+}
+
+// ---- fused prover ------------------------------------------------------------------------------
+int gs_stark_create(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,
+                    gs_stark** out) {
+    if (!c || !air_blob || !out) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    *out = nullptr;
+    if (hash_alg != HASH_SHA256 && hash_alg != HASH_BLAKE2S) return c->fail(GS_E_ARG, "Hash algorithm %d is not supported", hash_alg);
+    if (exe_queries < 1 || exe_queries > 128) return c->fail(GS_E_ARG, "Execution sample size must be an integer between 1 and 128");
+    if (fri_queries < 1 || fri_queries > 64) return c->fail(GS_E_ARG, "FRI sample size must be an integer between 1 and 64");
+    cudaSetDevice(c->device);
+    BlobReader r{air_blob, blob_len};
+    if (r.u32() != 0x52494147u) return c->fail(GS_E_ARG, "bad AIR blob magic");
+    std::unique_ptr<gs_stark> S(new gs_stark());
+    S->ctx = c; S->hash_alg = hash_alg; S->exe_queries = exe_queries; S->fri_queries = fri_queries;
+    uint8_t modulus[16];
+    for (int i = 0; i < 4; ++i) { uint32_t w = r.u32(); memcpy(modulus + 4 * i, &w, 4); }
+    if (gs_field_supported(modulus, 16) != GS_OK) return c->fail(GS_E_UNSUPPORTED, "no native backend for this modulus (isOptimized = false)");
+    S->R = (int)r.u32(); S->K = (int)r.u32(); S->log_t = (int)r.u32(); S->log_e = (int)r.u32();
+    const uint32_t n_static = r.u32();
+    if (!r.ok || S->R < 1 || S->R > GS_MAX_COLS || S->K < 1 || S->K > GS_MAX_CONSTRAINTS || n_static > GS_MAX_COLS)
+        return c->fail(GS_E_UNSUPPORTED, "AIR shape out of range (registers %d, constraints %d, static %u)", S->R, S->K, n_static);
+    if (S->log_t < 2 || S->log_e < 1 || S->log_e > 5) return c->fail(GS_E_ARG, "trace length >= 4 and extension factor 2..32 required");
+    S->statics.resize(n_static);
+    for (auto& sr : S->statics) {
+        sr.kind = (int)r.u32();
+        const uint32_t len = r.u32();
+        if (!r.ok || len > (1u << 24)) return c->fail(GS_E_ARG, "bad static register");
+        sr.values.resize(len);
+        for (auto& v : sr.values) v = r.elem();
+        if (sr.kind == 0 && (len == 0 || (len & (len - 1)) || len > (1u << S->log_t))) return c->fail(GS_E_ARG, "cycle length must be a power of two <= steps");
+        if (sr.kind == 1) S->n_secret++;
+        if (sr.kind == 2) S->n_public++;
+    }
+    S->degrees.resize(S->K);
+    for (auto& d : S->degrees) d = (int)r.u32();
+    if (!read_program(r, S->transition) || !read_program(r, S->evaluation)) return c->fail(GS_E_ARG, "bad AIR program");
+    if (S->transition.n_out != S->R || S->evaluation.n_out != S->K) return c->fail(GS_E_ARG, "program outputs do not match the register / constraint counts");
+    for (auto& ins : S->evaluation.instrs) if (ins[0] == OP_EXP) return c->fail(GS_E_UNSUPPORTED, "exp with a large exponent in a constraint");
+    // device copies of the evaluation program
+    int rc;
+    const size_t ib = S->evaluation.instrs.size() * 16, cb = std::max<size_t>(S->evaluation.consts.size(), 1) * 16;
+    if ((rc = S->d_instrs.ensure(c, ib))) return rc;
+    if ((rc = S->d_consts.ensure(c, cb))) return rc;
+    std::vector<fp> cs(std::max<size_t>(S->evaluation.consts.size(), 1), fp_zero());
+    for (size_t i = 0; i < S->evaluation.consts.size(); ++i) cs[i] = fp_from_u128(S->evaluation.consts[i]);
+    GS_CUDA(c, cudaMemcpy(S->d_instrs.p, S->evaluation.instrs.data(), ib, cudaMemcpyHostToDevice));
+    GS_CUDA(c, cudaMemcpy(S->d_consts.p, cs.data(), cb, cudaMemcpyHostToDevice));
+    // cyclic registers: k~ over the subgroup of order len, evaluated on the subgroup of order E*len
+    S->cyc_off.assign(n_static, 0); S->cyc_mask.assign(n_static, 0);
+    size_t total = 0;
+    for (size_t k = 0; k < n_static; ++k) if (S->statics[k].kind == 0) { S->cyc_off[k] = total; total += S->statics[k].values.size() << S->log_e; }
+    if ((rc = S->d_cyc.ensure(c, std::max<size_t>(total, 1) * sizeof(fp)))) return rc;
+    for (size_t k = 0; k < n_static; ++k) {
+        const StaticReg& sr = S->statics[k];
+        if (sr.kind != 0) continue;
+        const size_t L = sr.values.size(), EL = L << S->log_e;
+        S->cyc_mask[k] = (unsigned)(EL - 1);
+        int log_l = 0; while ((1u << log_l) < L) ++log_l;
+        std::vector<fp> table(EL);
+        if (log_l < 2) {
+            // tiny cycles on the host: evaluate the interpolant of (g_L^s, v_s) at g_EL^i
+            std::vector<u128> xs(L), ys(sr.values);
+            const u128 gl = c->root_of_order(log_l), gel = c->root_of_order(log_l + S->log_e);
+            u128 a = 1; for (size_t s2 = 0; s2 < L; ++s2) { xs[s2] = a; a = h_mul(a, gl); }
+            const std::vector<u128> poly = h_interpolate(xs, ys);
+            a = 1; for (size_t i = 0; i < EL; ++i) { table[i] = fp_from_u128(h_eval_poly(poly, a)); a = h_mul(a, gel); }
+            GS_CUDA(c, cudaMemcpy(S->d_cyc.as<fp>() + S->cyc_off[k], table.data(), EL * sizeof(fp), cudaMemcpyHostToDevice));
+        } else {
+            std::vector<fp> vals(L); for (size_t i = 0; i < L; ++i) vals[i] = fp_from_u128(sr.values[i]);
+            DevBuf tmp_v, tmp_p, tmp_w;
+            if ((rc = tmp_v.ensure(c, L * sizeof(fp))) || (rc = tmp_p.ensure(c, L * sizeof(fp))) || (rc = tmp_w.ensure(c, EL * sizeof(fp)))) return rc;
+            GS_CUDA(c, cudaMemcpy(tmp_v.p, vals.data(), L * sizeof(fp), cudaMemcpyHostToDevice));
+            rc = ntt_run(c, tmp_v.as<fp>(), L, tmp_p.as<fp>(), L, tmp_w.as<fp>(), L, 1, log_l, 0, true);
+            if (rc == GS_OK) rc = ntt_run(c, tmp_p.as<fp>(), L, S->d_cyc.as<fp>() + S->cyc_off[k], EL, tmp_w.as<fp>(), EL, 1, log_l, S->log_e, false);
+            cudaStreamSynchronize(c->stream);
+            tmp_v.release(); tmp_p.release(); tmp_w.release();
+            if (rc != GS_OK) return rc;
+        }
+    }
+    *out = S.release();
+    return GS_OK;
+}
+
+void gs_stark_destroy(gs_stark* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    delete s;
+}
+
+int gs_stark_set_debug(gs_stark* s, int keep_intermediates) {
+    if (!s) return GS_E_ARG;
+    s->keep_intermediates = keep_intermediates != 0;
+    return GS_OK;
+}
+
+int gs_stark_prove(gs_stark* s, const uint8_t* assertions, int n_assertions, const uint8_t* init_state16,
+                   const uint8_t* input_traces, const uint8_t* shapes_blob, size_t shapes_len,
+                   const uint8_t** proof_out, size_t* proof_len) {
+    if (!s || !assertions || !init_state16 || !proof_out || !proof_len) return s ? s->ctx->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    Ctx* c = s->ctx;
+    if ((s->n_secret + s->n_public) > 0 && !input_traces) return c->fail(GS_E_ARG, "input register traces required");
+    std::vector<Assertion> as(n_assertions > 0 ? n_assertions : 0);
+    for (int i = 0; i < n_assertions; ++i) {
+        const uint8_t* p = assertions + 24 * (size_t)i;
+        memcpy(&as[i].reg, p, 4); memcpy(&as[i].step, p + 4, 4);
+        fp v; memcpy(&v, p + 8, 16); as[i].value = fp_to_u128(v);
+    }
+    std::vector<u128> init(s->R);
+    for (int r = 0; r < s->R; ++r) { fp v; memcpy(&v, init_state16 + 16 * r, 16); init[r] = fp_to_u128(v); if (init[r] >= HP) return c->fail(GS_E_ARG, "non-canonical initial state"); }
+    int rc = stark_prove(s, as.data(), n_assertions, init.data(), (const fp*)input_traces, shapes_blob, shapes_len, s->proof);
+    if (rc != GS_OK) return rc;
+    *proof_out = s->proof.data(); *proof_len = s->proof.size();
+    return GS_OK;
+}
+
+const char* gs_stark_stage_times(gs_stark* s) {
+    if (!s) return "";
+    std::string j = "[";
+    for (size_t i = 0; i < s->last_times.items.size(); ++i) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s[\"%s\", %.4f]", i ? ", " : "", s->last_times.items[i].first.c_str(), s->last_times.items[i].second);
+        j += buf;
+    }
+    s->times_json = j + "]";
+    return s->times_json.c_str();
+}
+
+/* which: 0 = P(x) evaluations (R x N), 1 = C(x) (N), 2 = L(x) (N), 3 = trace polynomials (R x T) */
+int gs_stark_read_intermediate(gs_stark* s, int which, void* out, size_t out_bytes) {
+    if (!s || !out) return GS_E_ARG;
+    Ctx* c = s->ctx;
+    const size_t N = (size_t)1 << (s->log_t + s->log_e), T = (size_t)1 << s->log_t;
+    const void* src = nullptr; size_t bytes = 0;
+    switch (which) {
+        case 0: src = s->d_pe.p; bytes = (size_t)s->R * N * 16; break;
+        case 1: src = s->d_c.p; bytes = N * 16; break;
+        case 2: src = s->d_l.p; bytes = N * 16; break;
+        case 3: src = s->d_poly.p; bytes = (size_t)s->R * T * 16; break;
+        default: return c->fail(GS_E_ARG, "unknown intermediate");
+    }
+    if (!src || out_bytes < bytes) return c->fail(GS_E_ARG, "intermediate not available (enable gs_stark_set_debug) or buffer too small");
+    GS_CUDA(c, cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
     return GS_OK;
 }
 

@@ -1,0 +1,55 @@
+// K3: batched modular inversion with the reference's inv(0) = 0 convention.
+//
+// Replaces galois divVectorElements / divMatrixElements (lib/components/CompositionPolynomial.ts:117,
+// BoundaryConstraints.ts:92).  Montgomery's trick per thread over a strided chunk of CH elements:
+// prefix products go to a scratch vector (coalesced), one Fermat inversion (~190 modmuls) per thread,
+// then a backward sweep.  Zeros are skipped in the running product so they invert to zero
+// (the zeros of Z(x) and Z_b(x) flow into the FRI commitment).
+// Cost per element: 3 modmuls + 190/CH, 80 B of HBM traffic.
+#pragma once
+#include "core.cuh"
+#include "ntt.cuh"
+
+namespace gs {
+
+#define GS_BINV_CH 64
+
+// in/out/scratch: n elements.  thread t owns elements t, t+T, t+2T, ... (T = total threads), CH of them.
+__global__ void __launch_bounds__(256) batch_inverse_kernel(const fp* __restrict__ in, fp* __restrict__ out,
+                                                            fp* __restrict__ scratch, long long n, long long nthreads) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    fp acc = fp_one();
+    long long i = t;
+    int cnt = 0;
+    for (; i < n; i += nthreads, ++cnt) {
+        st_fp(scratch + i, acc);               // product of the non-zero elements before i
+        fp x = ld_fp(in + i);
+        if (!fp_is_zero(x)) acc = fp_mul(acc, x);
+    }
+    fp inv = fp_inv(acc);
+    for (i -= nthreads; i >= 0 && cnt > 0; i -= nthreads, --cnt) {
+        fp x = ld_fp(in + i);
+        fp r = fp_zero();
+        if (!fp_is_zero(x)) {
+            r = fp_mul(inv, ld_fp(scratch + i));
+            inv = fp_mul(inv, x);
+        }
+        st_fp(out + i, r);
+    }
+}
+
+// out may alias in only if scratch is distinct from both
+static inline int batch_inverse(Ctx* c, const fp* in, fp* out, fp* scratch, long long n) {
+    long long nthreads = (n + GS_BINV_CH - 1) / GS_BINV_CH;
+    const long long min_threads = (long long)c->sm_count * 256;
+    if (nthreads < min_threads) nthreads = n < min_threads ? n : min_threads;
+    const unsigned blocks = (unsigned)((nthreads + 255) / 256);
+    batch_inverse_kernel<<<blocks, 256, 0, c->stream>>>(in, out, scratch, n, nthreads);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return c->cuda_fail(e, "batch_inverse_kernel");
+    c->launches++;
+    return GS_OK;
+}
+
+}  // namespace gs

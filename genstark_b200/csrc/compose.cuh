@@ -1,0 +1,163 @@
+// K2: constraint evaluation + composition polynomial C(x) + random linear combination L(x), fused.
+//
+// Reference data flow (lib/components/CompositionPolynomial.ts:71-146, LinearCombination.ts:36-64):
+//   Q = constraints over the composition domain (M points) -> degree adjust -> sum d_i Q_i
+//     -> iNTT(M) -> NTT(N) -> * Z^-1 -> + boundary part -> C ;  L = C + sum kappa_j V_j (+ x^D copies)
+// Every term of the combined constraint polynomial has degree < M (term i: d_i (T-1) + (M - d_i T)),
+// so interpolating it on M points and evaluating on N points returns exactly its values on the N
+// points; those values are obtained here by evaluating the constraints directly at the evaluation
+// points (next state = position i + E, same coset).  Exact arithmetic => identical field elements; the
+// oracle keeps the literal detour and tests/ compare the two.
+//
+// One thread per evaluation point, 16-byte coalesced loads of the trace / secret columns; the AIR
+// evaluation function is a flat register-machine program (genstark_b200/air.py) interpreted with the
+// instruction stream read uniformly by the whole warp.
+#pragma once
+#include "core.cuh"
+#include "ntt.cuh"
+
+namespace gs {
+
+enum { OP_CONST = 0, OP_CUR = 1, OP_NEXT = 2, OP_STATIC = 3, OP_ADD = 4, OP_SUB = 5, OP_MUL = 6, OP_NEG = 7,
+       OP_INV = 8, OP_EXP = 9, OP_OUT = 10 };
+
+#define GS_MAX_COLS 64          // trace + static registers visible to a program
+#define GS_MAX_CONSTRAINTS 64
+#define GS_MAX_POWERS 8
+
+struct ComposeParams {
+    long long n;                 // evaluation domain size N
+    int log_n, log_e;            // N = 2^log_n, E = 2^log_e
+    // program
+    const uint4* instrs; int n_instr; const fp* consts; int n_slots;
+    // trace columns (LDE over N)
+    int n_trace; const fp* trace[GS_MAX_COLS];
+    // static registers: kind 0 = cyclic table (index i & mask), kind 1 = full column over N
+    int n_static; const fp* stat[GS_MAX_COLS]; unsigned stat_mask[GS_MAX_COLS];
+    // transition part: q_k * (dk[k] + dk_adj[k] * x^incr[pow_idx[k]])
+    int n_constraints;
+    const fp* dk; const fp* dk_adj; const int* pow_idx;      // device arrays [K]
+    int n_powers; unsigned long long pow_incr[GS_MAX_POWERS]; // x^incr, incr < N
+    // zero polynomial: D = qc * (x - x_last) * inv_num[i mod E]
+    fp x_last; const fp* inv_num;
+    // boundary part: for asserted register slot b: (P_reg - I(x)) * zb_inv[b][i] * (bk[b] + bk_adj[b] * x^delta)
+    int n_boundary; const int* b_reg; const int* b_ipoly_off; const int* b_ipoly_len; const fp* b_ipoly;
+    const fp* zb_inv;            // [n_boundary x N]
+    const fp* bk; const fp* bk_adj;
+    // linear combination: columns V = trace then secret; L = C + sum V_j (lk[j] + lk_adj[j] * x^delta)
+    int n_lc; const fp* lc_col[GS_MAX_COLS]; const fp* lk; const fp* lk_adj;
+    unsigned long long delta;    // compositionDegree - T (0 => no adjusted copies)
+    // roots
+    const fp* tw_lo; const fp* tw_hi; int log_g, log_lo;
+    fp* out;                     // L(x) over N
+    fp* c_out;                   // optional: C(x) over N (stage-level parity tests); may be null
+    int* fail_flag;              // [0] = 1 + constraint index, [1] = step, when a constraint is non-zero on a trace step
+};
+
+GS_D fp root_pow(const ComposeParams& P, unsigned long long e_n) {
+    // w_N^e for e < N, from the w_G tables
+    const unsigned e = (unsigned)(e_n << (P.log_g - P.log_n));
+    fp lo = ldg_fp(P.tw_lo + (e & ((1u << P.log_lo) - 1u)));
+    if (P.log_g <= P.log_lo) return lo;
+    return fp_mul(lo, ldg_fp(P.tw_hi + (e >> P.log_lo)));
+}
+
+template <int NSLOT>
+__global__ void __launch_bounds__(256) compose_kernel(const ComposeParams* __restrict__ Pp) {
+    const ComposeParams& P = *Pp;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const unsigned long long nmask = (unsigned long long)P.n - 1ull;
+    const unsigned E = 1u << P.log_e;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+        const long long inext = (i + E) & (long long)nmask;
+        fp slot[NSLOT];
+        // powers of x used by this point
+        const fp x = root_pow(P, (unsigned long long)i);
+        fp xpow[GS_MAX_POWERS];
+#pragma unroll 1
+        for (int g = 0; g < P.n_powers; ++g) xpow[g] = root_pow(P, ((unsigned long long)i * P.pow_incr[g]) & nmask);
+        fp xdelta = fp_one();
+        if (P.delta) xdelta = root_pow(P, ((unsigned long long)i * P.delta) & nmask);
+
+        // ---- transition constraints, combined on the fly
+        fp acc = fp_zero();
+#pragma unroll 1
+        for (int pc = 0; pc < P.n_instr; ++pc) {
+            const uint4 ins = __ldg(P.instrs + pc);
+            const unsigned op = ins.x, d = ins.y, a = ins.z, b = ins.w;
+            switch (op) {
+                case OP_CONST: slot[d] = ldg_fp(P.consts + a); break;
+                case OP_CUR: slot[d] = ld_fp(P.trace[a] + i); break;
+                case OP_NEXT: slot[d] = ld_fp(P.trace[a] + inext); break;
+                case OP_STATIC: slot[d] = ld_fp(P.stat[a] + ((unsigned long long)i & P.stat_mask[a])); break;
+                case OP_ADD: slot[d] = fp_add(slot[a], slot[b]); break;
+                case OP_SUB: slot[d] = fp_sub(slot[a], slot[b]); break;
+                case OP_MUL: slot[d] = fp_mul(slot[a], slot[b]); break;
+                case OP_NEG: slot[d] = fp_neg(slot[a]); break;
+                case OP_INV: slot[d] = fp_inv(slot[a]); break;
+                case OP_OUT: {
+                    const fp qv = slot[a];
+                    // the reference (air-assembly) refuses a trace that violates a constraint: positions that
+                    // are trace steps (i % E == 0) other than the last step must evaluate to zero
+                    if (((unsigned)i & (E - 1)) == 0 && i < P.n - E && !fp_is_zero(qv)) {
+                        if (atomicCAS(P.fail_flag, 0, 1 + (int)d) == 0) P.fail_flag[1] = (int)(i >> P.log_e);
+                    }
+                    fp coef = ldg_fp(P.dk + d);
+                    const int pi = __ldg(P.pow_idx + d);
+                    if (pi >= 0) coef = fp_add(coef, fp_mul(ldg_fp(P.dk_adj + d), xpow[pi]));
+                    acc = fp_add(acc, fp_mul(qv, coef));
+                    break;
+                }
+                default: break;
+            }
+        }
+        // ---- D(x) = Q(x) / Z(x) = Q * (x - x_last) * inv(x^T - 1)
+        fp c = fp_mul(fp_mul(acc, fp_sub(x, P.x_last)), ldg_fp(P.inv_num + ((unsigned)i & (E - 1))));
+        // ---- boundary constraints
+#pragma unroll 1
+        for (int bi = 0; bi < P.n_boundary; ++bi) {
+            const int off = P.b_ipoly_off[bi], len = P.b_ipoly_len[bi];
+            fp iv = ldg_fp(P.b_ipoly + off + len - 1);
+            for (int k = len - 2; k >= 0; --k) iv = fp_add(fp_mul(iv, x), ldg_fp(P.b_ipoly + off + k));
+            const fp pv = ld_fp(P.trace[P.b_reg[bi]] + i);
+            const fp bv = fp_mul(fp_sub(pv, iv), ld_fp(P.zb_inv + (long long)bi * P.n + i));
+            fp coef = ldg_fp(P.bk + bi);
+            if (P.delta) coef = fp_add(coef, fp_mul(ldg_fp(P.bk_adj + bi), xdelta));
+            c = fp_add(c, fp_mul(bv, coef));
+        }
+        if (P.c_out) st_fp(P.c_out + i, c);
+        // ---- linear combination with P(x) and S(x)
+        fp l = c;
+#pragma unroll 1
+        for (int j = 0; j < P.n_lc; ++j) {
+            fp coef = ldg_fp(P.lk + j);
+            if (P.delta) coef = fp_add(coef, fp_mul(ldg_fp(P.lk_adj + j), xdelta));
+            l = fp_add(l, fp_mul(ld_fp(P.lc_col[j] + i), coef));
+        }
+        st_fp(P.out + i, l);
+    }
+}
+
+// Z_b(x_i) for every boundary slot: zb[bi][i] = prod_k (x_i - X_k) given as a monic polynomial
+struct ZbParams {
+    long long n; int log_n;
+    int n_boundary; const int* zpoly_off; const int* zpoly_len; const fp* zpoly;
+    const fp* tw_lo; const fp* tw_hi; int log_g, log_lo;
+    fp* out;
+};
+__global__ void __launch_bounds__(256) zb_eval_kernel(const ZbParams P) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+        const unsigned e = (unsigned)((unsigned long long)i << (P.log_g - P.log_n));
+        fp x = ldg_fp(P.tw_lo + (e & ((1u << P.log_lo) - 1u)));
+        if (P.log_g > P.log_lo) x = fp_mul(x, ldg_fp(P.tw_hi + (e >> P.log_lo)));
+        for (int bi = 0; bi < P.n_boundary; ++bi) {
+            const int off = P.zpoly_off[bi], len = P.zpoly_len[bi];
+            fp z = ldg_fp(P.zpoly + off + len - 1);
+            for (int k = len - 2; k >= 0; --k) z = fp_add(fp_mul(z, x), ldg_fp(P.zpoly + off + k));
+            st_fp(P.out + (long long)bi * P.n + i, z);
+        }
+    }
+}
+
+}  // namespace gs

@@ -1,0 +1,73 @@
+// K4: FRI layer fold, and K6: row gathers for the query phase.
+//
+// Replaces, per layer, transposeVector(domain,4,4^d) + interpolateQuarticBatch + evalQuarticBatch
+// (lib/components/LowDegreeProver.ts:190-195).  Row i of a layer vector v of length L is
+// (v[i], v[i+L/4], v[i+2L/4], v[i+3L/4]) at x-coordinates x_i * iota^j, x_i = w^(i*4^d), iota = w^(N/4)
+// (LowDegreeProver.ts:270-282).  The cubic through those four points evaluated at the challenge x* is
+//      column[i] = 1/4 * sum_k c_k t^k,   c_k = sum_j y_j iota^(-jk),   t = x* / x_i
+// i.e. a radix-4 inverse butterfly followed by Horner -- 7 modmuls per output and no
+// inversions, against a generic Lagrange interpolation in the reference.  Exact field arithmetic, so
+// the values are identical.
+#pragma once
+#include "core.cuh"
+#include "ntt.cuh"
+
+namespace gs {
+
+struct FriFoldParams {
+    const fp* v;          // layer vector, length L
+    fp* out;              // next layer, length L/4
+    long long quarter;    // L/4
+    const fp* special_x;  // device pointer to the challenge (so the host need not sync to launch)
+    const fp* tw_lo; const fp* tw_hi; int log_g, log_lo;
+    int x_shift;          // exponent of x_i in units of w_G:  e = i << x_shift  (= 4^d * G/N)
+    fp iota_inv;          // w^(-N/4)
+    fp quarter_inv;       // 4^-1
+};
+
+__global__ void __launch_bounds__(256) fri_fold_kernel(const FriFoldParams P) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const fp xs = ldg_fp(P.special_x);
+    const unsigned g_mask = (1u << P.log_g) - 1u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.quarter; i += stride) {
+        const fp y0 = ld_fp(P.v + i), y1 = ld_fp(P.v + i + P.quarter);
+        const fp y2 = ld_fp(P.v + i + 2 * P.quarter), y3 = ld_fp(P.v + i + 3 * P.quarter);
+        // t = x* * x_i^-1,  x_i^-1 = w_G^(G - e)
+        const unsigned e = (0u - ((unsigned)i << P.x_shift)) & g_mask;
+        fp xinv = ldg_fp(P.tw_lo + (e & ((1u << P.log_lo) - 1u)));
+        if (P.log_g > P.log_lo) xinv = fp_mul(xinv, ldg_fp(P.tw_hi + (e >> P.log_lo)));
+        const fp t = fp_mul(xs, xinv);
+        // inverse radix-4 butterfly
+        const fp s02 = fp_add(y0, y2), d02 = fp_sub(y0, y2);
+        const fp s13 = fp_add(y1, y3), d13 = fp_mul(fp_sub(y1, y3), P.iota_inv);
+        const fp c0 = fp_add(s02, s13), c2 = fp_sub(s02, s13);
+        const fp c1 = fp_add(d02, d13), c3 = fp_sub(d02, d13);
+        // Horner in t
+        fp acc = fp_add(fp_mul(c3, t), c2);
+        acc = fp_add(fp_mul(acc, t), c1);
+        acc = fp_add(fp_mul(acc, t), c0);
+        st_fp(P.out + i, fp_mul(acc, P.quarter_inv));
+    }
+}
+
+// ---- K6 ------------------------------------------------------------------------------------------
+// out[q][c] = col[c][idx[q]]  (merged leaf values, lib/Stark.ts:284-296; rowsToBuffers of a 4-column matrix)
+struct GatherCols {
+    const fp* col[64];
+    int ncols;
+};
+__global__ void gather_rows_kernel(const GatherCols cols, const unsigned* __restrict__ idx, int nq, fp* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = t / cols.ncols, cidx = t % cols.ncols;
+    if (q < nq) st_fp(out + (long long)q * cols.ncols + cidx, ld_fp(cols.col[cidx] + idx[q]));
+}
+
+// out[q] = nodes[idx[q]] (32-byte digests)
+__global__ void gather_digests_kernel(const uint32_t* __restrict__ nodes, const unsigned* __restrict__ idx, int nq,
+                                      uint32_t* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = t >> 1, half = t & 1;
+    if (q < nq) reinterpret_cast<uint4*>(out)[2 * q + half] = reinterpret_cast<const uint4*>(nodes)[2ll * idx[q] + half];
+}
+
+}  // namespace gs

@@ -1,0 +1,284 @@
+// K5: blake2s-256 / sha-256 leaf and row hashing and Merkle tree construction.
+//
+// Replaces merkle's hash.mergeVectorRows (lib/Stark.ts:115), hash.digestValues
+// (lib/components/LowDegreeProver.ts:45,163,201) and MerkleTree.create (lib/Stark.ts:118,
+// LowDegreeProver.ts:46,164,202).  Digests are the standard unkeyed 32-byte outputs.
+//
+// Layout: a leaf is the concatenation of element i of `ncols` column vectors (16 bytes each, the
+// canonical little-endian residue), so thread i reads column[c][i] -- coalesced across the warp.  A
+// 4-column FRI row (v[i], v[i+L/4], v[i+2L/4], v[i+3L/4]) is the same thing with the four quarters
+// of v as columns, so no transposed copy is ever materialised.
+// Tree: nodes[1] = root, nodes[i] = H(nodes[2i] || nodes[2i+1]), leaves at nodes[n..2n).
+#pragma once
+#include "core.cuh"
+#include "ntt.cuh"
+
+namespace gs {
+
+enum { HASH_SHA256 = 0, HASH_BLAKE2S = 1 };
+#define GS_MAX_HASH_COLS 64
+
+struct HashCols {
+    const fp* col[GS_MAX_HASH_COLS];
+    int ncols;
+};
+
+// ------------------------------------------------------------------------------------------ blake2s
+GS_D uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
+
+#define B2S_IV0 0x6A09E667u
+#define B2S_IV1 0xBB67AE85u
+#define B2S_IV2 0x3C6EF372u
+#define B2S_IV3 0xA54FF53Au
+#define B2S_IV4 0x510E527Fu
+#define B2S_IV5 0x9B05688Cu
+#define B2S_IV6 0x1F83D9ABu
+#define B2S_IV7 0x5BE0CD19u
+
+#define B2S_G(a, b, c, d, x, y)                    \
+    a = a + b + (x); d = __byte_perm(d ^ a, 0, 0x1032); \
+    c = c + d; b = rotr32(b ^ c, 12);              \
+    a = a + b + (y); d = __byte_perm(d ^ a, 0, 0x0321); \
+    c = c + d; b = rotr32(b ^ c, 7);
+
+// one compression; sigma is fully unrolled so message words stay in registers
+GS_D void blake2s_compress(uint32_t (&h)[8], const uint32_t (&m)[16], uint32_t t0, bool last) {
+    uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
+    uint32_t v8 = B2S_IV0, v9 = B2S_IV1, v10 = B2S_IV2, v11 = B2S_IV3;
+    uint32_t v12 = B2S_IV4 ^ t0, v13 = B2S_IV5, v14 = last ? ~B2S_IV6 : B2S_IV6, v15 = B2S_IV7;
+#define B2S_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
+    B2S_G(v0, v4, v8, v12, m[s0], m[s1]) B2S_G(v1, v5, v9, v13, m[s2], m[s3])             \
+    B2S_G(v2, v6, v10, v14, m[s4], m[s5]) B2S_G(v3, v7, v11, v15, m[s6], m[s7])           \
+    B2S_G(v0, v5, v10, v15, m[s8], m[s9]) B2S_G(v1, v6, v11, v12, m[s10], m[s11])         \
+    B2S_G(v2, v7, v8, v13, m[s12], m[s13]) B2S_G(v3, v4, v9, v14, m[s14], m[s15])
+    B2S_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+    B2S_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3)
+    B2S_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4)
+    B2S_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8)
+    B2S_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13)
+    B2S_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9)
+    B2S_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11)
+    B2S_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10)
+    B2S_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5)
+    B2S_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0)
+#undef B2S_ROUND
+    h[0] ^= v0 ^ v8; h[1] ^= v1 ^ v9; h[2] ^= v2 ^ v10; h[3] ^= v3 ^ v11;
+    h[4] ^= v4 ^ v12; h[5] ^= v5 ^ v13; h[6] ^= v6 ^ v14; h[7] ^= v7 ^ v15;
+}
+
+GS_D void blake2s_init(uint32_t (&h)[8]) {
+    h[0] = B2S_IV0 ^ 0x01010020u; h[1] = B2S_IV1; h[2] = B2S_IV2; h[3] = B2S_IV3;
+    h[4] = B2S_IV4; h[5] = B2S_IV5; h[6] = B2S_IV6; h[7] = B2S_IV7;
+}
+
+// ------------------------------------------------------------------------------------------- sha256
+__device__ __constant__ uint32_t SHA256_K[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01,
+    0x243185be, 0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc,
+    0x2de92c6f, 0x4a7484aa, 0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147,
+    0x06ca6351, 0x14292967, 0x27b70a85, 0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85,
+    0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3, 0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08,
+    0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f, 0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208,
+    0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+
+GS_D void sha256_init(uint32_t (&h)[8]) {
+    h[0] = 0x6a09e667; h[1] = 0xbb67ae85; h[2] = 0x3c6ef372; h[3] = 0xa54ff53a;
+    h[4] = 0x510e527f; h[5] = 0x9b05688c; h[6] = 0x1f83d9ab; h[7] = 0x5be0cd19;
+}
+
+// w: 16 big-endian message words (clobbered)
+GS_D void sha256_compress(uint32_t (&h)[8], uint32_t (&w)[16]) {
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+        if (i >= 16) {
+            const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+            const uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+            const uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+            w[i & 15] = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+        }
+        const uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+        const uint32_t ch = (e & f) ^ (~e & g);
+        const uint32_t t1 = hh + S1 + ch + SHA256_K[i] + w[i & 15];
+        const uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+        const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        const uint32_t t2 = S0 + mj;
+        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+GS_D uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// ------------------------------------------------------------------------------ message -> digest
+// Hash a message given as `nwords` little-endian 32-bit words produced by `get(w)` (nwords % 4 == 0).
+template <int ALG, typename Get>
+GS_D void hash_words(Get get, int nwords, uint32_t (&out)[8]) {
+    uint32_t h[8];
+    if (ALG == HASH_BLAKE2S) {
+        blake2s_init(h);
+        const int nblocks = (nwords + 15) / 16;
+        for (int b = 0; b < nblocks; ++b) {
+            uint32_t m[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { const int w = b * 16 + i; m[i] = (w < nwords) ? get(w) : 0u; }
+            const bool last = (b == nblocks - 1);
+            blake2s_compress(h, m, last ? (uint32_t)nwords * 4u : (uint32_t)(b + 1) * 64u, last);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = h[i];
+    } else {
+        sha256_init(h);
+        const int nbytes = nwords * 4;
+        const int nblocks = (nbytes + 9 + 63) / 64;
+        for (int b = 0; b < nblocks; ++b) {
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int k = b * 16 + i;
+                uint32_t v = 0;
+                if (k < nwords) v = bswap32(get(k));
+                else if (k == nwords) v = 0x80000000u;
+                if (b == nblocks - 1 && i == 15) v = (uint32_t)nbytes * 8u;
+                w[i] = v;
+            }
+            sha256_compress(h, w);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = bswap32(h[i]);
+    }
+}
+
+GS_D void store_digest(uint32_t* dst, const uint32_t (&d)[8]) {
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(d[0], d[1], d[2], d[3]);
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(d[4], d[5], d[6], d[7]);
+}
+
+// leaf i = H(col[0][i] || col[1][i] || ...)   ->  out[i] (32 bytes)
+template <int ALG>
+__global__ void __launch_bounds__(256) hash_columns_kernel(const HashCols cols, long long n, uint32_t* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t d[8];
+        auto get = [&](int w) -> uint32_t { return cols.col[w >> 2][i].v[w & 3]; };
+        if (cols.ncols <= 4) {
+            // common case (MiMC leaves, every FRI row): one block, words straight from registers
+            uint32_t m[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                fp e = (c < cols.ncols) ? ld_fp(cols.col[c] + i) : fp_zero();
+                m[4 * c] = e.v[0]; m[4 * c + 1] = e.v[1]; m[4 * c + 2] = e.v[2]; m[4 * c + 3] = e.v[3];
+            }
+            auto getm = [&](int w) -> uint32_t { return m[w]; };
+            hash_words<ALG>(getm, cols.ncols * 4, d);
+        } else {
+            hash_words<ALG>(get, cols.ncols * 4, d);
+        }
+        store_digest(out + 8 * i, d);
+    }
+}
+
+// generic digestValues over a raw byte buffer: row r = bytes [r*row_bytes, (r+1)*row_bytes), row_bytes % 16 == 0
+template <int ALG>
+__global__ void __launch_bounds__(256) hash_rows_kernel(const uint32_t* __restrict__ buf, int row_words, long long n,
+                                                        uint32_t* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t* row = buf + i * row_words;
+        uint32_t d[8];
+        auto get = [&](int w) -> uint32_t { return row[w]; };
+        hash_words<ALG>(get, row_words, d);
+        store_digest(out + 8 * i, d);
+    }
+}
+
+// parents [count, 2*count) <- H(children)
+template <int ALG>
+__global__ void __launch_bounds__(256) merkle_level_kernel(uint32_t* __restrict__ nodes, long long count) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+        const long long i = count + j;
+        const uint4* ch = reinterpret_cast<const uint4*>(nodes + 16 * i);     // nodes[2i], nodes[2i+1]
+        uint32_t m[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { uint4 t = ch[q]; m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
+        uint32_t d[8];
+        auto getm = [&](int w) -> uint32_t { return m[w]; };
+        hash_words<ALG>(getm, 16, d);
+        store_digest(nodes + 8 * i, d);
+    }
+}
+
+// all levels from `count` parents down to the root inside one block
+template <int ALG>
+__global__ void __launch_bounds__(1024) merkle_tail_kernel(uint32_t* __restrict__ nodes, int count) {
+    for (int c = count; c >= 1; c >>= 1) {
+        for (int j = threadIdx.x; j < c; j += blockDim.x) {
+            const int i = c + j;
+            const uint4* ch = reinterpret_cast<const uint4*>(nodes + 16 * i);
+            uint32_t m[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { uint4 t = ch[q]; m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
+            uint32_t d[8];
+            auto getm = [&](int w) -> uint32_t { return m[w]; };
+            hash_words<ALG>(getm, 16, d);
+            store_digest(nodes + 8 * i, d);
+        }
+        __syncthreads();
+    }
+}
+
+static inline unsigned grid_for(Ctx* c, long long n, int threads, int waves = 8) {
+    long long blocks = (n + threads - 1) / threads;
+    const long long cap = (long long)c->sm_count * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+static inline int hash_columns(Ctx* c, int alg, const HashCols& cols, long long n, uint32_t* out) {
+    if (cols.ncols < 1 || cols.ncols > GS_MAX_HASH_COLS) return c->fail(GS_E_ARG, "1..%d columns per leaf", GS_MAX_HASH_COLS);
+    const unsigned g = grid_for(c, n, 256);
+    if (alg == HASH_BLAKE2S) hash_columns_kernel<HASH_BLAKE2S><<<g, 256, 0, c->stream>>>(cols, n, out);
+    else if (alg == HASH_SHA256) hash_columns_kernel<HASH_SHA256><<<g, 256, 0, c->stream>>>(cols, n, out);
+    else return c->fail(GS_E_ARG, "unknown hash algorithm");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return c->cuda_fail(e, "hash_columns_kernel");
+    c->launches++;
+    return GS_OK;
+}
+
+static inline int hash_rows(Ctx* c, int alg, const void* buf, int row_bytes, long long n, uint32_t* out) {
+    if (row_bytes <= 0 || row_bytes % 16) return c->fail(GS_E_ARG, "row size must be a positive multiple of 16 bytes");
+    const unsigned g = grid_for(c, n, 256);
+    if (alg == HASH_BLAKE2S) hash_rows_kernel<HASH_BLAKE2S><<<g, 256, 0, c->stream>>>((const uint32_t*)buf, row_bytes / 4, n, out);
+    else if (alg == HASH_SHA256) hash_rows_kernel<HASH_SHA256><<<g, 256, 0, c->stream>>>((const uint32_t*)buf, row_bytes / 4, n, out);
+    else return c->fail(GS_E_ARG, "unknown hash algorithm");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return c->cuda_fail(e, "hash_rows_kernel");
+    c->launches++;
+    return GS_OK;
+}
+
+// nodes: 2n digests with the leaves already at [n, 2n)
+static inline int merkle_build(Ctx* c, int alg, uint32_t* nodes, long long n) {
+    if (alg != HASH_BLAKE2S && alg != HASH_SHA256) return c->fail(GS_E_ARG, "unknown hash algorithm");
+    long long count = n >> 1;
+    while (count > 1024) {
+        const unsigned g = grid_for(c, count, 256);
+        if (alg == HASH_BLAKE2S) merkle_level_kernel<HASH_BLAKE2S><<<g, 256, 0, c->stream>>>(nodes, count);
+        else merkle_level_kernel<HASH_SHA256><<<g, 256, 0, c->stream>>>(nodes, count);
+        c->launches++;
+        count >>= 1;
+    }
+    if (count >= 1) {
+        if (alg == HASH_BLAKE2S) merkle_tail_kernel<HASH_BLAKE2S><<<1, 1024, 0, c->stream>>>(nodes, (int)count);
+        else merkle_tail_kernel<HASH_SHA256><<<1, 1024, 0, c->stream>>>(nodes, (int)count);
+        c->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return c->cuda_fail(e, "merkle kernels");
+    return GS_OK;
+}
+
+}  // namespace gs

@@ -1,0 +1,579 @@
+// The fused prover: body of Stark.prove (/root/reference/lib/Stark.ts:81-163) as one host routine that
+// enqueues K1..K6 on the context stream and keeps every O(N) object in HBM.  The host only sees
+// 32-byte Merkle roots (for Fiat-Shamir), the <= 256-value FRI remainder and the queried rows.
+#pragma once
+#include <array>
+#include <chrono>
+#include <cstdlib>
+#include "core.cuh"
+#include "ntt_host.cuh"
+#include "pointwise.cuh"
+#include "hash.cuh"
+#include "batchinv.cuh"
+#include "fri.cuh"
+#include "compose.cuh"
+#include "hostcrypto.h"
+
+namespace gs {
+
+struct HostProgram {
+    std::vector<std::array<uint32_t, 4>> instrs;
+    std::vector<u128> consts;
+    int n_slots = 0, n_out = 0;
+};
+
+struct StaticReg {
+    int kind = 0;                 // 0 cycle, 1 secret input, 2 public input
+    std::vector<u128> values;     // cycle values
+};
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(Ctx* c, size_t bytes) {
+        if (bytes <= cap) return GS_OK;
+        if (p) { cudaStreamSynchronize(c->stream); cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return c->cuda_fail(e, "cudaMalloc(prover buffer)");
+        cap = bytes;
+        return GS_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct StageTimes {                 // milliseconds, host wall clock around each stage (sync'ed)
+    std::vector<std::pair<std::string, double>> items;
+};
+
+struct Stark {
+    Ctx* ctx = nullptr;
+    // AIR
+    int R = 0, K = 0, log_t = 0, log_e = 0;
+    std::vector<StaticReg> statics;
+    std::vector<int> degrees;
+    HostProgram transition, evaluation;
+    // options
+    int hash_alg = HASH_SHA256, exe_queries = 80, fri_queries = 40;
+    // derived
+    int n_secret = 0, n_public = 0;
+    // device-resident program + cyclic tables
+    DevBuf d_instrs, d_consts, d_cyc;
+    std::vector<size_t> cyc_off;      // per static register (cycle kind): element offset into d_cyc
+    std::vector<unsigned> cyc_mask;
+    // per-prove buffers (grow only)
+    DevBuf d_trace, d_poly, d_pe, d_in_trace, d_in_poly, d_in_e, d_work, d_tree, d_zb, d_zbs, d_l, d_c, d_fri, d_fri_trees,
+           d_params, d_small, d_idx, d_gather;
+    void* h_trace = nullptr; size_t h_trace_bytes = 0;     // pinned
+    StageTimes last_times;
+    bool keep_intermediates = false;  // stage-level parity tests read P/C/L back
+    ~Stark() {
+        for (DevBuf* b : {&d_instrs, &d_consts, &d_cyc, &d_trace, &d_poly, &d_pe, &d_in_trace, &d_in_poly, &d_in_e, &d_work, &d_tree,
+                          &d_zb, &d_zbs, &d_l, &d_c, &d_fri, &d_fri_trees, &d_params, &d_small, &d_idx, &d_gather}) b->release();
+        if (h_trace) cudaFreeHost(h_trace);
+    }
+};
+
+// ------------------------------------------------------------------------------ AIR blob (air.py)
+struct BlobReader {
+    const uint8_t* p; size_t n, off = 0; bool ok = true;
+    uint32_t u32() { if (off + 4 > n) { ok = false; return 0; } uint32_t v; memcpy(&v, p + off, 4); off += 4; return v; }
+    u128 elem() { if (off + 16 > n) { ok = false; return 0; } fp f; memcpy(&f, p + off, 16); off += 16; return fp_to_u128(f); }
+};
+
+static inline bool read_program(BlobReader& r, HostProgram& pr) {
+    uint32_t ni = r.u32(), nc = r.u32(); pr.n_slots = (int)r.u32(); pr.n_out = (int)r.u32();
+    if (!r.ok || ni > (1u << 20) || nc > (1u << 20)) return false;
+    pr.instrs.resize(ni);
+    for (auto& i : pr.instrs) for (int k = 0; k < 4; ++k) i[k] = r.u32();
+    pr.consts.resize(nc);
+    for (auto& c : pr.consts) c = r.elem();
+    return r.ok;
+}
+
+// host interpreter (trace generation): state -> next state
+static inline void run_transition(const HostProgram& pr, const u128* cur, const u128* statics, u128* slots, u128* out) {
+    for (const auto& ins : pr.instrs) {
+        const uint32_t op = ins[0], d = ins[1], a = ins[2], b = ins[3];
+        switch (op) {
+            case OP_CONST: slots[d] = pr.consts[a]; break;
+            case OP_CUR: slots[d] = cur[a]; break;
+            case OP_STATIC: slots[d] = statics[a]; break;
+            case OP_ADD: slots[d] = h_add(slots[a], slots[b]); break;
+            case OP_SUB: slots[d] = h_sub(slots[a], slots[b]); break;
+            case OP_MUL: slots[d] = h_mul(slots[a], slots[b]); break;
+            case OP_NEG: slots[d] = h_sub(0, slots[a]); break;
+            case OP_INV: slots[d] = h_inv(slots[a]); break;
+            case OP_EXP: slots[d] = h_pow(slots[a], pr.consts[b]); break;
+            case OP_OUT: out[d] = slots[a]; break;
+            default: break;
+        }
+    }
+}
+
+// Lagrange interpolation on the host (BoundaryConstraints.ts:42, LowDegreeProver.ts:243), low -> high
+static inline std::vector<u128> h_interpolate(const std::vector<u128>& xs, const std::vector<u128>& ys) {
+    const size_t n = xs.size();
+    std::vector<u128> root(n + 1, 0); root[0] = 1;
+    for (size_t i = 0; i < n; ++i) {            // root *= (x - xs[i])
+        for (size_t k = i + 1; k > 0; --k) root[k] = h_sub(root[k - 1], h_mul(root[k], xs[i]));
+        root[0] = h_sub(0, h_mul(root[0], xs[i]));
+    }
+    std::vector<u128> out(n, 0), num(n);
+    for (size_t i = 0; i < n; ++i) {
+        u128 acc = 0;
+        for (size_t k = n; k > 0; --k) { acc = h_add(root[k], h_mul(acc, xs[i])); num[k - 1] = acc; }
+        u128 den = 0;
+        for (size_t k = n; k > 0; --k) den = h_add(h_mul(den, xs[i]), num[k - 1]);
+        const u128 f = h_mul(ys[i], h_inv(den));
+        for (size_t k = 0; k < n; ++k) out[k] = h_add(out[k], h_mul(num[k], f));
+    }
+    return out;
+}
+static inline u128 h_eval_poly(const std::vector<u128>& poly, u128 x) {
+    u128 acc = 0;
+    for (size_t k = poly.size(); k > 0; --k) acc = h_add(h_mul(acc, x), poly[k - 1]);
+    return acc;
+}
+
+struct Assertion { uint32_t reg, step; u128 value; };
+
+struct FriLayer {
+    fp* v; long long len; uint32_t* tree; uint8_t root[32];
+};
+
+static inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// Build a BatchMerkleProof for `indexes` of a device-resident tree (n leaves): plan on the host, gather
+// the needed digests on the device, copy them back.
+static inline int device_merkle_proof(Stark* S, const uint32_t* tree, uint64_t n, const std::vector<uint32_t>& indexes,
+                                      BatchProof& bp, std::string& err) {
+    Ctx* c = S->ctx;
+    if (merkle_prove_plan(indexes, n, bp, err) != 0) return c->fail(GS_E_STARK, "%s", err.c_str());
+    std::vector<uint32_t> flat;
+    for (auto& col : bp.node_ids) flat.insert(flat.end(), col.begin(), col.end());
+    bp.nodes.assign(bp.node_ids.size(), {});
+    if (flat.empty()) return GS_OK;
+    int rc = S->d_idx.ensure(c, flat.size() * 4); if (rc) return rc;
+    rc = S->d_gather.ensure(c, flat.size() * 32); if (rc) return rc;
+    if (flat.size() * 32 > c->mailbox_bytes) return c->fail(GS_E_STARK, "batch proof too large");
+    GS_CUDA(c, cudaMemcpyAsync(S->d_idx.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    const int threads = 128, total = (int)flat.size() * 2;
+    gather_digests_kernel<<<(total + threads - 1) / threads, threads, 0, c->stream>>>(tree, S->d_idx.as<unsigned>(), (int)flat.size(),
+                                                                                       S->d_gather.as<uint32_t>());
+    c->launches++;
+    GS_CUDA(c, cudaMemcpyAsync(c->mailbox, S->d_gather.p, flat.size() * 32, cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    const uint8_t* src = (const uint8_t*)c->mailbox;
+    size_t k = 0;
+    for (size_t col = 0; col < bp.node_ids.size(); ++col) {
+        bp.nodes[col].resize(bp.node_ids[col].size());
+        for (size_t j = 0; j < bp.node_ids[col].size(); ++j, ++k) memcpy(bp.nodes[col][j].data(), src + 32 * k, 32);
+    }
+    return GS_OK;
+}
+
+// gather rows (idx) of `ncols` column vectors into raw value buffers
+static inline int device_gather_rows(Stark* S, const std::vector<const fp*>& cols, const std::vector<uint32_t>& idx,
+                                     std::vector<std::vector<uint8_t>>& values) {
+    Ctx* c = S->ctx;
+    const size_t nq = idx.size(), nc = cols.size();
+    values.assign(nq, {});
+    if (!nq) return GS_OK;
+    int rc = S->d_idx.ensure(c, nq * 4); if (rc) return rc;
+    rc = S->d_gather.ensure(c, nq * nc * 16); if (rc) return rc;
+    if (nq * nc * 16 > c->mailbox_bytes) return c->fail(GS_E_STARK, "too many queried values");
+    GatherCols gc; gc.ncols = (int)nc;
+    for (size_t i = 0; i < nc; ++i) gc.col[i] = cols[i];
+    GS_CUDA(c, cudaMemcpyAsync(S->d_idx.p, idx.data(), nq * 4, cudaMemcpyHostToDevice, c->stream));
+    const int threads = 128, total = (int)(nq * nc);
+    gather_rows_kernel<<<(total + threads - 1) / threads, threads, 0, c->stream>>>(gc, S->d_idx.as<unsigned>(), (int)nq, S->d_gather.as<fp>());
+    c->launches++;
+    GS_CUDA(c, cudaMemcpyAsync(c->mailbox, S->d_gather.p, nq * nc * 16, cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    const uint8_t* src = (const uint8_t*)c->mailbox;
+    for (size_t q = 0; q < nq; ++q) values[q].assign(src + q * nc * 16, src + (q + 1) * nc * 16);
+    return GS_OK;
+}
+
+static inline std::vector<uint32_t> first_seen_unique(const std::vector<uint32_t>& v) {
+    std::vector<uint32_t> out; std::map<uint32_t, bool> seen;
+    for (uint32_t x : v) if (!seen.count(x)) { seen[x] = true; out.push_back(x); }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------- prove
+// inputs: initial state (R elements), input register traces (n_input x T, register order), shapes blob
+static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, const u128* init_state,
+                              const fp* input_traces, const uint8_t* shapes_blob, size_t shapes_len,
+                              std::vector<uint8_t>& proof_out) {
+    Ctx* c = S->ctx;
+    cudaSetDevice(c->device);
+    StageTimes& tm = S->last_times; tm.items.clear();
+    double t_prev = now_ms();
+    auto mark = [&](const char* name, bool sync) {
+        if (sync) cudaStreamSynchronize(c->stream);
+        double t = now_ms(); tm.items.emplace_back(name, t - t_prev); t_prev = t;
+    };
+    const bool timing = S->keep_intermediates || getenv("GS_STAGE_TIMES") != nullptr;
+
+    if (n_assert <= 0) return c->fail(GS_E_ARG, "At least one assertion must be provided");
+    const int R = S->R, K = S->K, log_t = S->log_t, log_e = S->log_e, log_n = log_t + log_e;
+    const long long T = 1ll << log_t, N = 1ll << log_n, E = 1ll << log_e;
+    const int n_in = S->n_secret + S->n_public;
+    if (log_n > c->log_g) return c->fail(GS_E_UNSUPPORTED, "evaluation domain 2^%d exceeds 2^%d", log_n, c->log_g);
+    // getComponentCount quirk (LowDegreeProver.ts:287-291): N < 128 throws RangeError in the reference
+    if (N < 128) return c->fail(GS_E_STARK, "Low degree proof failed: Invalid array length");
+    int rc;
+
+    // 1-2 ---- execution trace on the host (sequential in steps), checked against the assertions
+    const size_t trace_bytes = (size_t)R * T * sizeof(fp);
+    if (S->h_trace_bytes < trace_bytes) {
+        if (S->h_trace) cudaFreeHost(S->h_trace);
+        GS_CUDA(c, cudaHostAlloc(&S->h_trace, trace_bytes, cudaHostAllocDefault));
+        S->h_trace_bytes = trace_bytes;
+    }
+    {
+        fp* tr = (fp*)S->h_trace;
+        std::vector<u128> state(init_state, init_state + R), next(R), slots(S->transition.n_slots + 1), stat(S->statics.size());
+        const u128* in_tr = nullptr; (void)in_tr;
+        for (long long s = 0; s < T; ++s) {
+            for (int r = 0; r < R; ++r) tr[(size_t)r * T + s] = fp_from_u128(state[r]);
+            if (s + 1 < T) {
+                int ii = 0;
+                for (size_t k = 0; k < S->statics.size(); ++k) {
+                    const StaticReg& sr = S->statics[k];
+                    if (sr.kind == 0) stat[k] = sr.values[s & (sr.values.size() - 1)];
+                    else stat[k] = fp_to_u128(input_traces[(size_t)(ii++) * T + s]);
+                }
+                run_transition(S->transition, state.data(), stat.data(), slots.data(), next.data());
+                state.swap(next);
+            }
+        }
+        for (int a = 0; a < n_assert; ++a) {
+            if ((int)asserts[a].reg >= R) return c->fail(GS_E_STARK, "Failed to generate the execution trace: Invalid assertion: register %u is outside of register bank", asserts[a].reg);
+            if (asserts[a].step >= (uint64_t)T) return c->fail(GS_E_STARK, "Failed to generate the execution trace: Invalid assertion: step %u is outside of execution trace", asserts[a].step);
+            if (fp_to_u128(tr[(size_t)asserts[a].reg * T + asserts[a].step]) != asserts[a].value)
+                return c->fail(GS_E_STARK, "Failed to generate the execution trace: Assertion at step %u, register %u conflicts with execution trace", asserts[a].step, asserts[a].reg);
+        }
+    }
+    mark("Generated execution trace", false);
+
+    // 3 ---- P(x) = iNTT(trace); low-degree extension over the evaluation domain
+    if ((rc = S->d_trace.ensure(c, trace_bytes))) return rc;
+    if ((rc = S->d_poly.ensure(c, trace_bytes))) return rc;
+    if ((rc = S->d_pe.ensure(c, (size_t)R * N * sizeof(fp)))) return rc;
+    const int wrows = R > n_in ? R : (n_in > 0 ? n_in : 1);
+    if ((rc = S->d_work.ensure(c, (size_t)wrows * N * sizeof(fp)))) return rc;
+    GS_CUDA(c, cudaMemcpyAsync(S->d_trace.p, S->h_trace, trace_bytes, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = ntt_run(c, S->d_trace.as<fp>(), T, S->d_poly.as<fp>(), T, S->d_work.as<fp>(), T, R, log_t, 0, true))) return rc;
+    if (timing) mark("Computed execution trace polynomials P(x)", true);
+    if ((rc = ntt_run(c, S->d_poly.as<fp>(), T, S->d_pe.as<fp>(), N, S->d_work.as<fp>(), N, R, log_t, log_e, false))) return rc;
+    // input registers (secret: committed; public: only feed the constraints)
+    if (n_in > 0) {
+        const size_t in_bytes = (size_t)n_in * T * sizeof(fp);
+        if ((rc = S->d_in_trace.ensure(c, in_bytes))) return rc;
+        if ((rc = S->d_in_poly.ensure(c, in_bytes))) return rc;
+        if ((rc = S->d_in_e.ensure(c, (size_t)n_in * N * sizeof(fp)))) return rc;
+        GS_CUDA(c, cudaMemcpyAsync(S->d_in_trace.p, input_traces, in_bytes, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = ntt_run(c, S->d_in_trace.as<fp>(), T, S->d_in_poly.as<fp>(), T, S->d_work.as<fp>(), T, n_in, log_t, 0, true))) return rc;
+        if ((rc = ntt_run(c, S->d_in_poly.as<fp>(), T, S->d_in_e.as<fp>(), N, S->d_work.as<fp>(), N, n_in, log_t, log_e, false))) return rc;
+    }
+    if (timing) mark("Low-degree extended P(x) polynomials over evaluation domain", true);
+
+    // 4 ---- Merkle tree over leaf_i = H(P_0[i] || .. || S_0[i] || ..)
+    std::vector<const fp*> e_cols;            // eVectors: trace rows then secret rows (Stark.ts:113-114)
+    for (int r = 0; r < R; ++r) e_cols.push_back(S->d_pe.as<fp>() + (size_t)r * N);
+    std::vector<const fp*> in_cols(S->statics.size(), nullptr);
+    {
+        int ii = 0;
+        for (size_t k = 0; k < S->statics.size(); ++k) if (S->statics[k].kind != 0) in_cols[k] = S->d_in_e.as<fp>() + (size_t)(ii++) * N;
+        for (size_t k = 0; k < S->statics.size(); ++k) if (S->statics[k].kind == 1) e_cols.push_back(in_cols[k]);
+    }
+    if (e_cols.size() > GS_MAX_HASH_COLS) return c->fail(GS_E_UNSUPPORTED, "more than %d committed registers", GS_MAX_HASH_COLS);
+    if ((rc = S->d_tree.ensure(c, (size_t)2 * N * 32))) return rc;
+    uint32_t* e_tree = S->d_tree.as<uint32_t>();
+    {
+        HashCols hc; hc.ncols = (int)e_cols.size();
+        for (size_t i = 0; i < e_cols.size(); ++i) hc.col[i] = e_cols[i];
+        if ((rc = hash_columns(c, S->hash_alg, hc, N, e_tree + 8 * N))) return rc;
+    }
+    if (timing) mark("Serialized evaluations of P(x) and S(x) polynomials", true);
+    if ((rc = merkle_build(c, S->hash_alg, e_tree, N))) return rc;
+    uint8_t ev_root[32];
+    GS_CUDA(c, cudaMemcpyAsync(c->mailbox, e_tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(ev_root, c->mailbox, 32);
+    mark("Built evaluation merkle tree", false);
+
+    // 5 ---- composition polynomial: coefficients, boundary polynomials, fused evaluation
+    int max_deg = 1;
+    for (int d : S->degrees) if (d > max_deg) max_deg = d;
+    int log_comp = 0; while ((1 << log_comp) < max_deg) ++log_comp;
+    const long long comb_degree = T << log_comp;                                    // CompositionPolynomial.ts:196-204
+    const long long comp_degree = std::max(comb_degree - T, T);                     // :40
+    // constraint groups by degree, first-appearance order (:206-225)
+    std::vector<long long> group_deg; std::vector<std::vector<int>> group_idx;
+    for (int k = 0; k < K; ++k) {
+        const long long dg = (long long)S->degrees[k] * T;
+        size_t g = 0; for (; g < group_deg.size(); ++g) if (group_deg[g] == dg) break;
+        if (g == group_deg.size()) { group_deg.push_back(dg); group_idx.emplace_back(); }
+        group_idx[g].push_back(k);
+    }
+    int d_count = K;
+    for (size_t g = 0; g < group_deg.size(); ++g) if (group_deg[g] < comb_degree) d_count += (int)group_idx[g].size();
+    // boundary constraints: registers in first-appearance order (BoundaryConstraints.ts:19-44)
+    std::vector<uint32_t> b_regs; std::vector<std::vector<u128>> b_xs, b_ys;
+    const u128 w_n = c->root_of_order(log_n);
+    for (int a = 0; a < n_assert; ++a) {
+        size_t b = 0; for (; b < b_regs.size(); ++b) if (b_regs[b] == asserts[a].reg) break;
+        if (b == b_regs.size()) { b_regs.push_back(asserts[a].reg); b_xs.emplace_back(); b_ys.emplace_back(); }
+        b_xs[b].push_back(h_pow(w_n, (u128)asserts[a].step * (u128)E));
+        b_ys[b].push_back(asserts[a].value);
+    }
+    const int nB = (int)b_regs.size();
+    int b_count = nB; if (comp_degree > T) b_count *= 2;
+    const std::vector<u128> coeffs = prng_many(ev_root, 32, d_count + b_count);          // :58-60
+    // per-constraint coefficient pair and power slot
+    std::vector<fp> dk(K), dk_adj(K, fp_zero()); std::vector<int> pow_idx(K, -1);
+    std::vector<unsigned long long> pow_incr;
+    for (int k = 0; k < K; ++k) dk[k] = fp_from_u128(coeffs[k]);
+    {
+        int next = K;
+        for (size_t g = 0; g < group_deg.size(); ++g) {
+            if (group_deg[g] == comb_degree) continue;                                    // :89
+            const unsigned long long incr = (unsigned long long)(comb_degree - group_deg[g]);
+            if (pow_incr.size() >= GS_MAX_POWERS) return c->fail(GS_E_UNSUPPORTED, "more than %d distinct constraint degrees", GS_MAX_POWERS);
+            pow_incr.push_back(incr);
+            for (int k : group_idx[g]) { dk_adj[k] = fp_from_u128(coeffs[next++]); pow_idx[k] = (int)pow_incr.size() - 1; }
+        }
+    }
+    std::vector<fp> bk(nB), bk_adj(nB, fp_zero());
+    for (int b = 0; b < nB; ++b) { bk[b] = fp_from_u128(coeffs[d_count + b]); if (comp_degree > T) bk_adj[b] = fp_from_u128(coeffs[d_count + nB + b]); }
+    // I(x), Z_b(x) per asserted register
+    std::vector<fp> ipoly, zpoly; std::vector<int> ioff(nB), ilen(nB), zoff(nB), zlen(nB), breg(nB);
+    for (int b = 0; b < nB; ++b) {
+        std::vector<u128> ip = h_interpolate(b_xs[b], b_ys[b]);
+        std::vector<u128> zp(1, 1);
+        for (u128 x : b_xs[b]) {             // zp *= (x - X)
+            zp.push_back(0);
+            for (size_t k = zp.size() - 1; k > 0; --k) zp[k] = h_sub(zp[k - 1], h_mul(zp[k], x));
+            zp[0] = h_sub(0, h_mul(zp[0], x));
+        }
+        ioff[b] = (int)ipoly.size(); ilen[b] = (int)ip.size(); for (u128 v : ip) ipoly.push_back(fp_from_u128(v));
+        zoff[b] = (int)zpoly.size(); zlen[b] = (int)zp.size(); for (u128 v : zp) zpoly.push_back(fp_from_u128(v));
+        breg[b] = (int)b_regs[b];
+    }
+    // linear combination coefficients continue the same stream (LinearCombination.ts:58-59, Stark.ts:129)
+    const int n_lc = (int)e_cols.size();
+    const long long delta = comp_degree - T;
+    const int lc_total = delta > 0 ? 2 * n_lc : n_lc;
+    const std::vector<u128> lc_all = prng_many(ev_root, 32, d_count + b_count + lc_total);
+    std::vector<fp> lk(n_lc), lk_adj(n_lc, fp_zero());
+    for (int j = 0; j < n_lc; ++j) { lk[j] = fp_from_u128(lc_all[d_count + b_count + j]); if (delta > 0) lk_adj[j] = fp_from_u128(lc_all[d_count + b_count + n_lc + j]); }
+    // inverse numerators of Z(x): num_i = w^(i*T) - 1 depends on i mod E (ZeroPolynomial.ts:40-41)
+    std::vector<fp> inv_num(E);
+    {
+        const u128 w_e = c->root_of_order(log_e);        // w^T
+        u128 acc = 1;
+        for (long long j = 0; j < E; ++j) { inv_num[j] = fp_from_u128(h_inv(h_sub(acc, 1))); acc = h_mul(acc, w_e); }
+    }
+    // small-object upload: one packed buffer
+    std::vector<uint8_t> small;
+    auto put = [&](const void* p, size_t n) { size_t off = (small.size() + 15) & ~(size_t)15; small.resize(off + n); memcpy(small.data() + off, p, n); return off; };
+    const size_t o_dk = put(dk.data(), K * 16), o_dka = put(dk_adj.data(), K * 16), o_pi = put(pow_idx.data(), K * 4);
+    const size_t o_bk = put(bk.data(), nB * 16), o_bka = put(bk_adj.data(), nB * 16);
+    const size_t o_ip = put(ipoly.data(), ipoly.size() * 16), o_zp = put(zpoly.data(), zpoly.size() * 16);
+    const size_t o_io = put(ioff.data(), nB * 4), o_il = put(ilen.data(), nB * 4), o_zo = put(zoff.data(), nB * 4), o_zl = put(zlen.data(), nB * 4);
+    const size_t o_br = put(breg.data(), nB * 4);
+    const size_t o_lk = put(lk.data(), n_lc * 16), o_lka = put(lk_adj.data(), n_lc * 16), o_in = put(inv_num.data(), E * 16);
+    const size_t o_flag = put("\0\0\0\0\0\0\0\0", 8);
+    if ((rc = S->d_small.ensure(c, small.size() + 64))) return rc;
+    uint8_t* ds = S->d_small.as<uint8_t>();
+    GS_CUDA(c, cudaMemcpyAsync(ds, small.data(), small.size(), cudaMemcpyHostToDevice, c->stream));
+    // Z_b evaluations and their inverses
+    if ((rc = S->d_zb.ensure(c, (size_t)nB * N * sizeof(fp)))) return rc;
+    if ((rc = S->d_zbs.ensure(c, (size_t)nB * N * sizeof(fp)))) return rc;
+    {
+        ZbParams zp; zp.n = N; zp.log_n = log_n; zp.n_boundary = nB;
+        zp.zpoly_off = (const int*)(ds + o_zo); zp.zpoly_len = (const int*)(ds + o_zl); zp.zpoly = (const fp*)(ds + o_zp);
+        zp.tw_lo = c->tw_lo; zp.tw_hi = c->tw_hi; zp.log_g = c->log_g; zp.log_lo = c->log_lo; zp.out = S->d_zb.as<fp>();
+        zb_eval_kernel<<<grid_for(c, N, 256), 256, 0, c->stream>>>(zp);
+        c->launches++;
+        if ((rc = batch_inverse(c, S->d_zb.as<fp>(), S->d_zb.as<fp>(), S->d_zbs.as<fp>(), (long long)nB * N))) return rc;
+    }
+    if ((rc = S->d_l.ensure(c, (size_t)N * sizeof(fp)))) return rc;
+    if (S->keep_intermediates && (rc = S->d_c.ensure(c, (size_t)N * sizeof(fp)))) return rc;
+    {
+        ComposeParams P; memset(&P, 0, sizeof P);
+        P.n = N; P.log_n = log_n; P.log_e = log_e;
+        P.instrs = S->d_instrs.as<uint4>(); P.n_instr = (int)S->evaluation.instrs.size(); P.consts = S->d_consts.as<fp>(); P.n_slots = S->evaluation.n_slots;
+        P.n_trace = R; for (int r = 0; r < R; ++r) P.trace[r] = S->d_pe.as<fp>() + (size_t)r * N;
+        P.n_static = (int)S->statics.size();
+        for (size_t k = 0; k < S->statics.size(); ++k) {
+            if (S->statics[k].kind == 0) { P.stat[k] = S->d_cyc.as<fp>() + S->cyc_off[k]; P.stat_mask[k] = S->cyc_mask[k]; }
+            else { P.stat[k] = in_cols[k]; P.stat_mask[k] = 0xFFFFFFFFu; }
+        }
+        P.n_constraints = K; P.dk = (const fp*)(ds + o_dk); P.dk_adj = (const fp*)(ds + o_dka); P.pow_idx = (const int*)(ds + o_pi);
+        P.n_powers = (int)pow_incr.size(); for (size_t g = 0; g < pow_incr.size(); ++g) P.pow_incr[g] = pow_incr[g] & (unsigned long long)(N - 1);
+        P.x_last = fp_from_u128(h_pow(w_n, (u128)(T - 1) * (u128)E)); P.inv_num = (const fp*)(ds + o_in);
+        P.n_boundary = nB; P.b_reg = (const int*)(ds + o_br); P.b_ipoly_off = (const int*)(ds + o_io); P.b_ipoly_len = (const int*)(ds + o_il);
+        P.b_ipoly = (const fp*)(ds + o_ip); P.zb_inv = S->d_zb.as<fp>(); P.bk = (const fp*)(ds + o_bk); P.bk_adj = (const fp*)(ds + o_bka);
+        P.n_lc = n_lc; for (int j = 0; j < n_lc; ++j) P.lc_col[j] = e_cols[j];
+        P.lk = (const fp*)(ds + o_lk); P.lk_adj = (const fp*)(ds + o_lka);
+        P.delta = (unsigned long long)delta;
+        P.tw_lo = c->tw_lo; P.tw_hi = c->tw_hi; P.log_g = c->log_g; P.log_lo = c->log_lo;
+        P.out = S->d_l.as<fp>(); P.c_out = S->keep_intermediates ? S->d_c.as<fp>() : nullptr;
+        P.fail_flag = (int*)(ds + o_flag);
+        if ((rc = S->d_params.ensure(c, sizeof P))) return rc;
+        GS_CUDA(c, cudaMemcpyAsync(S->d_params.p, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
+        const unsigned g = grid_for(c, N, 256);
+        const int ns = S->evaluation.n_slots;
+        if (ns <= 8) compose_kernel<8><<<g, 256, 0, c->stream>>>(S->d_params.as<ComposeParams>());
+        else if (ns <= 32) compose_kernel<32><<<g, 256, 0, c->stream>>>(S->d_params.as<ComposeParams>());
+        else if (ns <= 128) compose_kernel<128><<<g, 256, 0, c->stream>>>(S->d_params.as<ComposeParams>());
+        else return c->fail(GS_E_UNSUPPORTED, "evaluation program needs %d value slots (max 128)", ns);
+        c->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return c->cuda_fail(e, "compose_kernel");
+        GS_CUDA(c, cudaMemcpyAsync(c->mailbox, ds + o_flag, 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+
+    // 7 ---- low-degree proof (LowDegreeProver.ts:39-68,176-221)
+    std::vector<FriLayer> layers;
+    {
+        long long tot_v = 0, tot_t = 0;
+        for (long long L = N; ; L >>= 2) { tot_t += 2 * (L >> 2); if (L <= 256) break; tot_v += L >> 2; }
+        if ((rc = S->d_fri.ensure(c, (size_t)(tot_v + 4) * sizeof(fp)))) return rc;
+        if ((rc = S->d_fri_trees.ensure(c, (size_t)tot_t * 32))) return rc;
+    }
+    const u128 iota_inv = h_inv(c->root_of_order(2));
+    const u128 quarter_inv = h_inv(4);
+    fp* d_special = S->d_fri.as<fp>();            // slot 0..3 reserved for the challenge
+    fp* v_next = S->d_fri.as<fp>() + 4;
+    uint32_t* t_next = S->d_fri_trees.as<uint32_t>();
+    fp* v_cur = S->d_l.as<fp>();
+    bool flag_checked = false;
+    std::vector<u128> remainder;
+    long long max_deg_p1 = comp_degree;
+    for (int depth = 0;; ++depth) {
+        const long long L = N >> (2 * depth), Q = L >> 2;
+        FriLayer ly; ly.v = v_cur; ly.len = L; ly.tree = t_next; t_next += (size_t)2 * Q * 8;
+        HashCols hc; hc.ncols = 4; for (int j = 0; j < 4; ++j) hc.col[j] = v_cur + j * Q;
+        if ((rc = hash_columns(c, S->hash_alg, hc, Q, ly.tree + 8 * Q))) return rc;
+        if ((rc = merkle_build(c, S->hash_alg, ly.tree, Q))) return rc;
+        GS_CUDA(c, cudaMemcpyAsync((uint8_t*)c->mailbox + 64, ly.tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
+        GS_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (!flag_checked) {
+            flag_checked = true;
+            const int* fl = (const int*)c->mailbox;
+            if (fl[0] != 0) return c->fail(GS_E_STARK, "Failed to evaluate transition constraints: Constraint %d didn't evaluate to 0 at step %d", fl[0] - 1, fl[1]);
+            if (timing) mark("Computed composition polynomial C(x) and combined P(x), S(x)", false);
+        }
+        memcpy(ly.root, (uint8_t*)c->mailbox + 64, 32);
+        layers.push_back(ly);
+        if (L <= 256) {
+            // remainder: transposeMatrix + joinMatrixRows restores natural order (:179-186)
+            GS_CUDA(c, cudaMemcpyAsync(c->mailbox, v_cur, L * sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
+            GS_CUDA(c, cudaStreamSynchronize(c->stream));
+            remainder.resize(L);
+            for (long long i = 0; i < L; ++i) remainder[i] = fp_to_u128(((const fp*)c->mailbox)[i]);
+            // verifyRemainder (:223-252)
+            const u128 rou = h_pow(w_n, (u128)1 << (2 * depth));
+            std::vector<long long> pos;
+            for (long long i = 0; i < L; ++i) if (i % E) pos.push_back(i);
+            if (max_deg_p1 > (long long)pos.size()) return c->fail(GS_E_STARK, "Low degree proof failed: remainder too short for degree %lld", max_deg_p1);
+            std::vector<u128> dom(L); { u128 a = 1; for (long long i = 0; i < L; ++i) { dom[i] = a; a = h_mul(a, rou); } }
+            std::vector<u128> xs(max_deg_p1), ys(max_deg_p1);
+            for (long long i = 0; i < max_deg_p1; ++i) { xs[i] = dom[pos[i]]; ys[i] = remainder[pos[i]]; }
+            const std::vector<u128> poly = h_interpolate(xs, ys);
+            for (size_t i = (size_t)max_deg_p1; i < pos.size(); ++i)
+                if (h_eval_poly(poly, dom[pos[i]]) != remainder[pos[i]])
+                    return c->fail(GS_E_STARK, "Low degree proof failed: Remainder is not a valid degree %lld polynomial", max_deg_p1 - 1);
+            break;
+        }
+        // challenge and fold
+        const fp sx = fp_from_u128(prng_one(ly.root, 32));                               // :194
+        GS_CUDA(c, cudaMemcpyAsync(d_special, &sx, sizeof(fp), cudaMemcpyHostToDevice, c->stream));
+        FriFoldParams F; F.v = v_cur; F.out = v_next; F.quarter = Q; F.special_x = d_special;
+        F.tw_lo = c->tw_lo; F.tw_hi = c->tw_hi; F.log_g = c->log_g; F.log_lo = c->log_lo;
+        F.x_shift = 2 * depth + (c->log_g - log_n); F.iota_inv = fp_from_u128(iota_inv); F.quarter_inv = fp_from_u128(quarter_inv);
+        fri_fold_kernel<<<grid_for(c, Q, 256), 256, 0, c->stream>>>(F);
+        c->launches++;
+        v_cur = v_next; v_next += Q;
+        max_deg_p1 /= 4;
+    }
+    mark("Computed low-degree proof (layers)", false);
+
+    // queries of the low-degree proof
+    std::string err;
+    const uint8_t* lc_root = layers[0].root;
+    std::vector<uint32_t> exe_pos;
+    if (pseudorandom_indexes(lc_root, (int)std::min<long long>(S->exe_queries, N - N / E), (uint64_t)N, (uint64_t)E, exe_pos, err) != 0)
+        return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str());
+    auto rows_of = [&](const FriLayer& ly, const std::vector<uint32_t>& idx, std::vector<std::vector<uint8_t>>& vals) {
+        std::vector<const fp*> cols; for (int j = 0; j < 4; ++j) cols.push_back(ly.v + j * (ly.len >> 2));
+        return device_gather_rows(S, cols, idx, vals);
+    };
+    auto aug4 = [&](const std::vector<uint32_t>& p, long long column_length) {
+        std::vector<uint32_t> m(p.size()); const uint32_t row_len = (uint32_t)(column_length >> 2);
+        for (size_t i = 0; i < p.size(); ++i) m[i] = p[i] % row_len;
+        return first_seen_unique(m);
+    };
+    BatchProof lc_proof;
+    {
+        const std::vector<uint32_t> lc_pos = aug4(exe_pos, N);
+        if ((rc = device_merkle_proof(S, layers[0].tree, (uint64_t)(N >> 2), lc_pos, lc_proof, err))) return rc;
+        if ((rc = rows_of(layers[0], lc_pos, lc_proof.values))) return rc;
+    }
+    struct Comp { const uint8_t* root; BatchProof column, poly; };
+    std::vector<Comp> comps(layers.size() - 1);
+    for (size_t d = 0; d + 1 < layers.size(); ++d) {
+        const FriLayer& pl = layers[d]; const FriLayer& cl = layers[d + 1];
+        std::vector<uint32_t> positions;
+        if (pseudorandom_indexes(cl.root, S->fri_queries, (uint64_t)cl.len, (uint64_t)E, positions, err) != 0)
+            return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str());
+        const std::vector<uint32_t> augmented = aug4(positions, cl.len);
+        comps[d].root = cl.root;
+        if ((rc = device_merkle_proof(S, cl.tree, (uint64_t)(cl.len >> 2), augmented, comps[d].column, err))) return rc;
+        if ((rc = rows_of(cl, augmented, comps[d].column.values))) return rc;
+        if ((rc = device_merkle_proof(S, pl.tree, (uint64_t)(pl.len >> 2), positions, comps[d].poly, err))) return rc;
+        if ((rc = rows_of(pl, positions, comps[d].poly.values))) return rc;
+    }
+    // 8 ---- trace queries (Stark.ts:147-151)
+    std::vector<uint32_t> aug_pos;
+    {
+        std::vector<uint32_t> m;
+        for (uint32_t p : exe_pos) { m.push_back(p); m.push_back((uint32_t)((p + E) % N)); }
+        aug_pos = first_seen_unique(m);
+    }
+    BatchProof ev_proof;
+    if ((rc = device_merkle_proof(S, e_tree, (uint64_t)N, aug_pos, ev_proof, err))) return rc;
+    if ((rc = device_gather_rows(S, e_cols, aug_pos, ev_proof.values))) return rc;
+    mark("Computed evaluation spot checks and Merkle proofs", false);
+
+    // serialize (Serializer.ts:35-79)
+    std::vector<uint8_t>& out = proof_out; out.clear();
+    const size_t ev_leaf = e_cols.size() * 16, ld_leaf = 64;
+    for (const BatchProof* p : {&ev_proof, &lc_proof}) if (check_merkle_proof_limits(*p, err) != 0) return c->fail(GS_E_STARK, "%s", err.c_str());
+    out.insert(out.end(), ev_root, ev_root + 32);
+    write_merkle_proof(out, ev_proof, ev_leaf);
+    out.insert(out.end(), lc_root, lc_root + 32);
+    write_merkle_proof(out, lc_proof, ld_leaf);
+    out.push_back((uint8_t)comps.size());
+    for (auto& cp : comps) {
+        if (check_merkle_proof_limits(cp.column, err) != 0 || check_merkle_proof_limits(cp.poly, err) != 0) return c->fail(GS_E_STARK, "%s", err.c_str());
+        out.insert(out.end(), cp.root, cp.root + 32);
+        write_merkle_proof(out, cp.column, ld_leaf);
+        write_merkle_proof(out, cp.poly, ld_leaf);
+    }
+    out.push_back((uint8_t)(remainder.size() == 256 ? 0 : remainder.size()));
+    for (u128 v : remainder) { fp f = fp_from_u128(v); const uint8_t* b = (const uint8_t*)&f; out.insert(out.end(), b, b + 16); }
+    if (shapes_blob && shapes_len) out.insert(out.end(), shapes_blob, shapes_blob + shapes_len);
+    else out.push_back(0);
+    mark("Serialized proof", false);
+    return GS_OK;
+}
+
+}  // namespace gs

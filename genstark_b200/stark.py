@@ -1,0 +1,268 @@
+"""Host-side mirror of genSTARK's public API on top of libgenstark_b200.so.
+
+``Stark`` keeps the interface of /root/reference/lib/Stark.ts (genstark.d.ts:85-124): ``prove`` /
+``verify`` / ``serialize`` / ``parse`` / ``sizeOf`` / ``securityLevel``; ``instantiate`` mirrors
+index.ts:18-33 with the AIR given as an ``AirModule`` (the AirScript / AirAssembly compilers are out
+of scope).  The prover body runs on the GPU through ``gs_stark_prove``; there is no
+CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import math
+import struct
+from typing import Dict, List, Optional, Sequence
+
+from . import _native
+from .air import AirModule, pack_air
+from .field import Context
+
+DEFAULT_EXE_QUERY_COUNT, DEFAULT_FRI_QUERY_COUNT = 80, 40          # Stark.ts:13-14
+MAX_EXE_QUERY_COUNT, MAX_FRI_QUERY_COUNT = 128, 64                 # Stark.ts:16-17
+HASH_ALGORITHMS = ['sha256', 'blake2s256']                         # Stark.ts:19
+DEFAULT_HASH_ALGORITHM = 'sha256'
+MAX_ARRAY_LENGTH, MAX_MATRIX_COLUMN_LENGTH = 256, 127              # lib/utils/sizeof.ts:7-8
+
+
+class StarkError(Exception):
+    """lib/StarkError.ts:3-13"""
+
+
+class BatchMerkleProof:
+    """@guildofweavers/merkle BatchMerkleProof {values, nodes, depth} (lib/utils/serialization.ts:31-35)"""
+
+    def __init__(self, values: List[bytes], nodes: List[List[bytes]], depth: int):
+        self.values, self.nodes, self.depth = values, nodes, depth
+
+
+def _pow_log2(base: float, exponent: int) -> float:                # lib/utils/index.ts:23-30
+    twos = 0
+    while exponent % 2 == 0:
+        twos += 1
+        exponent //= 2
+    return (2 ** twos) * math.log2(base ** exponent)
+
+
+class Stark:
+    def __init__(self, air: AirModule, options: Optional[dict] = None, logger=None, context: Optional[Context] = None):
+        options = options or {}
+        self.air = air.with_options(options.get('extensionFactor'))
+        # buildSecurityOptions (Stark.ts:318-344)
+        exe = options.get('exeQueryCount') or DEFAULT_EXE_QUERY_COUNT
+        if exe < 1 or exe > MAX_EXE_QUERY_COUNT or int(exe) != exe:
+            raise TypeError(f'Execution sample size must be an integer between 1 and {MAX_EXE_QUERY_COUNT}')
+        fri = options.get('friQueryCount') or DEFAULT_FRI_QUERY_COUNT
+        if fri < 1 or fri > MAX_FRI_QUERY_COUNT or int(fri) != fri:
+            raise TypeError(f'FRI sample size must be an integer between 1 and {MAX_FRI_QUERY_COUNT}')
+        alg = options.get('hashAlgorithm') or DEFAULT_HASH_ALGORITHM
+        if alg not in HASH_ALGORITHMS:
+            raise TypeError(f'Hash algorithm {alg} is not supported')
+        if not self.air.extension_factor:
+            raise TypeError('Extension factor is undefined')
+        self.exeQueryCount, self.friQueryCount, self.hashAlgorithm = int(exe), int(fri), alg
+        self.digestSize = 32
+        self.elementSize = self.air.element_size
+        self.logger = logger
+        self._lib = _native.lib()
+        self.context = context or Context(options.get('device', 0))
+        h = C.c_void_p()
+        blob = pack_air(self.air)
+        rc = self._lib.gs_stark_create(self.context.handle, blob, len(blob), HASH_ALGORITHMS.index(alg),
+                                       self.exeQueryCount, self.friQueryCount, C.byref(h))
+        self.context.check(rc)
+        self._handle = h
+
+    def close(self):
+        if getattr(self, '_handle', None):
+            self._lib.gs_stark_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ACCESSORS -------------------------------------------------------------------------------------
+    @property
+    def securityLevel(self) -> int:                                # Stark.ts:62-77
+        e = self.air.extension_factor
+        es = _pow_log2(e / self.air.max_constraint_degree, self.exeQueryCount)
+        fs = math.log2(e) * self.friQueryCount
+        hs = self.digestSize * 4
+        return math.floor(min(es, fs, hs))
+
+    # PROVER ----------------------------------------------------------------------------------------
+    def prove_bytes(self, assertions: Sequence[dict], inputs=None, seed=None) -> bytes:
+        """Stark.prove + serialize in one crossing: the serialized proof as produced on the device path."""
+        if not isinstance(assertions, (list, tuple)):
+            raise TypeError('Assertions parameter must be an array')
+        if len(assertions) == 0:
+            raise TypeError('At least one assertion must be provided')
+        air = self.air
+        p = air.modulus
+        init = [int(v) % p for v in air.init(inputs or [], seed or [])]
+        if len(init) != air.trace_register_count:
+            raise StarkError('Failed to generate the execution trace: initial state has the wrong width')
+        a_blob = b''.join(struct.pack('<II', int(a['register']), int(a['step'])) + (int(a['value']) % p).to_bytes(16, 'little')
+                          for a in assertions)
+        init_blob = b''.join(v.to_bytes(16, 'little') for v in init)
+        traces = air.expand_inputs(inputs or [])
+        in_blob = None
+        if traces:
+            in_blob = b''.join((int(v) % p).to_bytes(16, 'little') for t in traces for v in t)
+        shapes = air.input_shapes(inputs or [])
+        s_blob = bytes([len(shapes)]) + b''.join(bytes([len(s)]) + b''.join(struct.pack('<I', x) for x in s) for s in shapes)
+        out_p, out_n = C.POINTER(C.c_uint8)(), C.c_size_t()
+        rc = self._lib.gs_stark_prove(self._handle, a_blob, len(assertions), init_blob, in_blob, s_blob, len(s_blob),
+                                      C.byref(out_p), C.byref(out_n))
+        if rc == -4:
+            raise StarkError(self._lib.gs_last_error(self.context.handle).decode())
+        self.context.check(rc)
+        return C.string_at(out_p, out_n.value)
+
+    def prove(self, assertions: Sequence[dict], inputs=None, seed=None) -> dict:
+        """lib/Stark.ts:81-163 -> StarkProof {evRoot, evProof, ldProof, iShapes}"""
+        return self.parse(self.prove_bytes(assertions, inputs, seed))
+
+    def stage_times(self) -> List:
+        return json.loads(self._lib.gs_stark_stage_times(self._handle).decode() or '[]')
+
+    # test hooks
+    def _set_debug(self, on: bool = True):
+        self.context.check(self._lib.gs_stark_set_debug(self._handle, 1 if on else 0))
+
+    def _read_intermediate(self, which: int) -> List[int]:
+        n = self.air.trace_length * self.air.extension_factor
+        count = {0: self.air.trace_register_count * n, 1: n, 2: n, 3: self.air.trace_register_count * self.air.trace_length}[which]
+        buf = C.create_string_buffer(count * 16)
+        self.context.check(self._lib.gs_stark_read_intermediate(self._handle, which, buf, count * 16))
+        raw = buf.raw
+        return [int.from_bytes(raw[i:i + 16], 'little') for i in range(0, len(raw), 16)]
+
+    # WIRE FORMAT (lib/Serializer.ts, lib/utils/serialization.ts, lib/utils/sizeof.ts) ------------------
+    def _leaf_sizes(self):
+        es = self.elementSize
+        return (self.air.trace_register_count + self.air.secret_input_count) * es, es * 4
+
+    def serialize(self, proof: dict) -> bytes:                      # Serializer.ts:35-79
+        ev_leaf, ld_leaf = self._leaf_sizes()
+        es = self.elementSize
+        out = bytearray(proof['evRoot'])
+        out += _write_merkle_proof(proof['evProof'], ev_leaf)
+        ld = proof['ldProof']
+        out += ld['lcRoot']
+        out += _write_merkle_proof(ld['lcProof'], ld_leaf)
+        out.append(len(ld['components']))
+        for comp in ld['components']:
+            out += comp['columnRoot']
+            out += _write_merkle_proof(comp['columnProof'], ld_leaf)
+            out += _write_merkle_proof(comp['polyProof'], ld_leaf)
+        rl = len(ld['remainder'])
+        out.append(0 if rl == 256 else rl)                           # zero means 256, :59-63
+        for v in ld['remainder']:
+            out += int(v).to_bytes(es, 'little')
+        out.append(len(proof['iShapes']))
+        for shape in proof['iShapes']:
+            out.append(len(shape))
+            for level in shape:
+                out += struct.pack('<I', level)
+        return bytes(out)
+
+    def parse(self, buf: bytes) -> dict:                            # Serializer.ts:83-144
+        ev_leaf, ld_leaf = self._leaf_sizes()
+        es, ds = self.elementSize, self.digestSize
+        ev_root = bytes(buf[:ds])
+        ev_proof, off = _read_merkle_proof(buf, ds, ev_leaf, ds)
+        lc_root = bytes(buf[off:off + ds]); off += ds
+        lc_proof, off = _read_merkle_proof(buf, off, ld_leaf, ds)
+        count = buf[off]; off += 1
+        comps = []
+        for _ in range(count):
+            column_root = bytes(buf[off:off + ds]); off += ds
+            column_proof, off = _read_merkle_proof(buf, off, ld_leaf, ds)
+            poly_proof, off = _read_merkle_proof(buf, off, ld_leaf, ds)
+            comps.append({'columnRoot': column_root, 'columnProof': column_proof, 'polyProof': poly_proof})
+        rl = buf[off] or MAX_ARRAY_LENGTH; off += 1
+        remainder = []
+        for _ in range(rl):
+            remainder.append(int.from_bytes(buf[off:off + es], 'little')); off += es
+        n_inputs = buf[off]; off += 1
+        shapes = []
+        for _ in range(n_inputs):
+            rank = buf[off]; off += 1
+            shape = []
+            for _ in range(rank):
+                shape.append(struct.unpack_from('<I', buf, off)[0]); off += 4
+            shapes.append(shape)
+        return {'evRoot': ev_root, 'evProof': ev_proof,
+                'ldProof': {'lcRoot': lc_root, 'lcProof': lc_proof, 'components': comps, 'remainder': remainder},
+                'iShapes': shapes}
+
+    def sizeOf(self, proof: dict) -> int:                           # sizeof.ts:12-53
+        es, ds = self.elementSize, self.digestSize
+        size = ds + _size_of_merkle_proof(proof['evProof'])
+        ld = proof['ldProof']
+        size += 1 + _size_of_merkle_proof(ld['lcProof']) + ds
+        for comp in ld['components']:
+            size += ds + _size_of_merkle_proof(comp['columnProof']) + _size_of_merkle_proof(comp['polyProof'])
+        size += len(ld['remainder']) * es + 1
+        size += 1 + sum(1 + 4 * len(s) for s in proof['iShapes'])
+        return size
+
+
+def _size_of_merkle_proof(p: BatchMerkleProof) -> int:              # sizeof.ts:55-99
+    if len(p.values) == 0:
+        raise ValueError('Array cannot be zero-length')
+    if len(p.values) > MAX_ARRAY_LENGTH:
+        raise ValueError(f'Array length ({len(p.values)}) cannot exceed {MAX_ARRAY_LENGTH}')
+    if len(p.nodes) > MAX_ARRAY_LENGTH:
+        raise ValueError(f'Matrix column count ({len(p.nodes)}) cannot exceed {MAX_ARRAY_LENGTH}')
+    size = 1 + sum(len(v) for v in p.values) + 1 + len(p.nodes)
+    for col in p.nodes:
+        if len(col) >= MAX_MATRIX_COLUMN_LENGTH:
+            raise ValueError(f'Matrix column length ({len(col)}) cannot exceed {MAX_MATRIX_COLUMN_LENGTH}')
+        size += sum(len(x) for x in col)
+    return size + 1
+
+
+def _write_merkle_proof(p: BatchMerkleProof, leaf_size: int) -> bytes:   # serialization.ts:18-96
+    out = bytearray([0 if len(p.values) == MAX_ARRAY_LENGTH else len(p.values)])
+    for v in p.values:
+        out += v
+    out.append(0 if len(p.nodes) == MAX_ARRAY_LENGTH else len(p.nodes))
+    for col in p.nodes:
+        t = 1 if (len(col) > 0 and len(col[0]) == leaf_size) else 0
+        out.append(((len(col) << 1) | t) & 0xFF)
+    for col in p.nodes:
+        for x in col:
+            out += x
+    out.append(p.depth)
+    return bytes(out)
+
+
+def _read_merkle_proof(buf: bytes, off: int, leaf_size: int, node_size: int):   # serialization.ts:25-124
+    n = buf[off] or MAX_ARRAY_LENGTH; off += 1
+    values = []
+    for _ in range(n):
+        values.append(bytes(buf[off:off + leaf_size])); off += leaf_size
+    cols = buf[off] or MAX_ARRAY_LENGTH; off += 1
+    lens, types = [], []
+    for _ in range(cols):
+        lt = buf[off]; off += 1
+        lens.append(lt >> 1); types.append(lt & 1)
+    nodes = []
+    for i in range(cols):
+        col = []
+        for j in range(lens[i]):
+            sz = (leaf_size if types[i] == 1 else node_size) if j == 0 else node_size
+            col.append(bytes(buf[off:off + sz])); off += sz
+        nodes.append(col)
+    depth = buf[off]; off += 1
+    return BatchMerkleProof(values, nodes, depth), off
+
+
+def instantiate(air: AirModule, options: Optional[dict] = None, logger=None) -> Stark:
+    """index.ts:18-33 with the schema already compiled to an AirModule."""
+    return Stark(air, options, logger)

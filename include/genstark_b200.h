@@ -26,6 +26,7 @@ extern "C" {
 
 typedef struct gs_ctx gs_ctx;     /* one device + stream + root tables              */
 typedef struct gs_mat gs_mat;     /* rows x cols field elements, row-major, in HBM  */
+typedef struct gs_stark gs_stark; /* one AIR + security options + device buffers    */
 
 enum gs_status {
     GS_OK = 0,
@@ -73,6 +74,29 @@ int gs_eval_polys_at_roots(gs_ctx* ctx, const gs_mat* polys, int log2_domain, gs
  * shape or a scalar (pass b = NULL and scalar16): op 0 add, 1 sub, 2 mul.
  * Call sites: CompositionPolynomial.ts:98,120,136,145; LinearCombination.ts:50,63; ZeroPolynomial.ts:41-42 */
 int gs_vec_binary(gs_ctx* ctx, int op, const gs_mat* a, const gs_mat* b, const uint8_t* scalar16, gs_mat** out);
+
+/* ---- fused prover: the body of Stark.prove in one crossing (lib/Stark.ts:81-163) -------------------
+ * gs_stark_create  <->  new Stark(schema, component, options)            lib/Stark.ts:35-58
+ *   air_blob: flattened AirModule (genstark_b200/air.py: pack_air); hash_alg 0 = sha256, 1 = blake2s256
+ *   (HASH_ALGORITHMS, lib/Stark.ts:19); query counts validated as buildSecurityOptions does (:318-344).
+ * gs_stark_prove   <->  stark.prove(assertions, inputs, seed)            lib/Stark.ts:81-163
+ *   assertions: n x { u32 register, u32 step, 16-byte value }; init_state16: the first trace row
+ *   (R x 16 bytes, from the AIR's init with inputs/seed); input_traces: one T-length column per input
+ *   register (register order), or NULL; shapes_blob: serialized iShapes (u8 count, then u8 rank +
+ *   rank x u32le each) appended to the proof.  *proof_out is the serialized proof
+ *   (lib/Serializer.ts:35-79), owned by the handle and valid until the next call.
+ *   GS_E_STARK carries the reference's StarkError texts (lib/Stark.ts:101,143; CompositionPolynomial.ts:79). */
+int gs_stark_create(gs_ctx* ctx, const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries,
+                    int fri_queries, gs_stark** out);
+void gs_stark_destroy(gs_stark* s);
+int gs_stark_prove(gs_stark* s, const uint8_t* assertions, int n_assertions, const uint8_t* init_state16,
+                   const uint8_t* input_traces, const uint8_t* shapes_blob, size_t shapes_len,
+                   const uint8_t** proof_out, size_t* proof_len);
+/* per-stage host milliseconds of the last prove as JSON [[name, ms], ...] (Logger, lib/utils/Logger.ts) */
+const char* gs_stark_stage_times(gs_stark* s);
+/* test hooks: keep C(x) and read device-resident intermediates back (0 P evals, 1 C, 2 L, 3 P polys) */
+int gs_stark_set_debug(gs_stark* s, int keep_intermediates);
+int gs_stark_read_intermediate(gs_stark* s, int which, void* out, size_t out_bytes);
 
 /* ---- measurement helpers ------------------------------------------------------------------------ */
 /* runs blocks x 256 threads x (4*iters) dependent modular multiplications; returns kernel ms */

@@ -1,0 +1,65 @@
+"""End-to-end parity of the fused GPU prover against the oracle's restatement of Stark.prove:
+serialized proof bytes identical, stage outputs identical, and the GPU proof accepted by the oracle's
+restatement of Stark.verify."""
+import pytest
+
+from genstark_b200 import airs
+from genstark_b200.stark import Stark, StarkError
+from oracle.stark import Stark as OracleStark
+
+pytestmark = pytest.mark.gpu
+
+OPTS = dict(hashAlgorithm='blake2s256', exeQueryCount=48, friQueryCount=24)
+
+
+def _mimc_case(steps, e, hash_alg='blake2s256', seed=3):
+    opts = dict(OPTS, extensionFactor=e, hashAlgorithm=hash_alg)
+    air = airs.mimc128(steps)
+    ctl = airs.run_mimc(steps, airs.mimc_round_constants(), seed)
+    a = [dict(step=0, register=0, value=ctl[0]), dict(step=steps - 1, register=0, value=ctl[-1])]
+    return air, opts, a, [seed]
+
+
+@pytest.mark.parametrize('steps,e,alg', [(64, 8, 'blake2s256'), (64, 16, 'sha256'), (256, 16, 'blake2s256'),
+                                         (1024, 8, 'sha256'), (2**13, 8, 'blake2s256')])
+def test_mimc_proof_bytes_match_oracle(steps, e, alg):
+    air, opts, a, seed = _mimc_case(steps, e, alg)
+    gpu = Stark(air, opts)
+    gpu._set_debug(True)
+    got = gpu.prove_bytes(a, [], seed)
+    ora = OracleStark(air, opts)
+    tr = {}
+    want_proof = ora.prove(a, [], seed, trace_out=tr)
+    n = steps * e
+    # stage-level parity first (sharper failure messages)
+    assert gpu._read_intermediate(3) == [v for row in tr['p_polys'] for v in row], 'P(x) coefficients'
+    assert gpu._read_intermediate(0) == [v for row in tr['p_evaluations'] for v in row], 'P(x) evaluations'
+    assert gpu._read_intermediate(1) == tr['c_evaluations'], 'C(x)'
+    assert gpu._read_intermediate(2) == tr['l_evaluations'], 'L(x)'
+    want = ora.serialize(want_proof)
+    assert got == want
+    # the reference verifier logic accepts the GPU proof; round trip through parse/serialize
+    proof = gpu.parse(got)
+    assert gpu.serialize(proof) == got
+    assert gpu.sizeOf(proof) == len(got)
+    assert ora.verify(a, ora.parse(got))
+
+
+def test_wrong_assertion_is_rejected_like_the_reference():
+    air, opts, a, seed = _mimc_case(64, 8)
+    gpu = Stark(air, opts)
+    bad = [dict(a[0]), dict(a[1], value=(a[1]['value'] + 1))]
+    with pytest.raises(StarkError, match='conflicts with execution trace'):
+        gpu.prove_bytes(bad, [], seed)
+    with pytest.raises(TypeError):
+        gpu.prove_bytes([], [], seed)
+
+
+def test_north_star_shape_proof_verifies_under_oracle_verifier():
+    """2^16 steps: too slow for the Python oracle prover, but its verifier is O(queries log N)."""
+    air, opts, a, seed = _mimc_case(2**16, 8)
+    gpu = Stark(air, opts)
+    got = gpu.prove_bytes(a, [], seed)
+    ora = OracleStark(air, opts)
+    assert ora.verify(a, ora.parse(got))
+    assert gpu.securityLevel == ora.security_level
