@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- MiMC-128 prove() on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+A "step" is one Stark.prove() of the north-star workload (MiMC over p128, 2^20 steps, extension factor 8,
+blake2s256, 48 trace / 24 FRI queries: examples/mimc/mimc128.ts:22-28 with the E of BASELINE.json's target).
+  value        ms per prove with the execution trace already resident in HBM (CUDA events on the prover stream)
+  e2e.value    ms per prove through the public API from host inputs to host-resident proof bytes
+               (host trace generation + H2D of the trace + every D2H inside the timed region)
+  roofline     dominant kernel class of the step: algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline the oracle port of the same path on the host cores (bounded sample), N=1 rank 0 only
+`--impl reference` times that CPU port alone (the reference itself needs node + npm packages that this
+image does not have: SURVEY.md §8c).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG_STEPS = int(os.environ.get('GS_BENCH_LOG_STEPS', '20'))
+EXT = int(os.environ.get('GS_BENCH_EXT', '8'))
+OPTS = dict(hashAlgorithm='blake2s256', extensionFactor=EXT, exeQueryCount=48, friQueryCount=24)
+METRIC = 'mimc128_prove_ms'
+
+
+def workload_name(log_steps=LOG_STEPS, ext=EXT):
+    return f'MiMC-128 prove(), 2^{log_steps} steps, extensionFactor {ext}, blake2s256, 48/24 queries (north-star target)'
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), 'measured'
+        except Exception:
+            pass
+    return {'hbm_gbs': 6650.0}, 'fallback'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], s[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def mimc_case(log_steps):
+    from genstark_b200 import airs
+    steps = 1 << log_steps
+    air = airs.mimc128(steps)
+    return air, steps
+
+
+def mimc_assertions(steps, seed=3):
+    """control values via the native library's scalar ops would be slow in Python for 2^20 steps; use the
+    closed loop in Python ints (examples/mimc/utils.ts:7-14) -- outside every timed region."""
+    from genstark_b200 import airs
+    from genstark_b200.air import P128
+    k = airs.mimc_round_constants()
+    x = seed % P128
+    for i in range(steps - 1):
+        x = (x * x % P128 * x + k[i & 63]) % P128
+    return [dict(step=0, register=0, value=seed), dict(step=steps - 1, register=0, value=x)]
+
+
+# ------------------------------------------------------------------------------------------ CPU port
+def cpu_port_prove_ms(log_steps, ext, threads=None):
+    """time the oracle's prove() on the host.  Prefers the compiled C port (oracle/_build), else the
+    Python restatement (single thread)."""
+    try:
+        from oracle import cport
+        if cport.available():
+            return cport.time_mimc_prove(log_steps, ext, threads)
+    except Exception as e:        # pragma: no cover
+        print(f'[bench] C port unavailable: {e}', file=sys.stderr)
+    from genstark_b200 import airs
+    from oracle.stark import Stark as OracleStark
+    steps = 1 << log_steps
+    air = airs.mimc128(steps)
+    st = OracleStark(air, dict(OPTS, extensionFactor=ext))
+    a = mimc_assertions(steps)
+    t = time.perf_counter()
+    st.prove(a, [], [3])
+    return (time.perf_counter() - t) * 1e3, 1, 'python'
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # bounded sample: the Python port cannot run 2^20 steps in minutes; the C port can
+    try:
+        from oracle import cport
+        have_c = cport.available()
+    except Exception:
+        have_c = False
+    log_steps = LOG_STEPS if have_c else 12
+    times = []
+    cores = 1
+    kind = 'python'
+    for i in range(args.warmup + args.steps):
+        ms, cores, kind = cpu_port_prove_ms(log_steps, EXT, None)
+        if i >= args.warmup:
+            times.append(ms)
+    ms = sum(times) / len(times)
+    scale = 1.0
+    sample = f'prove() of MiMC-128 2^{log_steps} steps E={EXT} ({kind} oracle port)'
+    if log_steps != LOG_STEPS:
+        # N log N extrapolation to the named workload, stated as such
+        n0, n1 = (1 << log_steps) * EXT, (1 << LOG_STEPS) * EXT
+        scale = (n1 * (LOG_STEPS + 3)) / (n0 * (log_steps + 3))
+        sample += f'; value extrapolated x{scale:.0f} by N log N to 2^{LOG_STEPS} steps'
+    v = ms * scale
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'ms', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': v, 'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'u128 (integer mod p)', 'data': 'synthetic',
+            'config': {'workload': workload_name(), 'parallelism': 'cpu'},
+            'cpu_baseline': {'value': v, 'unit': 'ms', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': v, 'unit': 'ms', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'note': 'the reference (genSTARK + galois/merkle/air-assembly WASM) cannot run here: no node in the image'}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def algorithmic_bytes(cls, log_t, log_e, r, s, n_boundary):
+    """SURVEY.md §8d / App. A.9 per-unit figures x units of ONE prove, per kernel class."""
+    T, N = 1 << log_t, 1 << (log_t + log_e)
+    B, D = 16, 32
+    fri = []
+    L = N
+    while True:
+        fri.append(L)
+        if L <= 256:
+            break
+        L >>= 2
+    if cls.startswith('ntt'):
+        # iNTT(T) + LDE(T -> N) for R (+S) rows: 32 B/point of the transform actually computed
+        return (r + s) * (2 * B * T + B * (T + N))
+    if cls == 'hash_columns':
+        return N * ((r + s) * B + D) + sum((l // 4) * (4 * B + D) for l in fri)
+    if cls == 'merkle_build':
+        return 2 * N * D + sum(2 * (l // 4) * D for l in fri)      # read 2 digests / write 1 per node ~ 2n*32... counted as 64 B/leaf
+    if cls == 'compose':
+        return N * B * (r + s + n_boundary + 1)
+    if cls in ('batch_inverse', 'zb_eval'):
+        return n_boundary * N * 2 * B
+    if cls == 'fri_fold':
+        return sum(B * l + B * l // 4 for l in fri[:-1])
+    return 0
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    from genstark_b200.field import Context, GpuField
+    from genstark_b200.stark import Stark
+    from genstark_b200 import _native
+    L = _native.lib()
+
+    air, steps = mimc_case(LOG_STEPS)
+    ctx = Context(local_rank)
+    st = Stark(air, dict(OPTS), context=ctx)
+    assertions = mimc_assertions(steps)
+    seed = [3]
+
+    # warm-up (also allocates every buffer)
+    for _ in range(max(args.warmup, 3)):
+        proof = st.prove_bytes(assertions, [], seed)
+    proof_len = len(proof)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- e2e leg: public API, host inputs -> host proof bytes
+    barrier()
+    launches0 = ctx.launch_count
+    t0 = time.perf_counter()
+    e2e_dev = []
+    for _ in range(args.steps):
+        st.prove_bytes(assertions, [], seed)
+        e2e_dev.append(st.last_timing())
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    launches_per_step = (ctx.launch_count - launches0) // args.steps
+    stage_times = st.stage_times()
+
+    # ---- resident leg: trace already in HBM; CUDA events on the prover stream; per-class kernel events
+    barrier()
+    L.gs_ctx_profile(ctx.handle, 1)
+    dev_ms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st.prove_bytes(assertions, [], seed, _reuse_resident_trace=True)
+        dev_ms.append(st.last_timing()[0])
+    barrier()
+    wall_resident = (time.perf_counter() - t0) * 1e3 / args.steps
+    prof = json.loads(L.gs_ctx_profile_report(ctx.handle).decode())
+    L.gs_ctx_profile(ctx.handle, 0)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    ms_step = sum(dev_ms) / len(dev_ms)
+    if dist is not None:
+        t = torch.tensor([ms_step, e2e_ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- K1 alone: NTT throughput (second half of BASELINE.json's metric)
+    ntt = {}
+    if rank == 0:
+        f = GpuField(ctx)
+        import random
+        r = random.Random(0xB200)
+        for name, log_t, log_n, inv in (('ntt_fwd_2^23', 23, 23, 0), ('lde_2^20_to_2^23', 20, 23, 0), ('intt_2^20', 20, 20, 1)):
+            t_, n_ = 1 << log_t, 1 << log_n
+            # uniform 127-bit residues (canonical: top bit of every element cleared)
+            ba = bytearray(r.randbytes(16 * t_))
+            ba[15::16] = bytes(x & 0x7F for x in ba[15::16])
+            src = f._from_bytes(bytes(ba), 1, t_)
+            dst, work = C.c_void_p(), C.c_void_p()
+            ctx.check(L.gs_mat_alloc(ctx.handle, 1, n_, C.byref(dst)))
+            ctx.check(L.gs_mat_alloc(ctx.handle, 1, n_, C.byref(work)))
+            ms = C.c_float()
+            best = []
+            for i in range(8):
+                L.gs_timer_begin(ctx.handle)
+                ctx.check(L.gs_ntt_into(ctx.handle, src.handle, dst, work, inv))
+                L.gs_timer_end(ctx.handle, C.byref(ms))
+                if i >= 3:
+                    best.append(ms.value)
+            med = sorted(best)[len(best) // 2]
+            alg_bytes = 16 * (t_ + n_)
+            ntt[name] = {'ms': round(med, 4), 'elements_per_s': n_ / (med * 1e-3), 'algorithmic_GBps': alg_bytes / (med * 1e-3) / 1e9}
+            L.gs_mat_free(dst); L.gs_mat_free(work); src.free()
+
+    if rank != 0:
+        return
+
+    peaks, peak_kind = measured_peaks()
+    hbm = float(peaks.get('hbm_gbs', 6650.0))
+    # dominant kernel class of the resident step
+    per_step = {k: v['ms'] / args.steps for k, v in prof.items()}
+    # group the K1 passes
+    grouped = {}
+    for k, v in per_step.items():
+        key = 'ntt' if k.startswith('ntt') else k
+        grouped[key] = grouped.get(key, 0.0) + v
+    dom = max(grouped, key=grouped.get)
+    log_t, log_e = LOG_STEPS, EXT.bit_length() - 1
+    alg = algorithmic_bytes(dom, log_t, log_e, air.trace_register_count, air.secret_input_count, 1)
+    achieved = alg / (grouped[dom] * 1e-3) / 1e9
+    traffic = None
+    summ = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
+    if os.path.exists(summ):
+        try:
+            traffic = json.load(open(summ)).get(dom, {}).get('dram_bytes_per_step')
+        except Exception:
+            traffic = None
+    roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
+                'traffic': traffic, 'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs)',
+                'kernel_ms_per_step': grouped[dom], 'algorithmic_bytes_per_step': alg,
+                'share_of_step': grouped[dom] / ms_step,
+                'note': '128-bit modular arithmetic on 32-bit integer pipes: every kernel here is issue-bound, not HBM-bound'}
+
+    cpu = None
+    if world == 1:
+        try:
+            from oracle import cport
+            have_c = cport.available()
+        except Exception:
+            have_c = False
+        ls = LOG_STEPS if have_c else 12
+        ms_cpu, cores, kind = cpu_port_prove_ms(ls, EXT, None)
+        sample = f'one prove() of MiMC-128 2^{ls} steps E={EXT} by the {kind} oracle port'
+        if ls != LOG_STEPS:
+            n0, n1 = (1 << ls) * EXT, (1 << LOG_STEPS) * EXT
+            sc = (n1 * (LOG_STEPS + 3)) / (n0 * (ls + 3))
+            ms_cpu *= sc
+            sample += f', extrapolated x{sc:.0f} (N log N) to 2^{LOG_STEPS} steps'
+        cpu = {'value': ms_cpu, 'unit': 'ms', 'cores': cores, 'kind': 'port', 'sample': sample}
+
+    trace_bytes = air.trace_register_count * steps * 16
+    value = ms_step / world if world > 1 else ms_step
+    e2e_val = e2e_ms / world if world > 1 else e2e_ms
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'ms', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_step, 'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'u128 (integer mod p = 2^128 - 9*2^32 + 1, 4x u32 limbs)', 'data': 'synthetic',
+        'config': {'workload': workload_name(), 'parallelism': 'single GPU' if world == 1 else f'{world} independent proofs (replicas), value = ms per proof aggregate',
+                   'l2': 'working set (>= 128 MiB per vector, ~1.4 GiB per prove) exceeds the 126 MB L2; no explicit flush',
+                   'proof_bytes': proof_len},
+        'e2e': {'value': e2e_val, 'unit': 'ms', 'h2d_bytes_per_step': trace_bytes + 4096, 'd2h_bytes_per_step': proof_len + 32 * 12,
+                'device_ms_inside': sum(d for d, _ in e2e_dev) / len(e2e_dev), 'host_ms_inside': sum(h for _, h in e2e_dev) / len(e2e_dev),
+                'stages_ms': stage_times},
+        'gpu_launches': int(launches_per_step),
+        'roofline': roofline,
+        'cpu_baseline': cpu,
+        'kernels_ms_per_step': {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
+        'resident_wall_ms': wall_resident,
+        'ntt': ntt,
+        'clocks': sampler.summary(),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -49,6 +49,13 @@ def lib() -> C.CDLL:
         'gs_stark_create': (i32, [vp, cp, C.c_size_t, i32, i32, i32, P(vp)]),
         'gs_stark_destroy': (None, [vp]),
         'gs_stark_prove': (i32, [vp, cp, i32, cp, cp, cp, C.c_size_t, P(P(C.c_uint8)), P(C.c_size_t)]),
+        'gs_stark_prove_ex': (i32, [vp, cp, i32, cp, cp, cp, C.c_size_t, i32, P(P(C.c_uint8)), P(C.c_size_t)]),
+        'gs_stark_last_timing': (i32, [vp, P(C.c_float), P(C.c_double)]),
+        'gs_ctx_profile': (i32, [vp, i32]),
+        'gs_ctx_profile_report': (cp, [vp]),
+        'gs_timer_begin': (i32, [vp]),
+        'gs_timer_end': (i32, [vp, P(C.c_float)]),
+        'gs_ntt_into': (i32, [vp, vp, vp, vp, i32]),
         'gs_stark_stage_times': (cp, [vp]),
         'gs_stark_set_debug': (i32, [vp, i32]),
         'gs_stark_read_intermediate': (i32, [vp, i32, vp, C.c_size_t]),

@@ -308,6 +308,12 @@ int gs_stark_set_debug(gs_stark* s, int keep_intermediates) {
 int gs_stark_prove(gs_stark* s, const uint8_t* assertions, int n_assertions, const uint8_t* init_state16,
                    const uint8_t* input_traces, const uint8_t* shapes_blob, size_t shapes_len,
                    const uint8_t** proof_out, size_t* proof_len) {
+    return gs_stark_prove_ex(s, assertions, n_assertions, init_state16, input_traces, shapes_blob, shapes_len, 0, proof_out, proof_len);
+}
+
+int gs_stark_prove_ex(gs_stark* s, const uint8_t* assertions, int n_assertions, const uint8_t* init_state16,
+                      const uint8_t* input_traces, const uint8_t* shapes_blob, size_t shapes_len, int flags,
+                      const uint8_t** proof_out, size_t* proof_len) {
     if (!s || !assertions || !init_state16 || !proof_out || !proof_len) return s ? s->ctx->fail(GS_E_ARG, "null argument") : GS_E_ARG;
     Ctx* c = s->ctx;
     if ((s->n_secret + s->n_public) > 0 && !input_traces) return c->fail(GS_E_ARG, "input register traces required");
@@ -319,10 +325,65 @@ int gs_stark_prove(gs_stark* s, const uint8_t* assertions, int n_assertions, con
     }
     std::vector<u128> init(s->R);
     for (int r = 0; r < s->R; ++r) { fp v; memcpy(&v, init_state16 + 16 * r, 16); init[r] = fp_to_u128(v); if (init[r] >= HP) return c->fail(GS_E_ARG, "non-canonical initial state"); }
-    int rc = stark_prove(s, as.data(), n_assertions, init.data(), (const fp*)input_traces, shapes_blob, shapes_len, s->proof);
+    int rc = stark_prove(s, as.data(), n_assertions, init.data(), (const fp*)input_traces, shapes_blob, shapes_len, s->proof, flags);
     if (rc != GS_OK) return rc;
     *proof_out = s->proof.data(); *proof_len = s->proof.size();
     return GS_OK;
+}
+
+int gs_stark_last_timing(gs_stark* s, float* device_ms, double* host_ms) {
+    if (!s) return GS_E_ARG;
+    if (device_ms) *device_ms = s->last_device_ms;
+    if (host_ms) *host_ms = s->last_host_ms;
+    return GS_OK;
+}
+
+int gs_ctx_profile(gs_ctx* c, int on) {
+    if (!c) return GS_E_ARG;
+    c->profiling = on != 0;
+    if (on) { c->prof_acc.clear(); }
+    return GS_OK;
+}
+
+const char* gs_ctx_profile_report(gs_ctx* c) {
+    if (!c) return "";
+    cudaStreamSynchronize(c->stream);
+    c->prof_collect();
+    std::string j = "{";
+    bool first = true;
+    for (auto& kv : c->prof_acc) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s\"%s\": {\"groups\": %llu, \"ms\": %.5f}", first ? "" : ", ", c->prof_names[kv.first].c_str(), kv.second.first, kv.second.second);
+        j += buf; first = false;
+    }
+    c->prof_json = j + "}";
+    return c->prof_json.c_str();
+}
+
+int gs_timer_begin(gs_ctx* c) {
+    if (!c) return GS_E_ARG;
+    if (!c->timer_a) { cudaEventCreate(&c->timer_a); cudaEventCreate(&c->timer_b); }
+    GS_CUDA(c, cudaEventRecord(c->timer_a, c->stream));
+    return GS_OK;
+}
+
+int gs_timer_end(gs_ctx* c, float* ms) {
+    if (!c || !ms || !c->timer_a) return GS_E_ARG;
+    GS_CUDA(c, cudaEventRecord(c->timer_b, c->stream));
+    GS_CUDA(c, cudaEventSynchronize(c->timer_b));
+    GS_CUDA(c, cudaEventElapsedTime(ms, c->timer_a, c->timer_b));
+    return GS_OK;
+}
+
+/* in-place transform into a caller-provided output (no allocation inside the timed region) */
+int gs_ntt_into(gs_ctx* c, const gs_mat* src, gs_mat* dst, gs_mat* work, int inverse) {
+    if (!c || !src || !dst) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    const int log_t = ilog2_exact(src->cols), log_n = ilog2_exact(dst->cols);
+    if (log_t < 1 || log_n < log_t || dst->rows != src->rows) return c->fail(GS_E_ARG, "shape mismatch");
+    if (work && (work->rows != dst->rows || work->cols != dst->cols)) return c->fail(GS_E_ARG, "work shape mismatch");
+    cudaSetDevice(c->device);
+    return ntt_run(c, src->data, src->cols, dst->data, dst->cols, work ? work->data : nullptr, dst->cols, (int)src->rows, log_t,
+                   log_n - log_t, inverse != 0);
 }
 
 const char* gs_stark_stage_times(gs_stark* s) {

@@ -45,6 +45,7 @@ static inline int batch_inverse(Ctx* c, const fp* in, fp* out, fp* scratch, long
     const long long min_threads = (long long)c->sm_count * 256;
     if (nthreads < min_threads) nthreads = n < min_threads ? n : min_threads;
     const unsigned blocks = (unsigned)((nthreads + 255) / 256);
+    ProfScope ps(c, "batch_inverse");
     batch_inverse_kernel<<<blocks, 256, 0, c->stream>>>(in, out, scratch, n, nthreads);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return c->cuda_fail(e, "batch_inverse_kernel");

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <map>
 #include <cuda_runtime.h>
 #include "fp128.cuh"
 #include "../../include/genstark_b200.h"
@@ -42,6 +43,31 @@ struct Ctx {
     size_t mailbox_bytes = 0;
     int sm_count = 148;
     unsigned long long launches = 0;   // kernels launched through this context (bench.py gpu_launches)
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+    // per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
+    bool profiling = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> prof_pool;
+    std::vector<std::string> prof_names;
+    std::map<int, std::pair<unsigned long long, double>> prof_acc;   // class -> (launch groups, ms)
+    std::string prof_json;
+    int prof_class(const char* name) {
+        for (size_t i = 0; i < prof_names.size(); ++i) if (prof_names[i] == name) return (int)i;
+        prof_names.push_back(name); return (int)prof_names.size() - 1;
+    }
+    cudaEvent_t prof_event() {
+        if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    // call after the stream is synchronized
+    void prof_collect() {
+        for (auto& r : prof_recs) {
+            float ms = 0; if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto& acc = prof_acc[r.cls]; acc.first++; acc.second += ms; }
+            prof_pool.push_back(r.a); prof_pool.push_back(r.b);
+        }
+        prof_recs.clear();
+    }
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -65,6 +91,17 @@ struct Ctx {
     u128 root_pow(u128 e) const { return h_pow(root_g, e); }
     // primitive root of order 2^log_n from the same family
     u128 root_of_order(int log_n) const { return h_pow(root_g, (u128)1 << (log_g - log_n)); }
+};
+
+struct ProfScope {
+    Ctx* c; int idx = -1;
+    ProfScope(Ctx* ctx, const char* name) : c(ctx) {
+        if (!c->profiling) return;
+        Ctx::ProfRec r; r.cls = c->prof_class(name); r.a = c->prof_event(); r.b = c->prof_event();
+        cudaEventRecord(r.a, c->stream);
+        c->prof_recs.push_back(r); idx = (int)c->prof_recs.size() - 1;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(c->prof_recs[idx].b, c->stream); }
 };
 
 #define GS_CUDA(ctx, call)                                              \

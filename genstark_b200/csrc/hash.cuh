@@ -239,6 +239,7 @@ static inline unsigned grid_for(Ctx* c, long long n, int threads, int waves = 8)
 static inline int hash_columns(Ctx* c, int alg, const HashCols& cols, long long n, uint32_t* out) {
     if (cols.ncols < 1 || cols.ncols > GS_MAX_HASH_COLS) return c->fail(GS_E_ARG, "1..%d columns per leaf", GS_MAX_HASH_COLS);
     const unsigned g = grid_for(c, n, 256);
+    ProfScope ps(c, "hash_columns");
     if (alg == HASH_BLAKE2S) hash_columns_kernel<HASH_BLAKE2S><<<g, 256, 0, c->stream>>>(cols, n, out);
     else if (alg == HASH_SHA256) hash_columns_kernel<HASH_SHA256><<<g, 256, 0, c->stream>>>(cols, n, out);
     else return c->fail(GS_E_ARG, "unknown hash algorithm");
@@ -264,6 +265,7 @@ static inline int hash_rows(Ctx* c, int alg, const void* buf, int row_bytes, lon
 static inline int merkle_build(Ctx* c, int alg, uint32_t* nodes, long long n) {
     if (alg != HASH_BLAKE2S && alg != HASH_SHA256) return c->fail(GS_E_ARG, "unknown hash algorithm");
     long long count = n >> 1;
+    ProfScope ps(c, "merkle_build");
     while (count > 1024) {
         const unsigned g = grid_for(c, count, 256);
         if (alg == HASH_BLAKE2S) merkle_level_kernel<HASH_BLAKE2S><<<g, 256, 0, c->stream>>>(nodes, count);

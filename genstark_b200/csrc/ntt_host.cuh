@@ -122,6 +122,8 @@ static inline int ntt_run(Ctx* c, const fp* src, long long src_stride, fp* dst, 
         if (threads > 256) threads = 256;
         if (threads < 32) threads = 32;
         size_t smem = ((size_t)(1 << lr) + (size_t)(1 << lr) * ((1 << log_c) + 1)) * sizeof(fp);
+        ProfScope ps(c, fin ? (log_e > 0 ? "ntt_final_lde" : (inverse ? "ntt_final_inv" : "ntt_final_fwd"))
+                               : (P.coset_log_ntot > 0 ? "ntt_column_coset" : "ntt_column"));
         cudaError_t e = launch_pass(lr, P, grid, threads, smem, c->stream);
         if (e != cudaSuccess) return c->cuda_fail(e, "ntt_pass_kernel");
         c->launches++;

@@ -66,10 +66,16 @@ struct Stark {
     void* h_trace = nullptr; size_t h_trace_bytes = 0;     // pinned
     StageTimes last_times;
     bool keep_intermediates = false;  // stage-level parity tests read P/C/L back
+    bool trace_resident = false;      // d_trace / d_in_trace hold the last proved trace
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_device_ms = 0;         // CUDA-event time from the first enqueue to the last kernel of prove()
+    double last_host_ms = 0;          // wall clock of the whole call
     ~Stark() {
         for (DevBuf* b : {&d_instrs, &d_consts, &d_cyc, &d_trace, &d_poly, &d_pe, &d_in_trace, &d_in_poly, &d_in_e, &d_work, &d_tree,
                           &d_zb, &d_zbs, &d_l, &d_c, &d_fri, &d_fri_trees, &d_params, &d_small, &d_idx, &d_gather}) b->release();
         if (h_trace) cudaFreeHost(h_trace);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
     }
 };
 
@@ -207,7 +213,7 @@ static inline std::vector<uint32_t> first_seen_unique(const std::vector<uint32_t
 // inputs: initial state (R elements), input register traces (n_input x T, register order), shapes blob
 static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, const u128* init_state,
                               const fp* input_traces, const uint8_t* shapes_blob, size_t shapes_len,
-                              std::vector<uint8_t>& proof_out) {
+                              std::vector<uint8_t>& proof_out, int flags = 0) {
     Ctx* c = S->ctx;
     cudaSetDevice(c->device);
     StageTimes& tm = S->last_times; tm.items.clear();
@@ -227,8 +233,12 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     if (N < 128) return c->fail(GS_E_STARK, "Low degree proof failed: Invalid array length");
     int rc;
 
+    const double t_call = now_ms();
+    const bool reuse_trace = (flags & 1) && S->trace_resident;
+    if (!S->ev0) { cudaEventCreate(&S->ev0); cudaEventCreate(&S->ev1); }
     // 1-2 ---- execution trace on the host (sequential in steps), checked against the assertions
     const size_t trace_bytes = (size_t)R * T * sizeof(fp);
+    if (!reuse_trace) {
     if (S->h_trace_bytes < trace_bytes) {
         if (S->h_trace) cudaFreeHost(S->h_trace);
         GS_CUDA(c, cudaHostAlloc(&S->h_trace, trace_bytes, cudaHostAllocDefault));
@@ -258,15 +268,17 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
                 return c->fail(GS_E_STARK, "Failed to generate the execution trace: Assertion at step %u, register %u conflicts with execution trace", asserts[a].step, asserts[a].reg);
         }
     }
+    }
     mark("Generated execution trace", false);
 
     // 3 ---- P(x) = iNTT(trace); low-degree extension over the evaluation domain
+    cudaEventRecord(S->ev0, c->stream);
     if ((rc = S->d_trace.ensure(c, trace_bytes))) return rc;
     if ((rc = S->d_poly.ensure(c, trace_bytes))) return rc;
     if ((rc = S->d_pe.ensure(c, (size_t)R * N * sizeof(fp)))) return rc;
     const int wrows = R > n_in ? R : (n_in > 0 ? n_in : 1);
     if ((rc = S->d_work.ensure(c, (size_t)wrows * N * sizeof(fp)))) return rc;
-    GS_CUDA(c, cudaMemcpyAsync(S->d_trace.p, S->h_trace, trace_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (!reuse_trace) GS_CUDA(c, cudaMemcpyAsync(S->d_trace.p, S->h_trace, trace_bytes, cudaMemcpyHostToDevice, c->stream));
     if ((rc = ntt_run(c, S->d_trace.as<fp>(), T, S->d_poly.as<fp>(), T, S->d_work.as<fp>(), T, R, log_t, 0, true))) return rc;
     if (timing) mark("Computed execution trace polynomials P(x)", true);
     if ((rc = ntt_run(c, S->d_poly.as<fp>(), T, S->d_pe.as<fp>(), N, S->d_work.as<fp>(), N, R, log_t, log_e, false))) return rc;
@@ -276,7 +288,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         if ((rc = S->d_in_trace.ensure(c, in_bytes))) return rc;
         if ((rc = S->d_in_poly.ensure(c, in_bytes))) return rc;
         if ((rc = S->d_in_e.ensure(c, (size_t)n_in * N * sizeof(fp)))) return rc;
-        GS_CUDA(c, cudaMemcpyAsync(S->d_in_trace.p, input_traces, in_bytes, cudaMemcpyHostToDevice, c->stream));
+        if (!reuse_trace) GS_CUDA(c, cudaMemcpyAsync(S->d_in_trace.p, input_traces, in_bytes, cudaMemcpyHostToDevice, c->stream));
         if ((rc = ntt_run(c, S->d_in_trace.as<fp>(), T, S->d_in_poly.as<fp>(), T, S->d_work.as<fp>(), T, n_in, log_t, 0, true))) return rc;
         if ((rc = ntt_run(c, S->d_in_poly.as<fp>(), T, S->d_in_e.as<fp>(), N, S->d_work.as<fp>(), N, n_in, log_t, log_e, false))) return rc;
     }
@@ -399,7 +411,8 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         ZbParams zp; zp.n = N; zp.log_n = log_n; zp.n_boundary = nB;
         zp.zpoly_off = (const int*)(ds + o_zo); zp.zpoly_len = (const int*)(ds + o_zl); zp.zpoly = (const fp*)(ds + o_zp);
         zp.tw_lo = c->tw_lo; zp.tw_hi = c->tw_hi; zp.log_g = c->log_g; zp.log_lo = c->log_lo; zp.out = S->d_zb.as<fp>();
-        zb_eval_kernel<<<grid_for(c, N, 256), 256, 0, c->stream>>>(zp);
+        { ProfScope ps(c, "zb_eval");
+        zb_eval_kernel<<<grid_for(c, N, 256), 256, 0, c->stream>>>(zp); }
         c->launches++;
         if ((rc = batch_inverse(c, S->d_zb.as<fp>(), S->d_zb.as<fp>(), S->d_zbs.as<fp>(), (long long)nB * N))) return rc;
     }
@@ -430,6 +443,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         GS_CUDA(c, cudaMemcpyAsync(S->d_params.p, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
         const unsigned g = grid_for(c, N, 256);
         const int ns = S->evaluation.n_slots;
+        ProfScope ps(c, "compose");
         if (ns <= 8) compose_kernel<8><<<g, 256, 0, c->stream>>>(S->d_params.as<ComposeParams>());
         else if (ns <= 32) compose_kernel<32><<<g, 256, 0, c->stream>>>(S->d_params.as<ComposeParams>());
         else if (ns <= 128) compose_kernel<128><<<g, 256, 0, c->stream>>>(S->d_params.as<ComposeParams>());
@@ -499,7 +513,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         FriFoldParams F; F.v = v_cur; F.out = v_next; F.quarter = Q; F.special_x = d_special;
         F.tw_lo = c->tw_lo; F.tw_hi = c->tw_hi; F.log_g = c->log_g; F.log_lo = c->log_lo;
         F.x_shift = 2 * depth + (c->log_g - log_n); F.iota_inv = fp_from_u128(iota_inv); F.quarter_inv = fp_from_u128(quarter_inv);
-        fri_fold_kernel<<<grid_for(c, Q, 256), 256, 0, c->stream>>>(F);
+        { ProfScope ps(c, "fri_fold"); fri_fold_kernel<<<grid_for(c, Q, 256), 256, 0, c->stream>>>(F); }
         c->launches++;
         v_cur = v_next; v_next += Q;
         max_deg_p1 /= 4;
@@ -551,6 +565,11 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     BatchProof ev_proof;
     if ((rc = device_merkle_proof(S, e_tree, (uint64_t)N, aug_pos, ev_proof, err))) return rc;
     if ((rc = device_gather_rows(S, e_cols, aug_pos, ev_proof.values))) return rc;
+    cudaEventRecord(S->ev1, c->stream);
+    cudaEventSynchronize(S->ev1);
+    cudaEventElapsedTime(&S->last_device_ms, S->ev0, S->ev1);
+    S->trace_resident = true;
+    if (c->profiling) c->prof_collect();
     mark("Computed evaluation spot checks and Merkle proofs", false);
 
     // serialize (Serializer.ts:35-79)
@@ -573,6 +592,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     if (shapes_blob && shapes_len) out.insert(out.end(), shapes_blob, shapes_blob + shapes_len);
     else out.push_back(0);
     mark("Serialized proof", false);
+    S->last_host_ms = now_ms() - t_call;
     return GS_OK;
 }
 

@@ -94,7 +94,7 @@ class Stark:
         return math.floor(min(es, fs, hs))
 
     # PROVER ----------------------------------------------------------------------------------------
-    def prove_bytes(self, assertions: Sequence[dict], inputs=None, seed=None) -> bytes:
+    def prove_bytes(self, assertions: Sequence[dict], inputs=None, seed=None, _reuse_resident_trace: bool = False) -> bytes:
         """Stark.prove + serialize in one crossing: the serialized proof as produced on the device path."""
         if not isinstance(assertions, (list, tuple)):
             raise TypeError('Assertions parameter must be an array')
@@ -115,8 +115,8 @@ class Stark:
         shapes = air.input_shapes(inputs or [])
         s_blob = bytes([len(shapes)]) + b''.join(bytes([len(s)]) + b''.join(struct.pack('<I', x) for x in s) for s in shapes)
         out_p, out_n = C.POINTER(C.c_uint8)(), C.c_size_t()
-        rc = self._lib.gs_stark_prove(self._handle, a_blob, len(assertions), init_blob, in_blob, s_blob, len(s_blob),
-                                      C.byref(out_p), C.byref(out_n))
+        rc = self._lib.gs_stark_prove_ex(self._handle, a_blob, len(assertions), init_blob, in_blob, s_blob, len(s_blob),
+                                         1 if _reuse_resident_trace else 0, C.byref(out_p), C.byref(out_n))
         if rc == -4:
             raise StarkError(self._lib.gs_last_error(self.context.handle).decode())
         self.context.check(rc)
@@ -125,6 +125,12 @@ class Stark:
     def prove(self, assertions: Sequence[dict], inputs=None, seed=None) -> dict:
         """lib/Stark.ts:81-163 -> StarkProof {evRoot, evProof, ldProof, iShapes}"""
         return self.parse(self.prove_bytes(assertions, inputs, seed))
+
+    def last_timing(self):
+        """(CUDA-event ms of the device part, host wall-clock ms) of the last prove"""
+        d, h = C.c_float(), C.c_double()
+        self._lib.gs_stark_last_timing(self._handle, C.byref(d), C.byref(h))
+        return d.value, h.value
 
     def stage_times(self) -> List:
         return json.loads(self._lib.gs_stark_stage_times(self._handle).decode() or '[]')

@@ -92,6 +92,13 @@ void gs_stark_destroy(gs_stark* s);
 int gs_stark_prove(gs_stark* s, const uint8_t* assertions, int n_assertions, const uint8_t* init_state16,
                    const uint8_t* input_traces, const uint8_t* shapes_blob, size_t shapes_len,
                    const uint8_t** proof_out, size_t* proof_len);
+/* flags bit 0: reuse the execution trace already resident in HBM from the previous call (skips host trace
+ * generation and the host->device copy: the "inputs resident" measurement leg of bench.py) */
+int gs_stark_prove_ex(gs_stark* s, const uint8_t* assertions, int n_assertions, const uint8_t* init_state16,
+                      const uint8_t* input_traces, const uint8_t* shapes_blob, size_t shapes_len, int flags,
+                      const uint8_t** proof_out, size_t* proof_len);
+/* CUDA-event time of the device part and host wall clock of the last prove */
+int gs_stark_last_timing(gs_stark* s, float* device_ms, double* host_ms);
 /* per-stage host milliseconds of the last prove as JSON [[name, ms], ...] (Logger, lib/utils/Logger.ts) */
 const char* gs_stark_stage_times(gs_stark* s);
 /* test hooks: keep C(x) and read device-resident intermediates back (0 P evals, 1 C, 2 L, 3 P polys) */
@@ -99,6 +106,14 @@ int gs_stark_set_debug(gs_stark* s, int keep_intermediates);
 int gs_stark_read_intermediate(gs_stark* s, int which, void* out, size_t out_bytes);
 
 /* ---- measurement helpers ------------------------------------------------------------------------ */
+/* CUDA events on the context stream around every kernel class; report is JSON {class: {groups, ms}} */
+int gs_ctx_profile(gs_ctx* ctx, int on);
+const char* gs_ctx_profile_report(gs_ctx* ctx);
+int gs_timer_begin(gs_ctx* ctx);
+int gs_timer_end(gs_ctx* ctx, float* ms);
+/* transform src (rows x t) into dst (rows x n >= t) with caller-provided work (rows x n): n == t -> NTT or
+ * (inverse) iNTT; n > t -> LDE.  No allocation: used to time K1 alone. */
+int gs_ntt_into(gs_ctx* ctx, const gs_mat* src, gs_mat* dst, gs_mat* work, int inverse);
 /* runs blocks x 256 threads x (4*iters) dependent modular multiplications; returns kernel ms */
 int gs_debug_modmul_probe(gs_ctx* ctx, int blocks, int iters, float* ms_out);
 
