@@ -41,7 +41,7 @@ int gs_ctx_create(int device, gs_ctx** out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     int rc = ctx_init_tables(c);
     if (rc != GS_OK) { g_null_error = c->last_error; delete c; return rc; }
-    c->mailbox_bytes = 1 << 20;
+    c->mailbox_bytes = 8 << 20;
     if (cudaHostAlloc(&c->mailbox, c->mailbox_bytes, cudaHostAllocDefault) != cudaSuccess) {
         g_null_error = "cudaHostAlloc(mailbox)"; delete c; return GS_E_CUDA;
     }
@@ -219,34 +219,14 @@ int gs_stark_create(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int has
     if (exe_queries < 1 || exe_queries > 128) return c->fail(GS_E_ARG, "Execution sample size must be an integer between 1 and 128");
     if (fri_queries < 1 || fri_queries > 64) return c->fail(GS_E_ARG, "FRI sample size must be an integer between 1 and 64");
     cudaSetDevice(c->device);
-    BlobReader r{air_blob, blob_len};
-    if (r.u32() != 0x52494147u) return c->fail(GS_E_ARG, "bad AIR blob magic");
     std::unique_ptr<gs_stark> S(new gs_stark());
     S->ctx = c; S->hash_alg = hash_alg; S->exe_queries = exe_queries; S->fri_queries = fri_queries;
-    uint8_t modulus[16];
-    for (int i = 0; i < 4; ++i) { uint32_t w = r.u32(); memcpy(modulus + 4 * i, &w, 4); }
-    if (gs_field_supported(modulus, 16) != GS_OK) return c->fail(GS_E_UNSUPPORTED, "no native backend for this modulus (isOptimized = false)");
-    S->R = (int)r.u32(); S->K = (int)r.u32(); S->log_t = (int)r.u32(); S->log_e = (int)r.u32();
-    const uint32_t n_static = r.u32();
-    if (!r.ok || S->R < 1 || S->R > GS_MAX_COLS || S->K < 1 || S->K > GS_MAX_CONSTRAINTS || n_static > GS_MAX_COLS)
-        return c->fail(GS_E_UNSUPPORTED, "AIR shape out of range (registers %d, constraints %d, static %u)", S->R, S->K, n_static);
-    if (S->log_t < 2 || S->log_e < 1 || S->log_e > 5) return c->fail(GS_E_ARG, "trace length >= 4 and extension factor 2..32 required");
-    S->statics.resize(n_static);
-    for (auto& sr : S->statics) {
-        sr.kind = (int)r.u32();
-        const uint32_t len = r.u32();
-        if (!r.ok || len > (1u << 24)) return c->fail(GS_E_ARG, "bad static register");
-        sr.values.resize(len);
-        for (auto& v : sr.values) v = r.elem();
-        if (sr.kind == 0 && (len == 0 || (len & (len - 1)) || len > (1u << S->log_t))) return c->fail(GS_E_ARG, "cycle length must be a power of two <= steps");
-        if (sr.kind == 1) S->n_secret++;
-        if (sr.kind == 2) S->n_public++;
+    {
+        int code = GS_OK;
+        const std::string err = parse_air(air_blob, blob_len, S.get(), &code);
+        if (code != GS_OK) return c->fail(code, "%s", err.c_str());
     }
-    S->degrees.resize(S->K);
-    for (auto& d : S->degrees) d = (int)r.u32();
-    if (!read_program(r, S->transition) || !read_program(r, S->evaluation)) return c->fail(GS_E_ARG, "bad AIR program");
-    if (S->transition.n_out != S->R || S->evaluation.n_out != S->K) return c->fail(GS_E_ARG, "program outputs do not match the register / constraint counts");
-    for (auto& ins : S->evaluation.instrs) if (ins[0] == OP_EXP) return c->fail(GS_E_UNSUPPORTED, "exp with a large exponent in a constraint");
+    const uint32_t n_static = (uint32_t)S->statics.size();
     // device copies of the evaluation program
     int rc;
     const size_t ib = S->evaluation.instrs.size() * 16, cb = std::max<size_t>(S->evaluation.consts.size(), 1) * 16;
@@ -289,6 +269,20 @@ int gs_stark_create(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int has
         }
     }
     *out = S.release();
+    return GS_OK;
+}
+
+/* Stark.generateExecutionTrace (genstark.d.ts:109): host only, no device needed.  out: R x T x 16 bytes */
+int gs_air_generate_trace(const uint8_t* air_blob, size_t blob_len, const uint8_t* init_state16, const uint8_t* input_traces,
+                          uint8_t* out_trace) {
+    if (!air_blob || !init_state16 || !out_trace) return GS_E_ARG;
+    Stark S; int code = GS_OK;
+    const std::string err = parse_air(air_blob, blob_len, &S, &code);
+    if (code != GS_OK) { g_null_error = err; return code; }
+    if ((S.n_secret + S.n_public) > 0 && !input_traces) { g_null_error = "input register traces required"; return GS_E_ARG; }
+    std::vector<u128> init(S.R);
+    for (int r = 0; r < S.R; ++r) { fp v; memcpy(&v, init_state16 + 16 * r, 16); init[r] = fp_to_u128(v); }
+    generate_trace(&S, init.data(), (const fp*)input_traces, (fp*)out_trace);
     return GS_OK;
 }
 

@@ -15,14 +15,10 @@
 #pragma once
 #include "core.cuh"
 #include "ntt.cuh"
+#include "hostair.h"
 
 namespace gs {
 
-enum { OP_CONST = 0, OP_CUR = 1, OP_NEXT = 2, OP_STATIC = 3, OP_ADD = 4, OP_SUB = 5, OP_MUL = 6, OP_NEG = 7,
-       OP_INV = 8, OP_EXP = 9, OP_OUT = 10 };
-
-#define GS_MAX_COLS 64          // trace + static registers visible to a program
-#define GS_MAX_CONSTRAINTS 64
 #define GS_MAX_POWERS 8
 
 struct ComposeParams {

@@ -9,16 +9,22 @@
 // so that ptxas pairs every mad.lo.cc/madc.hi.cc into one IMAD.WIDE.U32 (16 per product).
 #pragma once
 #include <cstdint>
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#define GS_HD __host__ __device__ __forceinline__
+#define GS_D __device__ __forceinline__
+#define GS_ALIGN16 __align__(16)
+#else
+#define GS_HD inline
+#define GS_D inline
+#define GS_ALIGN16 alignas(16)
+#endif
 
 namespace gs {
 
-struct __align__(16) fp {
+struct GS_ALIGN16 fp {
     uint32_t v[4];
 };
-
-#define GS_HD __host__ __device__ __forceinline__
-#define GS_D __device__ __forceinline__
 
 // p and 2^128 - p
 static constexpr uint32_t P0 = 0x00000001u, P1 = 0xFFFFFFF7u, P2 = 0xFFFFFFFFu, P3 = 0xFFFFFFFFu;

@@ -70,4 +70,11 @@ __global__ void gather_digests_kernel(const uint32_t* __restrict__ nodes, const 
     if (q < nq) reinterpret_cast<uint4*>(out)[2 * q + half] = reinterpret_cast<const uint4*>(nodes)[2ll * idx[q] + half];
 }
 
+// out[t] = 16 bytes at addr[t]: the whole query phase (every queried row and Merkle node of every tree)
+// is one launch + one device->host copy
+__global__ void gather_chunks_kernel(const unsigned long long* __restrict__ addr, int n, uint4* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = *reinterpret_cast<const uint4*>(addr[t]);
+}
+
 }  // namespace gs

@@ -13,19 +13,10 @@
 #include "fri.cuh"
 #include "compose.cuh"
 #include "hostcrypto.h"
+#include "hostfield.h"
+#include "hostair.h"
 
 namespace gs {
-
-struct HostProgram {
-    std::vector<std::array<uint32_t, 4>> instrs;
-    std::vector<u128> consts;
-    int n_slots = 0, n_out = 0;
-};
-
-struct StaticReg {
-    int kind = 0;                 // 0 cycle, 1 secret input, 2 public input
-    std::vector<u128> values;     // cycle values
-};
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
@@ -45,17 +36,10 @@ struct StageTimes {                 // milliseconds, host wall clock around each
     std::vector<std::pair<std::string, double>> items;
 };
 
-struct Stark {
+struct Stark : public AirHost {
     Ctx* ctx = nullptr;
-    // AIR
-    int R = 0, K = 0, log_t = 0, log_e = 0;
-    std::vector<StaticReg> statics;
-    std::vector<int> degrees;
-    HostProgram transition, evaluation;
     // options
     int hash_alg = HASH_SHA256, exe_queries = 80, fri_queries = 40;
-    // derived
-    int n_secret = 0, n_public = 0;
     // device-resident program + cyclic tables
     DevBuf d_instrs, d_consts, d_cyc;
     std::vector<size_t> cyc_off;      // per static register (cycle kind): element offset into d_cyc
@@ -78,43 +62,6 @@ struct Stark {
         if (ev1) cudaEventDestroy(ev1);
     }
 };
-
-// ------------------------------------------------------------------------------ AIR blob (air.py)
-struct BlobReader {
-    const uint8_t* p; size_t n, off = 0; bool ok = true;
-    uint32_t u32() { if (off + 4 > n) { ok = false; return 0; } uint32_t v; memcpy(&v, p + off, 4); off += 4; return v; }
-    u128 elem() { if (off + 16 > n) { ok = false; return 0; } fp f; memcpy(&f, p + off, 16); off += 16; return fp_to_u128(f); }
-};
-
-static inline bool read_program(BlobReader& r, HostProgram& pr) {
-    uint32_t ni = r.u32(), nc = r.u32(); pr.n_slots = (int)r.u32(); pr.n_out = (int)r.u32();
-    if (!r.ok || ni > (1u << 20) || nc > (1u << 20)) return false;
-    pr.instrs.resize(ni);
-    for (auto& i : pr.instrs) for (int k = 0; k < 4; ++k) i[k] = r.u32();
-    pr.consts.resize(nc);
-    for (auto& c : pr.consts) c = r.elem();
-    return r.ok;
-}
-
-// host interpreter (trace generation): state -> next state
-static inline void run_transition(const HostProgram& pr, const u128* cur, const u128* statics, u128* slots, u128* out) {
-    for (const auto& ins : pr.instrs) {
-        const uint32_t op = ins[0], d = ins[1], a = ins[2], b = ins[3];
-        switch (op) {
-            case OP_CONST: slots[d] = pr.consts[a]; break;
-            case OP_CUR: slots[d] = cur[a]; break;
-            case OP_STATIC: slots[d] = statics[a]; break;
-            case OP_ADD: slots[d] = h_add(slots[a], slots[b]); break;
-            case OP_SUB: slots[d] = h_sub(slots[a], slots[b]); break;
-            case OP_MUL: slots[d] = h_mul(slots[a], slots[b]); break;
-            case OP_NEG: slots[d] = h_sub(0, slots[a]); break;
-            case OP_INV: slots[d] = h_inv(slots[a]); break;
-            case OP_EXP: slots[d] = h_pow(slots[a], pr.consts[b]); break;
-            case OP_OUT: out[d] = slots[a]; break;
-            default: break;
-        }
-    }
-}
 
 // Lagrange interpolation on the host (BoundaryConstraints.ts:42, LowDegreeProver.ts:243), low -> high
 static inline std::vector<u128> h_interpolate(const std::vector<u128>& xs, const std::vector<u128>& ys) {
@@ -246,21 +193,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     }
     {
         fp* tr = (fp*)S->h_trace;
-        std::vector<u128> state(init_state, init_state + R), next(R), slots(S->transition.n_slots + 1), stat(S->statics.size());
-        const u128* in_tr = nullptr; (void)in_tr;
-        for (long long s = 0; s < T; ++s) {
-            for (int r = 0; r < R; ++r) tr[(size_t)r * T + s] = fp_from_u128(state[r]);
-            if (s + 1 < T) {
-                int ii = 0;
-                for (size_t k = 0; k < S->statics.size(); ++k) {
-                    const StaticReg& sr = S->statics[k];
-                    if (sr.kind == 0) stat[k] = sr.values[s & (sr.values.size() - 1)];
-                    else stat[k] = fp_to_u128(input_traces[(size_t)(ii++) * T + s]);
-                }
-                run_transition(S->transition, state.data(), stat.data(), slots.data(), next.data());
-                state.swap(next);
-            }
-        }
+        generate_trace(S, init_state, input_traces, tr);
         for (int a = 0; a < n_assert; ++a) {
             if ((int)asserts[a].reg >= R) return c->fail(GS_E_STARK, "Failed to generate the execution trace: Invalid assertion: register %u is outside of register bank", asserts[a].reg);
             if (asserts[a].step >= (uint64_t)T) return c->fail(GS_E_STARK, "Failed to generate the execution trace: Invalid assertion: step %u is outside of execution trace", asserts[a].step);
@@ -520,56 +453,85 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     }
     mark("Computed low-degree proof (layers)", false);
 
-    // queries of the low-degree proof
+    // ---- query phase: every position depends only on the roots, so all rows and Merkle nodes of all trees
+    // are planned on the host, fetched by ONE gather kernel and ONE device->host copy
     std::string err;
     const uint8_t* lc_root = layers[0].root;
-    std::vector<uint32_t> exe_pos;
-    if (pseudorandom_indexes(lc_root, (int)std::min<long long>(S->exe_queries, N - N / E), (uint64_t)N, (uint64_t)E, exe_pos, err) != 0)
-        return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str());
-    auto rows_of = [&](const FriLayer& ly, const std::vector<uint32_t>& idx, std::vector<std::vector<uint8_t>>& vals) {
-        std::vector<const fp*> cols; for (int j = 0; j < 4; ++j) cols.push_back(ly.v + j * (ly.len >> 2));
-        return device_gather_rows(S, cols, idx, vals);
+    std::vector<unsigned long long> g_addr;
+    auto add_chunk = [&](const void* p) { g_addr.push_back((unsigned long long)(uintptr_t)p); return g_addr.size() - 1; };
+    struct PlannedProof { BatchProof bp; std::vector<size_t> node_chunk; std::vector<size_t> value_chunk; int chunks_per_value = 0; };
+    auto plan_proof = [&](PlannedProof& pp, const uint32_t* tree, uint64_t n, const std::vector<uint32_t>& idx,
+                          const std::vector<const fp*>& cols) -> int {
+        if (merkle_prove_plan(idx, n, pp.bp, err) != 0) return c->fail(GS_E_STARK, "%s", err.c_str());
+        for (auto& col : pp.bp.node_ids) for (uint32_t id : col) { pp.node_chunk.push_back(add_chunk(tree + 8ull * id)); add_chunk(tree + 8ull * id + 4); }
+        pp.chunks_per_value = (int)cols.size();
+        for (uint32_t i : idx) for (const fp* cp : cols) pp.value_chunk.push_back(add_chunk(cp + i));
+        return GS_OK;
     };
     auto aug4 = [&](const std::vector<uint32_t>& p, long long column_length) {
         std::vector<uint32_t> m(p.size()); const uint32_t row_len = (uint32_t)(column_length >> 2);
         for (size_t i = 0; i < p.size(); ++i) m[i] = p[i] % row_len;
         return first_seen_unique(m);
     };
-    BatchProof lc_proof;
-    {
-        const std::vector<uint32_t> lc_pos = aug4(exe_pos, N);
-        if ((rc = device_merkle_proof(S, layers[0].tree, (uint64_t)(N >> 2), lc_pos, lc_proof, err))) return rc;
-        if ((rc = rows_of(layers[0], lc_pos, lc_proof.values))) return rc;
-    }
-    struct Comp { const uint8_t* root; BatchProof column, poly; };
+    auto row_cols = [&](const FriLayer& ly) { std::vector<const fp*> cols; for (int j = 0; j < 4; ++j) cols.push_back(ly.v + j * (ly.len >> 2)); return cols; };
+    std::vector<uint32_t> exe_pos;
+    if (pseudorandom_indexes(lc_root, (int)std::min<long long>(S->exe_queries, N - N / E), (uint64_t)N, (uint64_t)E, exe_pos, err) != 0)
+        return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str());
+    PlannedProof lc_pp, ev_pp;
+    if ((rc = plan_proof(lc_pp, layers[0].tree, (uint64_t)(N >> 2), aug4(exe_pos, N), row_cols(layers[0])))) return rc;
+    struct Comp { const uint8_t* root; PlannedProof column, poly; };
     std::vector<Comp> comps(layers.size() - 1);
     for (size_t d = 0; d + 1 < layers.size(); ++d) {
         const FriLayer& pl = layers[d]; const FriLayer& cl = layers[d + 1];
         std::vector<uint32_t> positions;
         if (pseudorandom_indexes(cl.root, S->fri_queries, (uint64_t)cl.len, (uint64_t)E, positions, err) != 0)
             return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str());
-        const std::vector<uint32_t> augmented = aug4(positions, cl.len);
         comps[d].root = cl.root;
-        if ((rc = device_merkle_proof(S, cl.tree, (uint64_t)(cl.len >> 2), augmented, comps[d].column, err))) return rc;
-        if ((rc = rows_of(cl, augmented, comps[d].column.values))) return rc;
-        if ((rc = device_merkle_proof(S, pl.tree, (uint64_t)(pl.len >> 2), positions, comps[d].poly, err))) return rc;
-        if ((rc = rows_of(pl, positions, comps[d].poly.values))) return rc;
+        if ((rc = plan_proof(comps[d].column, cl.tree, (uint64_t)(cl.len >> 2), aug4(positions, cl.len), row_cols(cl)))) return rc;
+        if ((rc = plan_proof(comps[d].poly, pl.tree, (uint64_t)(pl.len >> 2), positions, row_cols(pl)))) return rc;
     }
     // 8 ---- trace queries (Stark.ts:147-151)
-    std::vector<uint32_t> aug_pos;
     {
         std::vector<uint32_t> m;
         for (uint32_t p : exe_pos) { m.push_back(p); m.push_back((uint32_t)((p + E) % N)); }
-        aug_pos = first_seen_unique(m);
+        if ((rc = plan_proof(ev_pp, e_tree, (uint64_t)N, first_seen_unique(m), e_cols))) return rc;
     }
-    BatchProof ev_proof;
-    if ((rc = device_merkle_proof(S, e_tree, (uint64_t)N, aug_pos, ev_proof, err))) return rc;
-    if ((rc = device_gather_rows(S, e_cols, aug_pos, ev_proof.values))) return rc;
+    {
+        const size_t nch = g_addr.size();
+        if (nch * 16 > c->mailbox_bytes) return c->fail(GS_E_STARK, "query phase needs %zu bytes of mailbox", nch * 16);
+        if ((rc = S->d_idx.ensure(c, nch * 8))) return rc;
+        if ((rc = S->d_gather.ensure(c, nch * 16))) return rc;
+        GS_CUDA(c, cudaMemcpyAsync(S->d_idx.p, g_addr.data(), nch * 8, cudaMemcpyHostToDevice, c->stream));
+        { ProfScope ps(c, "gather_queries");
+          gather_chunks_kernel<<<(unsigned)((nch + 255) / 256), 256, 0, c->stream>>>(S->d_idx.as<unsigned long long>(), (int)nch, S->d_gather.as<uint4>()); }
+        c->launches++;
+        GS_CUDA(c, cudaMemcpyAsync(c->mailbox, S->d_gather.p, nch * 16, cudaMemcpyDeviceToHost, c->stream));
+    }
     cudaEventRecord(S->ev1, c->stream);
     cudaEventSynchronize(S->ev1);
     cudaEventElapsedTime(&S->last_device_ms, S->ev0, S->ev1);
     S->trace_resident = true;
     if (c->profiling) c->prof_collect();
+    {
+        const uint8_t* mb = (const uint8_t*)c->mailbox;
+        auto fill = [&](PlannedProof& pp) {
+            size_t k = 0;
+            pp.bp.nodes.assign(pp.bp.node_ids.size(), {});
+            for (size_t col = 0; col < pp.bp.node_ids.size(); ++col) {
+                pp.bp.nodes[col].resize(pp.bp.node_ids[col].size());
+                for (size_t j = 0; j < pp.bp.node_ids[col].size(); ++j, ++k) memcpy(pp.bp.nodes[col][j].data(), mb + 16 * pp.node_chunk[k], 32);
+            }
+            const size_t nv = pp.chunks_per_value ? pp.value_chunk.size() / pp.chunks_per_value : 0;
+            pp.bp.values.assign(nv, {});
+            for (size_t q = 0; q < nv; ++q) {
+                pp.bp.values[q].resize((size_t)pp.chunks_per_value * 16);
+                for (int j = 0; j < pp.chunks_per_value; ++j) memcpy(pp.bp.values[q].data() + 16 * j, mb + 16 * pp.value_chunk[q * pp.chunks_per_value + j], 16);
+            }
+        };
+        fill(lc_pp); fill(ev_pp);
+        for (auto& cp : comps) { fill(cp.column); fill(cp.poly); }
+    }
+    BatchProof& lc_proof = lc_pp.bp; BatchProof& ev_proof = ev_pp.bp;
     mark("Computed evaluation spot checks and Merkle proofs", false);
 
     // serialize (Serializer.ts:35-79)
@@ -582,10 +544,10 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     write_merkle_proof(out, lc_proof, ld_leaf);
     out.push_back((uint8_t)comps.size());
     for (auto& cp : comps) {
-        if (check_merkle_proof_limits(cp.column, err) != 0 || check_merkle_proof_limits(cp.poly, err) != 0) return c->fail(GS_E_STARK, "%s", err.c_str());
+        if (check_merkle_proof_limits(cp.column.bp, err) != 0 || check_merkle_proof_limits(cp.poly.bp, err) != 0) return c->fail(GS_E_STARK, "%s", err.c_str());
         out.insert(out.end(), cp.root, cp.root + 32);
-        write_merkle_proof(out, cp.column, ld_leaf);
-        write_merkle_proof(out, cp.poly, ld_leaf);
+        write_merkle_proof(out, cp.column.bp, ld_leaf);
+        write_merkle_proof(out, cp.poly.bp, ld_leaf);
     }
     out.push_back((uint8_t)(remainder.size() == 256 ? 0 : remainder.size()));
     for (u128 v : remainder) { fp f = fp_from_u128(v); const uint8_t* b = (const uint8_t*)&f; out.insert(out.end(), b, b + 16); }

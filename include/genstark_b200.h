@@ -89,6 +89,9 @@ int gs_vec_binary(gs_ctx* ctx, int op, const gs_mat* a, const gs_mat* b, const u
 int gs_stark_create(gs_ctx* ctx, const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries,
                     int fri_queries, gs_stark** out);
 void gs_stark_destroy(gs_stark* s);
+/* Stark.generateExecutionTrace (lib/Stark.ts:252-257): host only; out_trace: R x T x 16 bytes, row = register */
+int gs_air_generate_trace(const uint8_t* air_blob, size_t blob_len, const uint8_t* init_state16,
+                          const uint8_t* input_traces, uint8_t* out_trace);
 int gs_stark_prove(gs_stark* s, const uint8_t* assertions, int n_assertions, const uint8_t* init_state16,
                    const uint8_t* input_traces, const uint8_t* shapes_blob, size_t shapes_len,
                    const uint8_t** proof_out, size_t* proof_len);
