@@ -63,3 +63,22 @@ def test_north_star_shape_proof_verifies_under_oracle_verifier():
     ora = OracleStark(air, opts)
     assert ora.verify(a, ora.parse(got))
     assert gpu.securityLevel == ora.security_level
+
+
+@pytest.mark.parametrize('log_steps,e', [(16, 8), (18, 16), (20, 8)])
+def test_large_proofs_match_c_oracle_port(log_steps, e):
+    """BASELINE sizes: the GPU proof is byte-identical to the plain-C oracle port (itself pinned to the Python
+    restatement by tests/test_cport.py), which runs the reference's unfused data flow on the host cores."""
+    from oracle import cport
+    import bench
+    steps = 1 << log_steps
+    air = airs.mimc128(steps)
+    opts = dict(OPTS, extensionFactor=e)
+    a = bench.mimc_assertions(steps)
+    gpu = Stark(air, opts)
+    got = gpu.prove_bytes(a, [], [3])
+    want = cport.prove(air, opts, a, [], [3])
+    assert len(got) == len(want)
+    assert got == want
+    # prove again: buffers are reused across calls and the result must not depend on it
+    assert gpu.prove_bytes(a, [], [3]) == want
