@@ -87,6 +87,7 @@ class ProgramBuilder:
         self._const_ids = {}
         self.outs: dict = {}
         self.expand_exp_up_to = expand_exp_up_to
+        self._cse = {}
 
     # leaves
     def const(self, v: int) -> _Node:
@@ -130,6 +131,12 @@ class ProgramBuilder:
 
     # internals
     def _emit(self, op, a, b, degree) -> _Node:
+        # common-subexpression elimination: the program is pure, identical (op, a, b) is the same value
+        key = (op, a, b) if op not in (OP_ADD, OP_MUL) else (op, min(a, b), max(a, b))
+        hit = self._cse.get(key)
+        if hit is not None:
+            return _Node(self, hit, self.deg[hit])
+        self._cse[key] = len(self.ssa)
         self.ssa.append((op, a, b))
         self.deg.append(degree)
         return _Node(self, len(self.ssa) - 1, degree)
@@ -229,6 +236,8 @@ class AirModule:
     # inputs -> list of T-length traces, one per 'input' static register, in register order
     expand_inputs: Callable = lambda inputs: []
     input_shapes: Callable = lambda inputs: []
+    # public inputs (verify side) -> T-length traces of the public input registers, in register order
+    expand_public_inputs: Callable = lambda public_inputs: []
 
     def __post_init__(self):
         if self.constraint_degrees is None:

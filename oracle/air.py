@@ -173,7 +173,7 @@ class VerificationContext(AirContext):
         self.public_polys = {}
         pub_regs = [k for k, r in enumerate(air.static_registers) if r.kind == 'input' and not r.secret]
         if pub_regs:
-            traces = air.expand_inputs(self.public_inputs)
+            traces = air.expand_public_inputs(self.public_inputs)
             dom = f.get_power_series(self._exe_root, T)
             for k, t in zip(pub_regs, traces):
                 self.public_polys[k] = f.interpolate_roots(dom, list(t))

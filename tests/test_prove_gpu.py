@@ -82,3 +82,42 @@ def test_large_proofs_match_c_oracle_port(log_steps, e):
     assert got == want
     # prove again: buffers are reused across calls and the result must not depend on it
     assert gpu.prove_bytes(a, [], [3]) == want
+
+
+def _check_against(gpu_case, oracle_kind):
+    import cases  # noqa: F401
+    air, opts, a, inputs, seed = gpu_case
+    gpu = Stark(air, opts)
+    got = gpu.prove_bytes(a, inputs, seed)
+    if oracle_kind == 'python':
+        ora = OracleStark(air, opts)
+        want = ora.serialize(ora.prove(a, inputs, seed))
+        pub = inputs[4:] if air.name == 'poseidon_mp' else None
+        assert ora.verify(a, ora.parse(got), pub)
+    else:
+        from oracle import cport
+        want = cport.prove(air, opts, a, inputs, seed)
+    assert len(got) == len(want)
+    assert got == want
+
+
+def test_rescue_chain_small_matches_python_oracle():
+    import cases
+    _check_against(cases.rescue(4), 'python')
+
+
+def test_rescue_config3_2e12_steps_matches_c_oracle():
+    """BASELINE config 3: Rescue 4x128, 2^12 steps (128 chained instances), 4 trace + 4 secret input registers."""
+    import cases
+    _check_against(cases.rescue(128), 'c')
+
+
+def test_poseidon_small_matches_python_oracle():
+    import cases
+    _check_against(cases.poseidon(2, 1, e=16), 'python')
+
+
+def test_poseidon_config5_2e16_steps_matches_c_oracle():
+    """BASELINE config 5: Poseidon Merkle proof, 12 registers, 2^16 steps (128 branches of depth 8), E=32."""
+    import cases
+    _check_against(cases.poseidon(8, 128, e=32), 'c')
