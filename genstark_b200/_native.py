@@ -46,6 +46,21 @@ def lib() -> C.CDLL:
         'gs_interpolate_roots': (i32, [vp, vp, P(vp)]),
         'gs_eval_polys_at_roots': (i32, [vp, vp, i32, P(vp)]),
         'gs_vec_binary': (i32, [vp, i32, vp, vp, cp, P(vp)]),
+        'gs_vec_div': (i32, [vp, vp, vp, P(vp)]),
+        'gs_vec_combine_many': (i32, [vp, P(vp), i32, cp, P(vp)]),
+        'gs_power_series': (i32, [vp, cp, i64, P(vp)]),
+        'gs_pluck_vector': (i32, [vp, vp, i64, i64, P(vp)]),
+        'gs_transpose_vector': (i32, [vp, vp, i32, i64, P(vp)]),
+        'gs_fri_fold': (i32, [vp, vp, i32, i32, cp, P(vp)]),
+        'gs_hash_merge_vector_rows': (i32, [vp, i32, P(vp), i32, P(vp)]),
+        'gs_hash_digest_values': (i32, [vp, i32, vp, P(vp)]),
+        'gs_digests_to_bytes': (i32, [vp, vp, vp]),
+        'gs_digests_count': (i64, [vp]),
+        'gs_digests_free': (None, [vp]),
+        'gs_merkle_create': (i32, [vp, i32, vp, P(vp)]),
+        'gs_merkle_root': (i32, [vp, vp, C.c_char_p]),
+        'gs_merkle_prove_batch': (i32, [vp, vp, P(C.c_uint32), i32, vp, C.c_size_t, P(C.c_size_t)]),
+        'gs_tree_free': (None, [vp]),
         'gs_stark_create': (i32, [vp, cp, C.c_size_t, i32, i32, i32, P(vp)]),
         'gs_stark_destroy': (None, [vp]),
         'gs_air_generate_trace': (i32, [cp, C.c_size_t, cp, cp, vp]),

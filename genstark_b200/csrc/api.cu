@@ -10,6 +10,8 @@ using namespace gs;
 
 struct gs_ctx : public Ctx {};
 struct gs_mat : public Mat {};
+struct gs_digests { Ctx* ctx; uint32_t* data; long long n; };
+struct gs_tree { Ctx* ctx; uint32_t* nodes; long long n; int alg; };
 struct gs_stark : public Stark { std::vector<uint8_t> proof; std::string times_json; };
 
 static thread_local std::string g_null_error;
@@ -191,6 +193,201 @@ int gs_vec_binary(gs_ctx* c, int op, const gs_mat* a, const gs_mat* b, const uin
     if (rc != GS_OK) { gs_mat_free(*out); *out = nullptr; }
     return rc;
 }
+
+// divVectorElements(a, b) = a * inv(b) with inv(0) = 0   (CompositionPolynomial.ts:117, BoundaryConstraints.ts:92)
+int gs_vec_div(gs_ctx* c, const gs_mat* a, const gs_mat* b, gs_mat** out) {
+    if (!c || !a || !b || !out) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    if (b->rows != a->rows || b->cols != a->cols) return c->fail(GS_E_ARG, "shape mismatch");
+    cudaSetDevice(c->device);
+    const long long n = a->rows * a->cols;
+    int rc = gs_mat_alloc(c, a->rows, a->cols, out);
+    if (rc != GS_OK) return rc;
+    rc = c->ensure_scratch((size_t)n * sizeof(fp));
+    if (rc == GS_OK) rc = batch_inverse(c, b->data, (*out)->data, (fp*)c->scratch, n);
+    if (rc == GS_OK) rc = vec_binary(c, VOP_MUL, a->data, (*out)->data, nullptr, (*out)->data, n);
+    if (rc != GS_OK) { gs_mat_free(*out); *out = nullptr; }
+    return rc;
+}
+
+int gs_vec_combine_many(gs_ctx* c, const gs_mat* const* vectors, int count, const uint8_t* coefficients16, gs_mat** out) {
+    if (!c || !vectors || !coefficients16 || !out || count < 1 || count > 64) return c ? c->fail(GS_E_ARG, "1..64 vectors required") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    CombineParams P; P.m = count;
+    const long long n = vectors[0]->rows * vectors[0]->cols;
+    for (int m = 0; m < count; ++m) {
+        if (!vectors[m] || vectors[m]->rows * vectors[m]->cols != n) return c->fail(GS_E_ARG, "shape mismatch");
+        P.v[m] = vectors[m]->data; memcpy(&P.k[m], coefficients16 + 16 * m, 16);
+    }
+    int rc = gs_mat_alloc(c, 1, n, out);
+    if (rc != GS_OK) return rc;
+    rc = c->ensure_scratch(sizeof P);
+    if (rc != GS_OK) { gs_mat_free(*out); *out = nullptr; return rc; }
+    GS_CUDA(c, cudaMemcpyAsync(c->scratch, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
+    combine_many_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>((const CombineParams*)c->scratch, (*out)->data, n);
+    c->launches++;
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return GS_OK;
+}
+
+int gs_power_series(gs_ctx* c, const uint8_t base16[16], int64_t n, gs_mat** out) {
+    if (!c || !base16 || !out || n < 1) return c ? c->fail(GS_E_ARG, "bad argument") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    int rc = gs_mat_alloc(c, 1, n, out);
+    if (rc != GS_OK) return rc;
+    fp b; memcpy(&b, base16, 16);
+    long long threads = n < 65536 ? n : 65536;
+    power_series_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, c->stream>>>(b, (*out)->data, n);
+    c->launches++;
+    return GS_OK;
+}
+
+int gs_pluck_vector(gs_ctx* c, const gs_mat* v, int64_t skip, int64_t times, gs_mat** out) {
+    if (!c || !v || !out || skip < 0 || times < 1) return c ? c->fail(GS_E_ARG, "bad argument") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    int rc = gs_mat_alloc(c, 1, times, out);
+    if (rc != GS_OK) return rc;
+    pluck_kernel<<<(unsigned)((times + 255) / 256), 256, 0, c->stream>>>(v->data, v->rows * v->cols, skip, (*out)->data, times);
+    c->launches++;
+    return GS_OK;
+}
+
+int gs_transpose_vector(gs_ctx* c, const gs_mat* v, int columns, int64_t step, gs_mat** out) {
+    if (!c || !v || !out || columns < 1 || step < 1) return c ? c->fail(GS_E_ARG, "bad argument") : GS_E_ARG;
+    const long long len = v->rows * v->cols;
+    if (len % ((long long)columns * step)) return c->fail(GS_E_ARG, "length not divisible by columns * step");
+    cudaSetDevice(c->device);
+    const long long rows = len / ((long long)columns * step);
+    int rc = gs_mat_alloc(c, rows, columns, out);
+    if (rc != GS_OK) return rc;
+    transpose_vector_kernel<<<(unsigned)((rows * columns + 255) / 256), 256, 0, c->stream>>>(v->data, rows, columns, step, (*out)->data);
+    c->launches++;
+    return GS_OK;
+}
+
+// one FRI layer: interpolateQuarticBatch(transposeVector(domain,4,4^depth), transposeVector(v,4)) evaluated at x*
+int gs_fri_fold(gs_ctx* c, const gs_mat* v, int log2_domain, int depth, const uint8_t special_x16[16], gs_mat** column) {
+    if (!c || !v || !special_x16 || !column) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    const long long L = v->rows * v->cols;
+    if (L < 4 || (L & 3) || (L << (2 * depth)) != (1ll << log2_domain) || log2_domain > c->log_g) return c->fail(GS_E_ARG, "layer length must be domain / 4^depth");
+    cudaSetDevice(c->device);
+    int rc = gs_mat_alloc(c, 1, L >> 2, column);
+    if (rc != GS_OK) return rc;
+    rc = c->ensure_scratch(64);
+    if (rc != GS_OK) { gs_mat_free(*column); *column = nullptr; return rc; }
+    GS_CUDA(c, cudaMemcpyAsync(c->scratch, special_x16, 16, cudaMemcpyHostToDevice, c->stream));
+    FriFoldParams F; F.v = v->data; F.out = (*column)->data; F.quarter = L >> 2; F.special_x = (const fp*)c->scratch;
+    F.tw_lo = c->tw_lo; F.tw_hi = c->tw_hi; F.log_g = c->log_g; F.log_lo = c->log_lo;
+    F.x_shift = 2 * depth + (c->log_g - log2_domain);
+    F.iota_inv = fp_from_u128(h_inv(c->root_of_order(2))); F.quarter_inv = fp_from_u128(h_inv(4));
+    fri_fold_kernel<<<grid_for(c, L >> 2, 256), 256, 0, c->stream>>>(F);
+    c->launches++;
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return GS_OK;
+}
+
+// ---- K5: hashing and Merkle trees ----------------------------------------------------------------
+static int digests_alloc(gs_ctx* c, long long n, gs_digests** out) {
+    gs_digests* d = new gs_digests(); d->ctx = c; d->n = n; d->data = nullptr;
+    cudaError_t e = cudaMalloc(&d->data, (size_t)n * 32);
+    if (e != cudaSuccess) { delete d; return c->cuda_fail(e, "cudaMalloc(digests)"); }
+    *out = d; return GS_OK;
+}
+
+int gs_hash_merge_vector_rows(gs_ctx* c, int alg, const gs_mat* const* mats, int count, gs_digests** out) {
+    if (!c || !mats || !out || count < 1) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    HashCols hc; hc.ncols = 0;
+    const long long n = mats[0]->cols;
+    for (int m = 0; m < count; ++m) {
+        if (!mats[m] || mats[m]->cols != n) return c->fail(GS_E_ARG, "all vectors must have the same length");
+        for (long long r = 0; r < mats[m]->rows; ++r) {
+            if (hc.ncols >= GS_MAX_HASH_COLS) return c->fail(GS_E_UNSUPPORTED, "more than %d columns", GS_MAX_HASH_COLS);
+            hc.col[hc.ncols++] = mats[m]->data + r * n;
+        }
+    }
+    int rc = digests_alloc(c, n, out);
+    if (rc != GS_OK) return rc;
+    rc = hash_columns(c, alg, hc, n, (*out)->data);
+    if (rc != GS_OK) { gs_digests_free(*out); *out = nullptr; }
+    return rc;
+}
+
+int gs_hash_digest_values(gs_ctx* c, int alg, const gs_mat* rows, gs_digests** out) {
+    if (!c || !rows || !out) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    int rc = digests_alloc(c, rows->rows, out);
+    if (rc != GS_OK) return rc;
+    rc = hash_rows(c, alg, rows->data, (int)(rows->cols * 16), rows->rows, (*out)->data);
+    if (rc != GS_OK) { gs_digests_free(*out); *out = nullptr; }
+    return rc;
+}
+
+int gs_digests_to_bytes(gs_ctx* c, const gs_digests* d, void* out) {
+    if (!c || !d || !out) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    GS_CUDA(c, cudaMemcpyAsync(out, d->data, (size_t)d->n * 32, cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return GS_OK;
+}
+int64_t gs_digests_count(const gs_digests* d) { return d ? d->n : 0; }
+void gs_digests_free(gs_digests* d) { if (!d) return; cudaSetDevice(d->ctx->device); cudaFree(d->data); delete d; }
+
+int gs_merkle_create(gs_ctx* c, int alg, const gs_digests* leaves, gs_tree** out) {
+    if (!c || !leaves || !out) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    const long long n = leaves->n;
+    if (n < 2 || (n & (n - 1))) return c->fail(GS_E_ARG, "leaf count must be a power of two >= 2");
+    cudaSetDevice(c->device);
+    gs_tree* t = new gs_tree(); t->ctx = c; t->n = n; t->alg = alg; t->nodes = nullptr;
+    cudaError_t e = cudaMalloc(&t->nodes, (size_t)2 * n * 32);
+    if (e != cudaSuccess) { delete t; return c->cuda_fail(e, "cudaMalloc(tree)"); }
+    cudaMemsetAsync(t->nodes, 0, 32, c->stream);
+    cudaMemcpyAsync(t->nodes + 8 * n, leaves->data, (size_t)n * 32, cudaMemcpyDeviceToDevice, c->stream);
+    int rc = merkle_build(c, alg, t->nodes, n);
+    if (rc != GS_OK) { cudaFree(t->nodes); delete t; return rc; }
+    *out = t;
+    return GS_OK;
+}
+
+int gs_merkle_root(gs_ctx* c, const gs_tree* t, uint8_t out32[32]) {
+    if (!c || !t || !out32) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    GS_CUDA(c, cudaMemcpyAsync(out32, t->nodes + 8, 32, cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return GS_OK;
+}
+
+// proveBatch(indexes): blob = u32 n_values | u32 n_columns | u32 depth | values (32 B leaf digests, input order) |
+//                             per column: u32 length, then length x 32 B
+int gs_merkle_prove_batch(gs_ctx* c, const gs_tree* t, const uint32_t* indexes, int count, uint8_t* out, size_t out_cap, size_t* out_len) {
+    if (!c || !t || !indexes || !out_len || count < 1) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    std::vector<uint32_t> idx(indexes, indexes + count);
+    BatchProof bp; std::string err;
+    if (merkle_prove_plan(idx, (uint64_t)t->n, bp, err) != 0) return c->fail(GS_E_ARG, "%s", err.c_str());
+    std::vector<unsigned long long> addr;
+    for (uint32_t i : idx) { addr.push_back((unsigned long long)(uintptr_t)(t->nodes + 8ull * (t->n + i))); addr.push_back((unsigned long long)(uintptr_t)(t->nodes + 8ull * (t->n + i) + 4)); }
+    for (auto& col : bp.node_ids) for (uint32_t id : col) { addr.push_back((unsigned long long)(uintptr_t)(t->nodes + 8ull * id)); addr.push_back((unsigned long long)(uintptr_t)(t->nodes + 8ull * id + 4)); }
+    const size_t nch = addr.size();
+    if (nch * 16 > c->mailbox_bytes) return c->fail(GS_E_ARG, "too many indexes");
+    int rc = c->ensure_scratch(nch * 24);
+    if (rc != GS_OK) return rc;
+    uint8_t* d_addr = (uint8_t*)c->scratch; uint8_t* d_out = d_addr + nch * 8;
+    GS_CUDA(c, cudaMemcpyAsync(d_addr, addr.data(), nch * 8, cudaMemcpyHostToDevice, c->stream));
+    gather_chunks_kernel<<<(unsigned)((nch + 255) / 256), 256, 0, c->stream>>>((const unsigned long long*)d_addr, (int)nch, (uint4*)d_out);
+    c->launches++;
+    GS_CUDA(c, cudaMemcpyAsync(c->mailbox, d_out, nch * 16, cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<uint8_t> blob;
+    auto put32 = [&](uint32_t v) { const uint8_t* p = (const uint8_t*)&v; blob.insert(blob.end(), p, p + 4); };
+    put32((uint32_t)count); put32((uint32_t)bp.node_ids.size()); put32((uint32_t)bp.depth);
+    const uint8_t* mb = (const uint8_t*)c->mailbox;
+    blob.insert(blob.end(), mb, mb + (size_t)count * 32);
+    size_t k = (size_t)count * 32;
+    for (auto& col : bp.node_ids) { put32((uint32_t)col.size()); blob.insert(blob.end(), mb + k, mb + k + col.size() * 32); k += col.size() * 32; }
+    *out_len = blob.size();
+    if (!out || out_cap < blob.size()) return c->fail(GS_E_ARG, "output buffer too small (%zu bytes needed)", blob.size());
+    memcpy(out, blob.data(), blob.size());
+    return GS_OK;
+}
+void gs_tree_free(gs_tree* t) { if (!t) return; cudaSetDevice(t->ctx->device); cudaFree(t->nodes); delete t; }
 
 int gs_debug_modmul_probe(gs_ctx* c, int blocks, int iters, float* ms_out) {
     if (!c || !ms_out) return GS_E_ARG;

@@ -44,6 +44,42 @@ static inline int vec_binary(Ctx* c, int op, const fp* a, const fp* b, const fp*
     return GS_OK;
 }
 
+// combineManyVectors(V, k): out[i] = sum_m k[m] * V[m][i]   (CompositionPolynomial.ts:105,142; LinearCombination.ts:60)
+struct CombineParams { const fp* v[64]; fp k[64]; int m; };
+__global__ void __launch_bounds__(256) combine_many_kernel(const CombineParams* __restrict__ P, fp* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        fp acc = fp_zero();
+        for (int m = 0; m < P->m; ++m) acc = fp_add(acc, fp_mul(ld_fp(P->v[m] + i), P->k[m]));
+        st_fp(out + i, acc);
+    }
+}
+
+// getPowerSeries(base, n): out[i] = base^i.  Each thread starts from base^(first index) by square-and-multiply
+// and then steps by base^(total threads).
+__global__ void __launch_bounds__(256) power_series_kernel(fp base, fp* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    fp v = fp_pow(base, (uint64_t)t);
+    const fp step = fp_pow(base, (uint64_t)stride);
+    for (long long i = t; i < n; i += stride) { st_fp(out + i, v); v = fp_mul(v, step); }
+}
+
+// pluckVector(v, skip, times): out[i] = v[(i*skip) mod len]      (ZeroPolynomial.ts:40)
+__global__ void pluck_kernel(const fp* __restrict__ v, long long len, long long skip, fp* __restrict__ out, long long times) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < times) st_fp(out + i, ld_fp(v + (unsigned long long)((unsigned __int128)i * skip % len)));
+}
+
+// transposeVector(v, columns, step): rows = len/(columns*step); M[i][j] = v[(i + j*rows)*step], row-major out
+__global__ void transpose_vector_kernel(const fp* __restrict__ v, long long rows, int columns, long long step, fp* __restrict__ out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * columns) return;
+    const long long i = t / columns; const int j = (int)(t % columns);
+    st_fp(out + t, ld_fp(v + (i + (long long)j * rows) * step));
+}
+
 // dependent modmul chains: throughput probe used by bench.py to state the integer roofline
 __global__ void __launch_bounds__(256) modmul_probe_kernel(fp* out, int iters) {
     fp a, b, c2, d;

@@ -163,6 +163,45 @@ class GpuField:
     def subVectorElements(self, a, b): return self._binary(1, a, b)
     def mulVectorElements(self, a, b): return self._binary(2, a, b)
 
+    def divVectorElements(self, a: Matrix, b) -> Matrix:
+        """a * inv(b) element-wise, inv(0) = 0 (CompositionPolynomial.ts:117)"""
+        if not isinstance(b, Matrix):
+            return self.mulVectorElements(a, self.inv(b))
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_vec_div(self.ctx.handle, a.handle, b.handle, C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    divMatrixElements = divVectorElements
+
+    def combineManyVectors(self, vectors: Sequence[Matrix], coefficients) -> Matrix:
+        ks = coefficients.toValues() if isinstance(coefficients, Matrix) else list(coefficients)
+        arr = (C.c_void_p * len(vectors))(*[v.handle for v in vectors])
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_vec_combine_many(self.ctx.handle, arr, len(vectors), b''.join(_enc(k % P128) for k in ks), C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    def getPowerSeries(self, base: int, n: int) -> Matrix:
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_power_series(self.ctx.handle, _enc(base % P128), n, C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    def pluckVector(self, v: Matrix, skip: int, times: int) -> Matrix:
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_pluck_vector(self.ctx.handle, v.handle, skip, times, C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    def transposeVector(self, v: Matrix, columns: int, step: int = 1) -> Matrix:
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_transpose_vector(self.ctx.handle, v.handle, columns, step, C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    def friFold(self, v: Matrix, domain_size: int, depth: int, special_x: int) -> Matrix:
+        """evalQuarticBatch(interpolateQuarticBatch(transposeVector(domain,4,4^depth), transposeVector(v,4)), x)
+        in one kernel (LowDegreeProver.ts:190-195)."""
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_fri_fold(self.ctx.handle, v.handle, domain_size.bit_length() - 1, depth, _enc(special_x % P128), C.byref(h)))
+        return Matrix(self.ctx, h)
+
     # polynomials over roots of unity (K1) ------------------------------------------------------------
     def interpolateRoots(self, domain, values: Matrix) -> Matrix:
         """lib/Stark.ts:106 -- ``domain`` is implied by the length (power series of getRootOfUnity)."""
@@ -178,3 +217,93 @@ class GpuField:
         return Matrix(self.ctx, h)
 
     evalPolyAtRoots = evalPolysAtRoots
+
+
+class Digests:
+    """n 32-byte digests in HBM (what hash.mergeVectorRows / digestValues return)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.handle = ctx, handle
+        self.length = int(ctx._lib.gs_digests_count(handle))
+
+    def toBuffers(self) -> List[bytes]:
+        buf = C.create_string_buffer(self.length * 32)
+        self.ctx.check(self.ctx._lib.gs_digests_to_bytes(self.ctx.handle, self.handle, buf))
+        return [buf.raw[i:i + 32] for i in range(0, self.length * 32, 32)]
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx._lib.gs_digests_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class GpuHash:
+    """merkle `Hash` (lib/Stark.ts:49-53): createHash(algorithm) with the O(N) methods on the device."""
+    ALGORITHMS = ['sha256', 'blake2s256']
+    digestSize = 32
+    isOptimized = True
+
+    def __init__(self, algorithm: str, ctx: Context):
+        if algorithm not in self.ALGORITHMS:
+            raise TypeError(f'Hash algorithm {algorithm} is not supported')
+        self.algorithm, self.alg, self.ctx = algorithm, self.ALGORITHMS.index(algorithm), ctx
+        self._lib = ctx._lib
+
+    def mergeVectorRows(self, vectors: Sequence[Matrix]) -> Digests:
+        arr = (C.c_void_p * len(vectors))(*[v.handle for v in vectors])
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_hash_merge_vector_rows(self.ctx.handle, self.alg, arr, len(vectors), C.byref(h)))
+        return Digests(self.ctx, h)
+
+    def digestValues(self, rows: Matrix, valueSize: Optional[int] = None) -> Digests:
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_hash_digest_values(self.ctx.handle, self.alg, rows.handle, C.byref(h)))
+        return Digests(self.ctx, h)
+
+
+class MerkleTree:
+    """merkle `MerkleTree` with the nodes in HBM: create / root / proveBatch (lib/Stark.ts:118,150)."""
+
+    def __init__(self, ctx: Context, handle, depth: int):
+        self.ctx, self.handle, self.depth = ctx, handle, depth
+
+    @staticmethod
+    def create(values: Digests, hash: GpuHash) -> 'MerkleTree':
+        h = C.c_void_p()
+        hash.ctx.check(hash._lib.gs_merkle_create(hash.ctx.handle, hash.alg, values.handle, C.byref(h)))
+        return MerkleTree(hash.ctx, h, values.length.bit_length() - 1)
+
+    @property
+    def root(self) -> bytes:
+        out = C.create_string_buffer(32)
+        self.ctx.check(self.ctx._lib.gs_merkle_root(self.ctx.handle, self.handle, out))
+        return out.raw
+
+    def proveBatch(self, indexes: Sequence[int]):
+        """-> (values, nodes, depth) of a BatchMerkleProof; values are the leaf digests in input order"""
+        idx = (C.c_uint32 * len(indexes))(*indexes)
+        cap = 64 + 32 * len(indexes) * (self.depth + 3) + 4 * len(indexes)
+        buf = C.create_string_buffer(cap)
+        n = C.c_size_t()
+        self.ctx.check(self.ctx._lib.gs_merkle_prove_batch(self.ctx.handle, self.handle, idx, len(indexes), buf, cap, C.byref(n)))
+        raw = buf.raw[:n.value]
+        nv, nc, depth = int.from_bytes(raw[0:4], 'little'), int.from_bytes(raw[4:8], 'little'), int.from_bytes(raw[8:12], 'little')
+        off = 12
+        values = [raw[off + 32 * i: off + 32 * i + 32] for i in range(nv)]
+        off += 32 * nv
+        nodes = []
+        for _ in range(nc):
+            ln = int.from_bytes(raw[off:off + 4], 'little'); off += 4
+            nodes.append([raw[off + 32 * j: off + 32 * j + 32] for j in range(ln)]); off += 32 * ln
+        return values, nodes, depth
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.ctx._lib.gs_tree_free(self.handle)
+                self.handle = None
+        except Exception:
+            pass

@@ -26,6 +26,8 @@ extern "C" {
 
 typedef struct gs_ctx gs_ctx;     /* one device + stream + root tables              */
 typedef struct gs_mat gs_mat;     /* rows x cols field elements, row-major, in HBM  */
+typedef struct gs_digests gs_digests; /* n 32-byte digests in HBM (hash.mergeVectorRows / digestValues output) */
+typedef struct gs_tree gs_tree;       /* MerkleTree: 2n digests, nodes[1] = root                            */
 typedef struct gs_stark gs_stark; /* one AIR + security options + device buffers    */
 
 enum gs_status {
@@ -74,6 +76,37 @@ int gs_eval_polys_at_roots(gs_ctx* ctx, const gs_mat* polys, int log2_domain, gs
  * shape or a scalar (pass b = NULL and scalar16): op 0 add, 1 sub, 2 mul.
  * Call sites: CompositionPolynomial.ts:98,120,136,145; LinearCombination.ts:50,63; ZeroPolynomial.ts:41-42 */
 int gs_vec_binary(gs_ctx* ctx, int op, const gs_mat* a, const gs_mat* b, const uint8_t* scalar16, gs_mat** out);
+
+/* field.divVectorElements(a, b) = a * inv(b), inv(0) = 0          CompositionPolynomial.ts:117, BoundaryConstraints.ts:92 */
+int gs_vec_div(gs_ctx* ctx, const gs_mat* a, const gs_mat* b, gs_mat** out);
+/* field.combineManyVectors(vectors, coefficients) -> vector        CompositionPolynomial.ts:105,142; LinearCombination.ts:60 */
+int gs_vec_combine_many(gs_ctx* ctx, const gs_mat* const* vectors, int count, const uint8_t* coefficients16, gs_mat** out);
+/* field.getPowerSeries(base, n)                                     CompositionPolynomial.ts:94,132; LowDegreeProver.ts:233 */
+int gs_power_series(gs_ctx* ctx, const uint8_t base16[16], int64_t n, gs_mat** out);
+/* field.pluckVector(v, skip, times): out[i] = v[(i*skip) mod len]   ZeroPolynomial.ts:40 */
+int gs_pluck_vector(gs_ctx* ctx, const gs_mat* v, int64_t skip, int64_t times, gs_mat** out);
+/* field.transposeVector(v, columns, step) -> rows x columns matrix  LowDegreeProver.ts:42,162,190,198 */
+int gs_transpose_vector(gs_ctx* ctx, const gs_mat* v, int columns, int64_t step, gs_mat** out);
+/* one FRI layer (K4): evalQuarticBatch(interpolateQuarticBatch(xs, rows), x*) with xs = transposeVector(domain, 4, 4^depth)
+ * and rows = transposeVector(v, 4); v has length domain / 4^depth.   LowDegreeProver.ts:190-195 */
+int gs_fri_fold(gs_ctx* ctx, const gs_mat* v, int log2_domain, int depth, const uint8_t special_x16[16], gs_mat** column);
+
+/* ---- Hash / MerkleTree (K5); alg 0 = sha256, 1 = blake2s256 --------------------------------------------
+ * hash.mergeVectorRows(vectors): digest i = H(v0[i] || v1[i] || ...) over every row of every matrix   lib/Stark.ts:115
+ * hash.digestValues(buffer, valueSize): one digest per row of a row-major matrix               LowDegreeProver.ts:45
+ * MerkleTree.create / .root / .proveBatch                                   lib/Stark.ts:118,150; LowDegreeProver.ts:46,52
+ * proveBatch blob: u32 n_values, u32 n_columns, u32 depth, n_values x 32 B (leaf digests in input order), then per
+ * column u32 length + length x 32 B -- the {values, nodes, depth} of BatchMerkleProof (serialization.ts:31-35) */
+int gs_hash_merge_vector_rows(gs_ctx* ctx, int alg, const gs_mat* const* mats, int count, gs_digests** out);
+int gs_hash_digest_values(gs_ctx* ctx, int alg, const gs_mat* rows, gs_digests** out);
+int gs_digests_to_bytes(gs_ctx* ctx, const gs_digests* d, void* out);
+int64_t gs_digests_count(const gs_digests* d);
+void gs_digests_free(gs_digests* d);
+int gs_merkle_create(gs_ctx* ctx, int alg, const gs_digests* leaves, gs_tree** out);
+int gs_merkle_root(gs_ctx* ctx, const gs_tree* tree, uint8_t out32[32]);
+int gs_merkle_prove_batch(gs_ctx* ctx, const gs_tree* tree, const uint32_t* indexes, int count, uint8_t* out,
+                          size_t out_cap, size_t* out_len);
+void gs_tree_free(gs_tree* tree);
 
 /* ---- fused prover: the body of Stark.prove in one crossing (lib/Stark.ts:81-163) -------------------
  * gs_stark_create  <->  new Stark(schema, component, options)            lib/Stark.ts:35-58
