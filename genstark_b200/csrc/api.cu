@@ -465,6 +465,18 @@ int gs_stark_create(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int has
             if (rc != GS_OK) return rc;
         }
     }
+    // u[j] = 1/(w_N^j - 1) over the evaluation domain (boundary constraints by partial fractions, compose.cuh)
+    {
+        const int log_n = S->log_t + S->log_e; const long long N = 1ll << log_n;
+        if (log_n > c->log_g) return c->fail(GS_E_UNSUPPORTED, "evaluation domain 2^%d exceeds 2^%d", log_n, c->log_g);
+        if ((rc = S->d_u.ensure(c, (size_t)N * sizeof(fp)))) return rc;
+        if ((rc = c->ensure_scratch((size_t)N * sizeof(fp)))) return rc;
+        UTableParams U; U.n = N; U.log_n = log_n; U.tw_lo = c->tw_lo; U.tw_hi = c->tw_hi; U.log_g = c->log_g; U.log_lo = c->log_lo; U.out = S->d_u.as<fp>();
+        u_table_kernel<<<grid_for(c, N, 256), 256, 0, c->stream>>>(U);
+        c->launches++;
+        if ((rc = batch_inverse(c, S->d_u.as<fp>(), S->d_u.as<fp>(), (fp*)c->scratch, N))) return rc;
+        GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     *out = S.release();
     return GS_OK;
 }

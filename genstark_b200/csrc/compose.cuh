@@ -36,9 +36,14 @@ struct ComposeParams {
     int n_powers; unsigned long long pow_incr[GS_MAX_POWERS]; // x^incr, incr < N
     // zero polynomial: D = qc * (x - x_last) * inv_num[i mod E]
     fp x_last; const fp* inv_num;
-    // boundary part: for asserted register slot b: (P_reg - I(x)) * zb_inv[b][i] * (bk[b] + bk_adj[b] * x^delta)
+    // boundary part: for asserted register slot b: (P_reg - I(x)) / Z_b(x) * (bk[b] + bk_adj[b] * x^delta).
+    // 1/Z_b(x_i) by partial fractions over the per-context table u[j] = 1/(w^j - 1):
+    //   1/prod_k (x - X_k) = sum_k c_k / (x - X_k),  1/(w^i - w^s) = w^-s * u[(i - s) mod N],
+    // so each assertion costs one coalesced table read and one modmul; at x = X_k the reference's
+    // inv(0) = 0 convention makes the whole term zero.
     int n_boundary; const int* b_reg; const int* b_ipoly_off; const int* b_ipoly_len; const fp* b_ipoly;
-    const fp* zb_inv;            // [n_boundary x N]
+    const int* b_pf_off; const int* b_pf_len; const fp* b_pf_coef; const unsigned* b_pf_shift;   // shift = step * E
+    const fp* u_table;           // [N]
     const fp* bk; const fp* bk_adj;
     // linear combination: columns V = trace then secret; L = C + sum V_j (lk[j] + lk_adj[j] * x^delta)
     int n_lc; const fp* lc_col[GS_MAX_COLS]; const fp* lk; const fp* lk_adj;
@@ -116,7 +121,17 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeParams* __res
             fp iv = ldg_fp(P.b_ipoly + off + len - 1);
             for (int k = len - 2; k >= 0; --k) iv = fp_add(fp_mul(iv, x), ldg_fp(P.b_ipoly + off + k));
             const fp pv = ld_fp(P.trace[P.b_reg[bi]] + i);
-            const fp bv = fp_mul(fp_sub(pv, iv), ld_fp(P.zb_inv + (long long)bi * P.n + i));
+            fp zinv = fp_zero();
+            bool at_root = false;
+            const int po = P.b_pf_off[bi], pl = P.b_pf_len[bi];
+            for (int k = 0; k < pl; ++k) {
+                const unsigned sh = P.b_pf_shift[po + k];
+                at_root |= ((unsigned)i == sh);
+                const unsigned long long j = ((unsigned long long)i - sh) & nmask;
+                zinv = fp_add(zinv, fp_mul(ldg_fp(P.b_pf_coef + po + k), ld_fp(P.u_table + j)));
+            }
+            if (at_root) zinv = fp_zero();
+            const fp bv = fp_mul(fp_sub(pv, iv), zinv);
             fp coef = ldg_fp(P.bk + bi);
             if (P.delta) coef = fp_add(coef, fp_mul(ldg_fp(P.bk_adj + bi), xdelta));
             c = fp_add(c, fp_mul(bv, coef));
@@ -134,25 +149,15 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeParams* __res
     }
 }
 
-// Z_b(x_i) for every boundary slot: zb[bi][i] = prod_k (x_i - X_k) given as a monic polynomial
-struct ZbParams {
-    long long n; int log_n;
-    int n_boundary; const int* zpoly_off; const int* zpoly_len; const fp* zpoly;
-    const fp* tw_lo; const fp* tw_hi; int log_g, log_lo;
-    fp* out;
-};
-__global__ void __launch_bounds__(256) zb_eval_kernel(const ZbParams P) {
+// u[j] = w_N^j - 1 (inverted afterwards by K3; u[0] stays 0)
+struct UTableParams { long long n; int log_n; const fp* tw_lo; const fp* tw_hi; int log_g, log_lo; fp* out; };
+__global__ void __launch_bounds__(256) u_table_kernel(const UTableParams P) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
         const unsigned e = (unsigned)((unsigned long long)i << (P.log_g - P.log_n));
         fp x = ldg_fp(P.tw_lo + (e & ((1u << P.log_lo) - 1u)));
         if (P.log_g > P.log_lo) x = fp_mul(x, ldg_fp(P.tw_hi + (e >> P.log_lo)));
-        for (int bi = 0; bi < P.n_boundary; ++bi) {
-            const int off = P.zpoly_off[bi], len = P.zpoly_len[bi];
-            fp z = ldg_fp(P.zpoly + off + len - 1);
-            for (int k = len - 2; k >= 0; --k) z = fp_add(fp_mul(z, x), ldg_fp(P.zpoly + off + k));
-            st_fp(P.out + (long long)bi * P.n + i, z);
-        }
+        st_fp(P.out + i, fp_sub(x, fp_one()));
     }
 }
 

@@ -13,18 +13,6 @@
 namespace gs {
 
 
-// ----------------------------------------------------------------------------------------------
-// host-side scalar helpers (u128) -- control path only
-static inline u128 h_root_of_unity(int log_order) {
-    // galois getRootOfUnity: smallest i >= 2 whose g = i^((p-1)/order) has exact order.
-    // The test g^(order/2) != 1 is i^((p-1)/2) != 1, independent of the order, so every order shares
-    // the same i and w_{n/2} = w_n^2.
-    const u128 pm1 = HP - 1;
-    for (u128 i = 2;; ++i) {
-        if (h_pow(i, pm1 >> 1) != 1) return h_pow(i, pm1 >> log_order);
-    }
-}
-
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;

@@ -86,6 +86,15 @@ static inline u128 h_pow(u128 b, u128 e) {
     return r;
 }
 static inline u128 h_inv(u128 a) { return a == 0 ? 0 : h_pow(a, HP - 2); }
+// galois getRootOfUnity: smallest i >= 2 whose g = i^((p-1)/order) has exact order.  The test
+// g^(order/2) != 1 is i^((p-1)/2) != 1, independent of the order, so every order shares the same i (= 3) and
+// w_{n/2} = w_n^2.
+static inline u128 h_root_of_unity(int log_order) {
+    const u128 pm1 = HP - 1;
+    for (u128 i = 2;; ++i) {
+        if (h_pow(i, pm1 >> 1) != 1) return h_pow(i, pm1 >> log_order);
+    }
+}
 
 #ifdef __CUDA_ARCH__
 // ---------------------------------------------------------------------------------------------- device

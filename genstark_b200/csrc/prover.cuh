@@ -41,7 +41,7 @@ struct Stark : public AirHost {
     // options
     int hash_alg = HASH_SHA256, exe_queries = 80, fri_queries = 40;
     // device-resident program + cyclic tables
-    DevBuf d_instrs, d_consts, d_cyc;
+    DevBuf d_instrs, d_consts, d_cyc, d_u;   // d_u: u[j] = 1/(w_N^j - 1), built once per instance
     std::vector<size_t> cyc_off;      // per static register (cycle kind): element offset into d_cyc
     std::vector<unsigned> cyc_mask;
     // per-prove buffers (grow only)
@@ -55,7 +55,7 @@ struct Stark : public AirHost {
     float last_device_ms = 0;         // CUDA-event time from the first enqueue to the last kernel of prove()
     double last_host_ms = 0;          // wall clock of the whole call
     ~Stark() {
-        for (DevBuf* b : {&d_instrs, &d_consts, &d_cyc, &d_trace, &d_poly, &d_pe, &d_in_trace, &d_in_poly, &d_in_e, &d_work, &d_tree,
+        for (DevBuf* b : {&d_instrs, &d_consts, &d_cyc, &d_u, &d_trace, &d_poly, &d_pe, &d_in_trace, &d_in_poly, &d_in_e, &d_work, &d_tree,
                           &d_zb, &d_zbs, &d_l, &d_c, &d_fri, &d_fri_trees, &d_params, &d_small, &d_idx, &d_gather}) b->release();
         if (h_trace) cudaFreeHost(h_trace);
         if (ev0) cudaEventDestroy(ev0);
@@ -296,19 +296,27 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     }
     std::vector<fp> bk(nB), bk_adj(nB, fp_zero());
     for (int b = 0; b < nB; ++b) { bk[b] = fp_from_u128(coeffs[d_count + b]); if (comp_degree > T) bk_adj[b] = fp_from_u128(coeffs[d_count + nB + b]); }
-    // I(x), Z_b(x) per asserted register
-    std::vector<fp> ipoly, zpoly; std::vector<int> ioff(nB), ilen(nB), zoff(nB), zlen(nB), breg(nB);
-    for (int b = 0; b < nB; ++b) {
-        std::vector<u128> ip = h_interpolate(b_xs[b], b_ys[b]);
-        std::vector<u128> zp(1, 1);
-        for (u128 x : b_xs[b]) {             // zp *= (x - X)
-            zp.push_back(0);
-            for (size_t k = zp.size() - 1; k > 0; --k) zp[k] = h_sub(zp[k - 1], h_mul(zp[k], x));
-            zp[0] = h_sub(0, h_mul(zp[0], x));
+    // I(x) per asserted register, and the partial-fraction form of 1/Z_b(x) (see compose.cuh)
+    std::vector<fp> ipoly, pf_coef; std::vector<unsigned> pf_shift; std::vector<int> ioff(nB), ilen(nB), pfoff(nB), pflen(nB), breg(nB);
+    {
+        std::vector<std::vector<unsigned>> b_steps(nB);
+        for (int a = 0; a < n_assert; ++a) { size_t b = 0; for (; b < b_regs.size(); ++b) if (b_regs[b] == asserts[a].reg) break; b_steps[b].push_back(asserts[a].step); }
+        for (int b = 0; b < nB; ++b) {
+            const std::vector<u128> ip = h_interpolate(b_xs[b], b_ys[b]);
+            ioff[b] = (int)ipoly.size(); ilen[b] = (int)ip.size(); for (u128 v : ip) ipoly.push_back(fp_from_u128(v));
+            pfoff[b] = (int)pf_coef.size(); pflen[b] = (int)b_xs[b].size();
+            for (size_t k = 0; k < b_xs[b].size(); ++k) {
+                u128 den = 1;
+                for (size_t m = 0; m < b_xs[b].size(); ++m) if (m != k) {
+                    if (b_xs[b][m] == b_xs[b][k]) return c->fail(GS_E_STARK, "Failed to generate the execution trace: repeated assertion for register %u", b_regs[b]);
+                    den = h_mul(den, h_sub(b_xs[b][k], b_xs[b][m]));
+                }
+                // c_k * X_k^-1
+                pf_coef.push_back(fp_from_u128(h_mul(h_inv(den), h_inv(b_xs[b][k]))));
+                pf_shift.push_back((unsigned)((unsigned long long)b_steps[b][k] * (unsigned long long)E));
+            }
+            breg[b] = (int)b_regs[b];
         }
-        ioff[b] = (int)ipoly.size(); ilen[b] = (int)ip.size(); for (u128 v : ip) ipoly.push_back(fp_from_u128(v));
-        zoff[b] = (int)zpoly.size(); zlen[b] = (int)zp.size(); for (u128 v : zp) zpoly.push_back(fp_from_u128(v));
-        breg[b] = (int)b_regs[b];
     }
     // linear combination coefficients continue the same stream (LinearCombination.ts:58-59, Stark.ts:129)
     const int n_lc = (int)e_cols.size();
@@ -329,26 +337,14 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     auto put = [&](const void* p, size_t n) { size_t off = (small.size() + 15) & ~(size_t)15; small.resize(off + n); memcpy(small.data() + off, p, n); return off; };
     const size_t o_dk = put(dk.data(), K * 16), o_dka = put(dk_adj.data(), K * 16), o_pi = put(pow_idx.data(), K * 4);
     const size_t o_bk = put(bk.data(), nB * 16), o_bka = put(bk_adj.data(), nB * 16);
-    const size_t o_ip = put(ipoly.data(), ipoly.size() * 16), o_zp = put(zpoly.data(), zpoly.size() * 16);
-    const size_t o_io = put(ioff.data(), nB * 4), o_il = put(ilen.data(), nB * 4), o_zo = put(zoff.data(), nB * 4), o_zl = put(zlen.data(), nB * 4);
+    const size_t o_ip = put(ipoly.data(), ipoly.size() * 16), o_pc = put(pf_coef.data(), pf_coef.size() * 16), o_ps = put(pf_shift.data(), pf_shift.size() * 4);
+    const size_t o_io = put(ioff.data(), nB * 4), o_il = put(ilen.data(), nB * 4), o_po = put(pfoff.data(), nB * 4), o_pl = put(pflen.data(), nB * 4);
     const size_t o_br = put(breg.data(), nB * 4);
     const size_t o_lk = put(lk.data(), n_lc * 16), o_lka = put(lk_adj.data(), n_lc * 16), o_in = put(inv_num.data(), E * 16);
     const size_t o_flag = put("\0\0\0\0\0\0\0\0", 8);
     if ((rc = S->d_small.ensure(c, small.size() + 64))) return rc;
     uint8_t* ds = S->d_small.as<uint8_t>();
     GS_CUDA(c, cudaMemcpyAsync(ds, small.data(), small.size(), cudaMemcpyHostToDevice, c->stream));
-    // Z_b evaluations and their inverses
-    if ((rc = S->d_zb.ensure(c, (size_t)nB * N * sizeof(fp)))) return rc;
-    if ((rc = S->d_zbs.ensure(c, (size_t)nB * N * sizeof(fp)))) return rc;
-    {
-        ZbParams zp; zp.n = N; zp.log_n = log_n; zp.n_boundary = nB;
-        zp.zpoly_off = (const int*)(ds + o_zo); zp.zpoly_len = (const int*)(ds + o_zl); zp.zpoly = (const fp*)(ds + o_zp);
-        zp.tw_lo = c->tw_lo; zp.tw_hi = c->tw_hi; zp.log_g = c->log_g; zp.log_lo = c->log_lo; zp.out = S->d_zb.as<fp>();
-        { ProfScope ps(c, "zb_eval");
-        zb_eval_kernel<<<grid_for(c, N, 256), 256, 0, c->stream>>>(zp); }
-        c->launches++;
-        if ((rc = batch_inverse(c, S->d_zb.as<fp>(), S->d_zb.as<fp>(), S->d_zbs.as<fp>(), (long long)nB * N))) return rc;
-    }
     if ((rc = S->d_l.ensure(c, (size_t)N * sizeof(fp)))) return rc;
     if (S->keep_intermediates && (rc = S->d_c.ensure(c, (size_t)N * sizeof(fp)))) return rc;
     {
@@ -365,7 +361,9 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         P.n_powers = (int)pow_incr.size(); for (size_t g = 0; g < pow_incr.size(); ++g) P.pow_incr[g] = pow_incr[g] & (unsigned long long)(N - 1);
         P.x_last = fp_from_u128(h_pow(w_n, (u128)(T - 1) * (u128)E)); P.inv_num = (const fp*)(ds + o_in);
         P.n_boundary = nB; P.b_reg = (const int*)(ds + o_br); P.b_ipoly_off = (const int*)(ds + o_io); P.b_ipoly_len = (const int*)(ds + o_il);
-        P.b_ipoly = (const fp*)(ds + o_ip); P.zb_inv = S->d_zb.as<fp>(); P.bk = (const fp*)(ds + o_bk); P.bk_adj = (const fp*)(ds + o_bka);
+        P.b_ipoly = (const fp*)(ds + o_ip);
+        P.b_pf_off = (const int*)(ds + o_po); P.b_pf_len = (const int*)(ds + o_pl); P.b_pf_coef = (const fp*)(ds + o_pc); P.b_pf_shift = (const unsigned*)(ds + o_ps);
+        P.u_table = S->d_u.as<fp>(); P.bk = (const fp*)(ds + o_bk); P.bk_adj = (const fp*)(ds + o_bka);
         P.n_lc = n_lc; for (int j = 0; j < n_lc; ++j) P.lc_col[j] = e_cols[j];
         P.lk = (const fp*)(ds + o_lk); P.lk_adj = (const fp*)(ds + o_lka);
         P.delta = (unsigned long long)delta;

@@ -132,6 +132,13 @@ class Stark:
         self._lib.gs_stark_last_timing(self._handle, C.byref(d), C.byref(h))
         return d.value, h.value
 
+    # VERIFIER ----------------------------------------------------------------------------------------
+    def verify(self, assertions: Sequence[dict], proof, publicInputs=None) -> bool:
+        """lib/Stark.ts:167-248 (native host code in the library; throws StarkError like the reference)."""
+        buf = proof if isinstance(proof, (bytes, bytearray)) else self.serialize(proof)
+        return verify_proof(self.air, dict(hashAlgorithm=self.hashAlgorithm, exeQueryCount=self.exeQueryCount,
+                                           friQueryCount=self.friQueryCount), assertions, buf, publicInputs)
+
     def stage_times(self) -> List:
         return json.loads(self._lib.gs_stark_stage_times(self._handle).decode() or '[]')
 
@@ -267,6 +274,30 @@ def _read_merkle_proof(buf: bytes, off: int, leaf_size: int, node_size: int):   
         nodes.append(col)
     depth = buf[off]; off += 1
     return BatchMerkleProof(values, nodes, depth), off
+
+
+def verify_proof(air: AirModule, options: dict, assertions: Sequence[dict], proof_bytes: bytes, publicInputs=None) -> bool:
+    """Stark.verify without a device: O(queries log N) host work inside libgenstark_b200.so (gs_stark_verify)."""
+    if len(assertions) < 1:
+        raise TypeError('At least one assertion must be provided')
+    lib = _native.lib()
+    air = air.with_options(options.get('extensionFactor'))
+    p = air.modulus
+    alg = options.get('hashAlgorithm') or DEFAULT_HASH_ALGORITHM
+    if alg not in HASH_ALGORITHMS:
+        raise TypeError(f'Hash algorithm {alg} is not supported')
+    a_blob = b''.join(struct.pack('<II', int(a['register']), int(a['step'])) + (int(a['value']) % p).to_bytes(16, 'little')
+                      for a in assertions)
+    pub = air.expand_public_inputs(publicInputs or [])
+    pub_blob = b''.join((int(v) % p).to_bytes(16, 'little') for t in pub for v in t) if pub else None
+    blob = pack_air(air)
+    err = C.create_string_buffer(512)
+    rc = lib.gs_stark_verify(blob, len(blob), HASH_ALGORITHMS.index(alg), int(options.get('exeQueryCount') or DEFAULT_EXE_QUERY_COUNT),
+                             int(options.get('friQueryCount') or DEFAULT_FRI_QUERY_COUNT), a_blob, len(assertions),
+                             bytes(proof_bytes), len(proof_bytes), pub_blob, err, 512)
+    if rc != 0:
+        raise StarkError(err.value.decode() or f'verification failed (status {rc})')
+    return True
 
 
 def instantiate(air: AirModule, options: Optional[dict] = None, logger=None) -> Stark:

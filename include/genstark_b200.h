@@ -135,6 +135,12 @@ int gs_stark_prove_ex(gs_stark* s, const uint8_t* assertions, int n_assertions, 
                       const uint8_t** proof_out, size_t* proof_len);
 /* CUDA-event time of the device part and host wall clock of the last prove */
 int gs_stark_last_timing(gs_stark* s, float* device_ms, double* host_ms);
+/* stark.verify(assertions, proof, publicInputs)  lib/Stark.ts:167-248 -- host only (O(queries log N), as in the
+ * reference).  proof: the serialized proof; public_traces: one T-length column per PUBLIC input register or NULL.
+ * Returns GS_OK, or GS_E_STARK with the reference's StarkError text in err_buf. */
+int gs_stark_verify(const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,
+                    const uint8_t* assertions, int n_assertions, const uint8_t* proof, size_t proof_len,
+                    const uint8_t* public_traces, char* err_buf, size_t err_cap);
 /* per-stage host milliseconds of the last prove as JSON [[name, ms], ...] (Logger, lib/utils/Logger.ts) */
 const char* gs_stark_stage_times(gs_stark* s);
 /* test hooks: keep C(x) and read device-resident intermediates back (0 P evals, 1 C, 2 L, 3 P polys) */

@@ -83,8 +83,11 @@ def time_mimc_prove(log_steps: int, ext: int, threads=None):
     air = airs.mimc128(steps)
     a = bench.mimc_assertions(steps)
     L = lib()
-    if threads:
-        L.oracle_set_threads(int(threads))
+    if not threads:
+        # physical cores: hyper-threads do not help these memory-bound loops (measured: 128 threads slower than 64)
+        ncpu = os.cpu_count() or 1
+        threads = ncpu // 2 if ncpu > 16 else ncpu
+    L.oracle_set_threads(int(threads))
     n = L.oracle_threads()
     t = time.perf_counter()
     prove(air, dict(bench.OPTS, extensionFactor=ext), a, [], [3])

@@ -43,6 +43,10 @@ def test_mimc_proof_bytes_match_oracle(steps, e, alg):
     assert gpu.serialize(proof) == got
     assert gpu.sizeOf(proof) == len(got)
     assert ora.verify(a, ora.parse(got))
+    # and so does the library's own verifier (Stark.verify)
+    assert gpu.verify(a, proof)
+    with pytest.raises(StarkError):
+        gpu.verify([dict(a[0]), dict(a[1], value=a[1]['value'] + 1)], proof)
 
 
 def test_wrong_assertion_is_rejected_like_the_reference():
