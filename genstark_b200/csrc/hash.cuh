@@ -228,6 +228,26 @@ __global__ void __launch_bounds__(1024) merkle_tail_kernel(uint32_t* __restrict_
     }
 }
 
+// x* = field.prng(root) = SHA-256(root) as a big-endian integer mod p (LowDegreeProver.ts:194) computed on the
+// device, so a FRI layer can be folded without a host round trip.  One thread.
+__global__ void fri_challenge_kernel(const uint32_t* __restrict__ root, fp* __restrict__ out) {
+    uint32_t d[8];
+    auto get = [&](int w) -> uint32_t { return root[w]; };
+    hash_words<HASH_SHA256>(get, 8, d);
+    // d[] holds the digest bytes as little-endian words of the byte string; big-endian integer: byte 0 is most significant
+    uint32_t be[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) be[i] = bswap32(d[i]);          // be[0] = most significant 32 bits
+    fp hi, lo;
+    hi.v[3] = be[0]; hi.v[2] = be[1]; hi.v[1] = be[2]; hi.v[0] = be[3];
+    lo.v[3] = be[4]; lo.v[2] = be[5]; lo.v[1] = be[6]; lo.v[0] = be[7];
+    // canonical residues of the two halves, then lo + hi * 2^128 = lo + hi * (9*2^32 - 1)
+    const fp zero = fp_zero();
+    hi = fp_add(hi, zero); lo = fp_add(lo, zero);                 // fp_add canonicalises (adds 2^128 - p when >= p)
+    fp c9; c9.v[0] = 0xFFFFFFFFu; c9.v[1] = 8u; c9.v[2] = 0; c9.v[3] = 0;
+    st_fp(out, fp_add(lo, fp_mul(hi, c9)));
+}
+
 static inline unsigned grid_for(Ctx* c, long long n, int threads, int waves = 8) {
     long long blocks = (n + threads - 1) / threads;
     const long long cap = (long long)c->sm_count * waves;

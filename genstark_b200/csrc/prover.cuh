@@ -52,6 +52,7 @@ struct Stark : public AirHost {
     bool keep_intermediates = false;  // stage-level parity tests read P/C/L back
     bool trace_resident = false;      // d_trace / d_in_trace hold the last proved trace
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t layer_ev[24] = {nullptr};   // root of FRI layer d is in the mailbox
     float last_device_ms = 0;         // CUDA-event time from the first enqueue to the last kernel of prove()
     double last_host_ms = 0;          // wall clock of the whole call
     ~Stark() {
@@ -60,6 +61,7 @@ struct Stark : public AirHost {
         if (h_trace) cudaFreeHost(h_trace);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (auto& e : layer_ev) if (e) cudaEventDestroy(e);
     }
 };
 
@@ -399,62 +401,39 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     fp* v_next = S->d_fri.as<fp>() + 4;
     uint32_t* t_next = S->d_fri_trees.as<uint32_t>();
     fp* v_cur = S->d_l.as<fp>();
-    bool flag_checked = false;
-    std::vector<u128> remainder;
-    long long max_deg_p1 = comp_degree;
+    // The whole layer chain is enqueued without host round trips: each challenge x* = prng(root_d) is derived on
+    // the device; roots are copied to mailbox slots as they appear and the host plans the queries behind them.
+    uint8_t* mb = (uint8_t*)c->mailbox;
+    const size_t MB_ROOT = 64, MB_REM = 4096;
+    int n_layers = 0;
     for (int depth = 0;; ++depth) {
         const long long L = N >> (2 * depth), Q = L >> 2;
         FriLayer ly; ly.v = v_cur; ly.len = L; ly.tree = t_next; t_next += (size_t)2 * Q * 8;
         HashCols hc; hc.ncols = 4; for (int j = 0; j < 4; ++j) hc.col[j] = v_cur + j * Q;
         if ((rc = hash_columns(c, S->hash_alg, hc, Q, ly.tree + 8 * Q))) return rc;
         if ((rc = merkle_build(c, S->hash_alg, ly.tree, Q))) return rc;
-        GS_CUDA(c, cudaMemcpyAsync((uint8_t*)c->mailbox + 64, ly.tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
-        GS_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (!flag_checked) {
-            flag_checked = true;
-            const int* fl = (const int*)c->mailbox;
-            if (fl[0] != 0) return c->fail(GS_E_STARK, "Failed to evaluate transition constraints: Constraint %d didn't evaluate to 0 at step %d", fl[0] - 1, fl[1]);
-            if (timing) mark("Computed composition polynomial C(x) and combined P(x), S(x)", false);
-        }
-        memcpy(ly.root, (uint8_t*)c->mailbox + 64, 32);
-        layers.push_back(ly);
+        if (depth >= 24) return c->fail(GS_E_UNSUPPORTED, "too many FRI layers");
+        GS_CUDA(c, cudaMemcpyAsync(mb + MB_ROOT + 32 * depth, ly.tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
+        if (!S->layer_ev[depth]) cudaEventCreateWithFlags(&S->layer_ev[depth], cudaEventDisableTiming);
+        cudaEventRecord(S->layer_ev[depth], c->stream);
+        layers.push_back(ly); ++n_layers;
         if (L <= 256) {
-            // remainder: transposeMatrix + joinMatrixRows restores natural order (:179-186)
-            GS_CUDA(c, cudaMemcpyAsync(c->mailbox, v_cur, L * sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
-            GS_CUDA(c, cudaStreamSynchronize(c->stream));
-            remainder.resize(L);
-            for (long long i = 0; i < L; ++i) remainder[i] = fp_to_u128(((const fp*)c->mailbox)[i]);
-            // verifyRemainder (:223-252)
-            const u128 rou = h_pow(w_n, (u128)1 << (2 * depth));
-            std::vector<long long> pos;
-            for (long long i = 0; i < L; ++i) if (i % E) pos.push_back(i);
-            if (max_deg_p1 > (long long)pos.size()) return c->fail(GS_E_STARK, "Low degree proof failed: remainder too short for degree %lld", max_deg_p1);
-            std::vector<u128> dom(L); { u128 a = 1; for (long long i = 0; i < L; ++i) { dom[i] = a; a = h_mul(a, rou); } }
-            std::vector<u128> xs(max_deg_p1), ys(max_deg_p1);
-            for (long long i = 0; i < max_deg_p1; ++i) { xs[i] = dom[pos[i]]; ys[i] = remainder[pos[i]]; }
-            const std::vector<u128> poly = h_interpolate(xs, ys);
-            for (size_t i = (size_t)max_deg_p1; i < pos.size(); ++i)
-                if (h_eval_poly(poly, dom[pos[i]]) != remainder[pos[i]])
-                    return c->fail(GS_E_STARK, "Low degree proof failed: Remainder is not a valid degree %lld polynomial", max_deg_p1 - 1);
+            GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM, v_cur, L * sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
             break;
         }
-        // challenge and fold
-        const fp sx = fp_from_u128(prng_one(ly.root, 32));                               // :194
-        GS_CUDA(c, cudaMemcpyAsync(d_special, &sx, sizeof(fp), cudaMemcpyHostToDevice, c->stream));
-        FriFoldParams F; F.v = v_cur; F.out = v_next; F.quarter = Q; F.special_x = d_special;
-        F.tw_lo = c->tw_lo; F.tw_hi = c->tw_hi; F.log_g = c->log_g; F.log_lo = c->log_lo;
-        F.x_shift = 2 * depth + (c->log_g - log_n); F.iota_inv = fp_from_u128(iota_inv); F.quarter_inv = fp_from_u128(quarter_inv);
-        { ProfScope ps(c, "fri_fold"); fri_fold_kernel<<<grid_for(c, Q, 256), 256, 0, c->stream>>>(F); }
-        c->launches++;
+        { ProfScope ps(c, "fri_fold");
+          fri_challenge_kernel<<<1, 1, 0, c->stream>>>(ly.tree + 8, d_special + (depth & 3));
+          FriFoldParams F; F.v = v_cur; F.out = v_next; F.quarter = Q; F.special_x = d_special + (depth & 3);
+          F.tw_lo = c->tw_lo; F.tw_hi = c->tw_hi; F.log_g = c->log_g; F.log_lo = c->log_lo;
+          F.x_shift = 2 * depth + (c->log_g - log_n); F.iota_inv = fp_from_u128(iota_inv); F.quarter_inv = fp_from_u128(quarter_inv);
+          fri_fold_kernel<<<grid_for(c, Q, 256), 256, 0, c->stream>>>(F); }
+        c->launches += 2;
         v_cur = v_next; v_next += Q;
-        max_deg_p1 /= 4;
     }
-    mark("Computed low-degree proof (layers)", false);
+    cudaEventRecord(S->ev1, c->stream);     // end of the enqueued chain (remainder copy included)
 
-    // ---- query phase: every position depends only on the roots, so all rows and Merkle nodes of all trees
-    // are planned on the host, fetched by ONE gather kernel and ONE device->host copy
+    // ---- query phase, planned on the host while the device runs the layers
     std::string err;
-    const uint8_t* lc_root = layers[0].root;
     std::vector<unsigned long long> g_addr;
     auto add_chunk = [&](const void* p) { g_addr.push_back((unsigned long long)(uintptr_t)p); return g_addr.size() - 1; };
     struct PlannedProof { BatchProof bp; std::vector<size_t> node_chunk; std::vector<size_t> value_chunk; int chunks_per_value = 0; };
@@ -472,38 +451,66 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         return first_seen_unique(m);
     };
     auto row_cols = [&](const FriLayer& ly) { std::vector<const fp*> cols; for (int j = 0; j < 4; ++j) cols.push_back(ly.v + j * (ly.len >> 2)); return cols; };
-    std::vector<uint32_t> exe_pos;
-    if (pseudorandom_indexes(lc_root, (int)std::min<long long>(S->exe_queries, N - N / E), (uint64_t)N, (uint64_t)E, exe_pos, err) != 0)
-        return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str());
     PlannedProof lc_pp, ev_pp;
-    if ((rc = plan_proof(lc_pp, layers[0].tree, (uint64_t)(N >> 2), aug4(exe_pos, N), row_cols(layers[0])))) return rc;
     struct Comp { const uint8_t* root; PlannedProof column, poly; };
     std::vector<Comp> comps(layers.size() - 1);
-    for (size_t d = 0; d + 1 < layers.size(); ++d) {
-        const FriLayer& pl = layers[d]; const FriLayer& cl = layers[d + 1];
-        std::vector<uint32_t> positions;
-        if (pseudorandom_indexes(cl.root, S->fri_queries, (uint64_t)cl.len, (uint64_t)E, positions, err) != 0)
-            return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str());
-        comps[d].root = cl.root;
-        if ((rc = plan_proof(comps[d].column, cl.tree, (uint64_t)(cl.len >> 2), aug4(positions, cl.len), row_cols(cl)))) return rc;
-        if ((rc = plan_proof(comps[d].poly, pl.tree, (uint64_t)(pl.len >> 2), positions, row_cols(pl)))) return rc;
+    for (int d = 0; d < n_layers; ++d) {
+        GS_CUDA(c, cudaEventSynchronize(S->layer_ev[d]));
+        memcpy(layers[d].root, mb + MB_ROOT + 32 * d, 32);
+        if (d == 0) {
+            const int* fl = (const int*)c->mailbox;
+            if (fl[0] != 0) { cudaStreamSynchronize(c->stream); return c->fail(GS_E_STARK, "Failed to evaluate transition constraints: Constraint %d didn't evaluate to 0 at step %d", fl[0] - 1, fl[1]); }
+            // lcProof and the trace queries depend on root_0 only (LowDegreeProver.ts:50-54, Stark.ts:147-151)
+            std::vector<uint32_t> exe_pos;
+            if (pseudorandom_indexes(layers[0].root, (int)std::min<long long>(S->exe_queries, N - N / E), (uint64_t)N, (uint64_t)E, exe_pos, err) != 0) {
+                cudaStreamSynchronize(c->stream); return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str()); }
+            if ((rc = plan_proof(lc_pp, layers[0].tree, (uint64_t)(N >> 2), aug4(exe_pos, N), row_cols(layers[0])))) return rc;
+            std::vector<uint32_t> m;
+            for (uint32_t p : exe_pos) { m.push_back(p); m.push_back((uint32_t)((p + E) % N)); }
+            if ((rc = plan_proof(ev_pp, e_tree, (uint64_t)N, first_seen_unique(m), e_cols))) return rc;
+        } else {
+            const FriLayer& pl = layers[d - 1]; const FriLayer& cl = layers[d];
+            std::vector<uint32_t> positions;
+            if (pseudorandom_indexes(cl.root, S->fri_queries, (uint64_t)cl.len, (uint64_t)E, positions, err) != 0) {
+                cudaStreamSynchronize(c->stream); return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str()); }
+            comps[d - 1].root = cl.root;
+            if ((rc = plan_proof(comps[d - 1].column, cl.tree, (uint64_t)(cl.len >> 2), aug4(positions, cl.len), row_cols(cl)))) return rc;
+            if ((rc = plan_proof(comps[d - 1].poly, pl.tree, (uint64_t)(pl.len >> 2), positions, row_cols(pl)))) return rc;
+        }
     }
-    // 8 ---- trace queries (Stark.ts:147-151)
+    const uint8_t* lc_root = layers[0].root;
+    // remainder (already on its way): verifyRemainder (:223-252)
+    std::vector<u128> remainder;
     {
-        std::vector<uint32_t> m;
-        for (uint32_t p : exe_pos) { m.push_back(p); m.push_back((uint32_t)((p + E) % N)); }
-        if ((rc = plan_proof(ev_pp, e_tree, (uint64_t)N, first_seen_unique(m), e_cols))) return rc;
+        GS_CUDA(c, cudaEventSynchronize(S->ev1));
+        const int depth = n_layers - 1;
+        const long long L = layers[depth].len;
+        long long max_deg_p1 = comp_degree; for (int d = 0; d < depth; ++d) max_deg_p1 /= 4;
+        remainder.resize(L);
+        for (long long i = 0; i < L; ++i) remainder[i] = fp_to_u128(((const fp*)(mb + MB_REM))[i]);
+        const u128 rou = h_pow(w_n, (u128)1 << (2 * depth));
+        std::vector<long long> pos;
+        for (long long i = 0; i < L; ++i) if (i % E) pos.push_back(i);
+        if (max_deg_p1 > (long long)pos.size()) return c->fail(GS_E_STARK, "Low degree proof failed: remainder too short for degree %lld", max_deg_p1);
+        std::vector<u128> dom(L); { u128 a = 1; for (long long i = 0; i < L; ++i) { dom[i] = a; a = h_mul(a, rou); } }
+        std::vector<u128> xs(max_deg_p1), ys(max_deg_p1);
+        for (long long i = 0; i < max_deg_p1; ++i) { xs[i] = dom[pos[i]]; ys[i] = remainder[pos[i]]; }
+        const std::vector<u128> poly = h_interpolate(xs, ys);
+        for (size_t i = (size_t)max_deg_p1; i < pos.size(); ++i)
+            if (h_eval_poly(poly, dom[pos[i]]) != remainder[pos[i]])
+                return c->fail(GS_E_STARK, "Low degree proof failed: Remainder is not a valid degree %lld polynomial", max_deg_p1 - 1);
     }
+    if (timing) mark("Computed low-degree proof (layers)", false);
     {
         const size_t nch = g_addr.size();
-        if (nch * 16 > c->mailbox_bytes) return c->fail(GS_E_STARK, "query phase needs %zu bytes of mailbox", nch * 16);
+        if (MB_REM + 4096 + nch * 16 > c->mailbox_bytes) return c->fail(GS_E_STARK, "query phase needs %zu bytes of mailbox", nch * 16);
         if ((rc = S->d_idx.ensure(c, nch * 8))) return rc;
         if ((rc = S->d_gather.ensure(c, nch * 16))) return rc;
         GS_CUDA(c, cudaMemcpyAsync(S->d_idx.p, g_addr.data(), nch * 8, cudaMemcpyHostToDevice, c->stream));
         { ProfScope ps(c, "gather_queries");
           gather_chunks_kernel<<<(unsigned)((nch + 255) / 256), 256, 0, c->stream>>>(S->d_idx.as<unsigned long long>(), (int)nch, S->d_gather.as<uint4>()); }
         c->launches++;
-        GS_CUDA(c, cudaMemcpyAsync(c->mailbox, S->d_gather.p, nch * 16, cudaMemcpyDeviceToHost, c->stream));
+        GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM + 4096, S->d_gather.p, nch * 16, cudaMemcpyDeviceToHost, c->stream));
     }
     cudaEventRecord(S->ev1, c->stream);
     cudaEventSynchronize(S->ev1);
@@ -511,7 +518,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     S->trace_resident = true;
     if (c->profiling) c->prof_collect();
     {
-        const uint8_t* mb = (const uint8_t*)c->mailbox;
+        const uint8_t* mb = (const uint8_t*)c->mailbox + 4096 + 4096;
         auto fill = [&](PlannedProof& pp) {
             size_t k = 0;
             pp.bp.nodes.assign(pp.bp.node_ids.size(), {});
