@@ -32,6 +32,11 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// A captured launch sequence.  Buffers and kernel arguments of a Stark instance are fixed between proves (values that
+// change -- coefficients, assertion data -- live in device memory at fixed addresses), so the ~80 small launches of a
+// prove are captured once per instance and replayed with one cudaGraphLaunch.
+struct GraphSlot { cudaGraphExec_t exec = nullptr; unsigned long long key = 0, launches = 0; };
+
 struct StageTimes {                 // milliseconds, host wall clock around each stage (sync'ed)
     std::vector<std::pair<std::string, double>> items;
 };
@@ -51,6 +56,9 @@ struct Stark : public AirHost {
     StageTimes last_times;
     bool keep_intermediates = false;  // stage-level parity tests read P/C/L back
     bool trace_resident = false;      // d_trace / d_in_trace hold the last proved trace
+    bool use_graphs = true;           // CUDA graphs for the launch-bound chains (off while profiling / stage timing)
+    unsigned long long proves_done = 0;
+    GraphSlot g_commit, g_fri;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t layer_ev[24] = {nullptr};   // root of FRI layer d is in the mailbox
     float last_device_ms = 0;         // CUDA-event time from the first enqueue to the last kernel of prove()
@@ -59,6 +67,8 @@ struct Stark : public AirHost {
         for (DevBuf* b : {&d_instrs, &d_consts, &d_cyc, &d_u, &d_trace, &d_poly, &d_pe, &d_in_trace, &d_in_poly, &d_in_e, &d_work, &d_tree,
                           &d_zb, &d_zbs, &d_l, &d_c, &d_fri, &d_fri_trees, &d_params, &d_small, &d_idx, &d_gather}) b->release();
         if (h_trace) cudaFreeHost(h_trace);
+        if (g_commit.exec) cudaGraphExecDestroy(g_commit.exec);
+        if (g_fri.exec) cudaGraphExecDestroy(g_fri.exec);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         for (auto& e : layer_ev) if (e) cudaEventDestroy(e);
@@ -91,6 +101,31 @@ static inline u128 h_eval_poly(const std::vector<u128>& poly, u128 x) {
 }
 
 struct Assertion { uint32_t reg, step; u128 value; };
+
+// run `fn` (which only enqueues work on the context stream) directly, or capture it once and replay it
+template <typename F>
+static inline int run_region(Stark* S, GraphSlot& slot, unsigned long long key, bool allow_graph, F&& fn) {
+    Ctx* c = S->ctx;
+    if (!allow_graph) return fn();
+    if (!slot.exec || slot.key != key) {
+        if (slot.exec) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+        const unsigned long long l0 = c->launches;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); S->use_graphs = false; return fn(); }
+        const int rc = fn();
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (rc != GS_OK) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }
+        if (e != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); cudaGetLastError(); S->use_graphs = false; c->launches = l0; return fn(); }
+        const cudaError_t e2 = cudaGraphInstantiate(&slot.exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e2 != cudaSuccess) { slot.exec = nullptr; cudaGetLastError(); S->use_graphs = false; c->launches = l0; return fn(); }
+        slot.key = key; slot.launches = c->launches - l0; c->launches = l0;
+    }
+    const cudaError_t e = cudaGraphLaunch(slot.exec, c->stream);
+    if (e != cudaSuccess) return c->cuda_fail(e, "cudaGraphLaunch");
+    c->launches += slot.launches;
+    return GS_OK;
+}
 
 struct FriLayer {
     fp* v; long long len; uint32_t* tree; uint8_t root[32];
@@ -206,30 +241,23 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     }
     mark("Generated execution trace", false);
 
-    // 3 ---- P(x) = iNTT(trace); low-degree extension over the evaluation domain
+    // 3-4 ---- P(x) = iNTT(trace); low-degree extension; leaf hashing; Merkle tree  (one captured region)
     cudaEventRecord(S->ev0, c->stream);
-    if ((rc = S->d_trace.ensure(c, trace_bytes))) return rc;
-    if ((rc = S->d_poly.ensure(c, trace_bytes))) return rc;
-    if ((rc = S->d_pe.ensure(c, (size_t)R * N * sizeof(fp)))) return rc;
     const int wrows = R > n_in ? R : (n_in > 0 ? n_in : 1);
-    if ((rc = S->d_work.ensure(c, (size_t)wrows * N * sizeof(fp)))) return rc;
-    if (!reuse_trace) GS_CUDA(c, cudaMemcpyAsync(S->d_trace.p, S->h_trace, trace_bytes, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = ntt_run(c, S->d_trace.as<fp>(), T, S->d_poly.as<fp>(), T, S->d_work.as<fp>(), T, R, log_t, 0, true))) return rc;
-    if (timing) mark("Computed execution trace polynomials P(x)", true);
-    if ((rc = ntt_run(c, S->d_poly.as<fp>(), T, S->d_pe.as<fp>(), N, S->d_work.as<fp>(), N, R, log_t, log_e, false))) return rc;
-    // input registers (secret: committed; public: only feed the constraints)
-    if (n_in > 0) {
-        const size_t in_bytes = (size_t)n_in * T * sizeof(fp);
-        if ((rc = S->d_in_trace.ensure(c, in_bytes))) return rc;
-        if ((rc = S->d_in_poly.ensure(c, in_bytes))) return rc;
-        if ((rc = S->d_in_e.ensure(c, (size_t)n_in * N * sizeof(fp)))) return rc;
-        if (!reuse_trace) GS_CUDA(c, cudaMemcpyAsync(S->d_in_trace.p, input_traces, in_bytes, cudaMemcpyHostToDevice, c->stream));
-        if ((rc = ntt_run(c, S->d_in_trace.as<fp>(), T, S->d_in_poly.as<fp>(), T, S->d_work.as<fp>(), T, n_in, log_t, 0, true))) return rc;
-        if ((rc = ntt_run(c, S->d_in_poly.as<fp>(), T, S->d_in_e.as<fp>(), N, S->d_work.as<fp>(), N, n_in, log_t, log_e, false))) return rc;
+    const size_t in_bytes = (size_t)n_in * T * sizeof(fp);
+    long long fri_tot_v = 0, fri_tot_t = 0;
+    for (long long L = N; ; L >>= 2) { fri_tot_t += 2 * (L >> 2); if (L <= 256) break; fri_tot_v += L >> 2; }
+    if ((rc = S->d_trace.ensure(c, trace_bytes)) || (rc = S->d_poly.ensure(c, trace_bytes)) || (rc = S->d_pe.ensure(c, (size_t)R * N * sizeof(fp))) ||
+        (rc = S->d_work.ensure(c, (size_t)wrows * N * sizeof(fp))) || (rc = S->d_tree.ensure(c, (size_t)2 * N * 32)) ||
+        (rc = S->d_l.ensure(c, (size_t)N * sizeof(fp))) || (rc = S->d_fri.ensure(c, (size_t)(fri_tot_v + 4) * sizeof(fp))) ||
+        (rc = S->d_fri_trees.ensure(c, (size_t)fri_tot_t * 32)) || (rc = S->d_params.ensure(c, sizeof(ComposeParams))) ||
+        (rc = S->d_small.ensure(c, 1 << 20))) return rc;
+    if (n_in > 0 && ((rc = S->d_in_trace.ensure(c, in_bytes)) || (rc = S->d_in_poly.ensure(c, in_bytes)) || (rc = S->d_in_e.ensure(c, (size_t)n_in * N * sizeof(fp))))) return rc;
+    if (S->keep_intermediates && (rc = S->d_c.ensure(c, (size_t)N * sizeof(fp)))) return rc;
+    if (!reuse_trace) {
+        GS_CUDA(c, cudaMemcpyAsync(S->d_trace.p, S->h_trace, trace_bytes, cudaMemcpyHostToDevice, c->stream));
+        if (n_in > 0) GS_CUDA(c, cudaMemcpyAsync(S->d_in_trace.p, input_traces, in_bytes, cudaMemcpyHostToDevice, c->stream));
     }
-    if (timing) mark("Low-degree extended P(x) polynomials over evaluation domain", true);
-
-    // 4 ---- Merkle tree over leaf_i = H(P_0[i] || .. || S_0[i] || ..)
     std::vector<const fp*> e_cols;            // eVectors: trace rows then secret rows (Stark.ts:113-114)
     for (int r = 0; r < R; ++r) e_cols.push_back(S->d_pe.as<fp>() + (size_t)r * N);
     std::vector<const fp*> in_cols(S->statics.size(), nullptr);
@@ -239,17 +267,34 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         for (size_t k = 0; k < S->statics.size(); ++k) if (S->statics[k].kind == 1) e_cols.push_back(in_cols[k]);
     }
     if (e_cols.size() > GS_MAX_HASH_COLS) return c->fail(GS_E_UNSUPPORTED, "more than %d committed registers", GS_MAX_HASH_COLS);
-    if ((rc = S->d_tree.ensure(c, (size_t)2 * N * 32))) return rc;
     uint32_t* e_tree = S->d_tree.as<uint32_t>();
-    {
+    const bool graphs = S->use_graphs && !c->profiling && !timing && S->proves_done > 0;
+    // any reallocation changes a pointer below and invalidates the captured graphs
+    unsigned long long gkey = 1469598103934665603ull;
+    for (const DevBuf* b : {&S->d_trace, &S->d_poly, &S->d_pe, &S->d_work, &S->d_tree, &S->d_l, &S->d_fri, &S->d_fri_trees, &S->d_params,
+                            &S->d_small, &S->d_in_trace, &S->d_in_poly, &S->d_in_e, &S->d_c, &S->d_u, &S->d_cyc, &S->d_instrs, &S->d_consts})
+        gkey = (gkey ^ (unsigned long long)(uintptr_t)b->p) * 1099511628211ull;
+    gkey = (gkey ^ (unsigned long long)S->keep_intermediates) * 1099511628211ull;
+    auto commit_region = [&]() -> int {
+        int r2;
+        if ((r2 = ntt_run(c, S->d_trace.as<fp>(), T, S->d_poly.as<fp>(), T, S->d_work.as<fp>(), T, R, log_t, 0, true))) return r2;
+        if (timing) mark("Computed execution trace polynomials P(x)", true);
+        if ((r2 = ntt_run(c, S->d_poly.as<fp>(), T, S->d_pe.as<fp>(), N, S->d_work.as<fp>(), N, R, log_t, log_e, false))) return r2;
+        if (n_in > 0) {      // input registers (secret: committed; public: only feed the constraints)
+            if ((r2 = ntt_run(c, S->d_in_trace.as<fp>(), T, S->d_in_poly.as<fp>(), T, S->d_work.as<fp>(), T, n_in, log_t, 0, true))) return r2;
+            if ((r2 = ntt_run(c, S->d_in_poly.as<fp>(), T, S->d_in_e.as<fp>(), N, S->d_work.as<fp>(), N, n_in, log_t, log_e, false))) return r2;
+        }
+        if (timing) mark("Low-degree extended P(x) polynomials over evaluation domain", true);
         HashCols hc; hc.ncols = (int)e_cols.size();
         for (size_t i = 0; i < e_cols.size(); ++i) hc.col[i] = e_cols[i];
-        if ((rc = hash_columns(c, S->hash_alg, hc, N, e_tree + 8 * N))) return rc;
-    }
-    if (timing) mark("Serialized evaluations of P(x) and S(x) polynomials", true);
-    if ((rc = merkle_build(c, S->hash_alg, e_tree, N))) return rc;
+        if ((r2 = hash_columns(c, S->hash_alg, hc, N, e_tree + 8 * N))) return r2;
+        if (timing) mark("Serialized evaluations of P(x) and S(x) polynomials", true);
+        if ((r2 = merkle_build(c, S->hash_alg, e_tree, N))) return r2;
+        GS_CUDA(c, cudaMemcpyAsync(c->mailbox, e_tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
+        return GS_OK;
+    };
+    if ((rc = run_region(S, S->g_commit, gkey, graphs, commit_region))) return rc;
     uint8_t ev_root[32];
-    GS_CUDA(c, cudaMemcpyAsync(c->mailbox, e_tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
     GS_CUDA(c, cudaStreamSynchronize(c->stream));
     memcpy(ev_root, c->mailbox, 32);
     mark("Built evaluation merkle tree", false);
@@ -337,18 +382,16 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     // small-object upload: one packed buffer
     std::vector<uint8_t> small;
     auto put = [&](const void* p, size_t n) { size_t off = (small.size() + 15) & ~(size_t)15; small.resize(off + n); memcpy(small.data() + off, p, n); return off; };
+    const size_t o_flag = put("\0\0\0\0\0\0\0\0", 8);        // fixed offset 0: the captured graph copies it back
     const size_t o_dk = put(dk.data(), K * 16), o_dka = put(dk_adj.data(), K * 16), o_pi = put(pow_idx.data(), K * 4);
     const size_t o_bk = put(bk.data(), nB * 16), o_bka = put(bk_adj.data(), nB * 16);
     const size_t o_ip = put(ipoly.data(), ipoly.size() * 16), o_pc = put(pf_coef.data(), pf_coef.size() * 16), o_ps = put(pf_shift.data(), pf_shift.size() * 4);
     const size_t o_io = put(ioff.data(), nB * 4), o_il = put(ilen.data(), nB * 4), o_po = put(pfoff.data(), nB * 4), o_pl = put(pflen.data(), nB * 4);
     const size_t o_br = put(breg.data(), nB * 4);
     const size_t o_lk = put(lk.data(), n_lc * 16), o_lka = put(lk_adj.data(), n_lc * 16), o_in = put(inv_num.data(), E * 16);
-    const size_t o_flag = put("\0\0\0\0\0\0\0\0", 8);
-    if ((rc = S->d_small.ensure(c, small.size() + 64))) return rc;
+    if (small.size() + 64 > S->d_small.cap) return c->fail(GS_E_UNSUPPORTED, "too many assertions / constraints for the parameter block");
     uint8_t* ds = S->d_small.as<uint8_t>();
     GS_CUDA(c, cudaMemcpyAsync(ds, small.data(), small.size(), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = S->d_l.ensure(c, (size_t)N * sizeof(fp)))) return rc;
-    if (S->keep_intermediates && (rc = S->d_c.ensure(c, (size_t)N * sizeof(fp)))) return rc;
     {
         ComposeParams P; memset(&P, 0, sizeof P);
         P.n = N; P.log_n = log_n; P.log_e = log_e;
@@ -372,8 +415,18 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         P.tw_lo = c->tw_lo; P.tw_hi = c->tw_hi; P.log_g = c->log_g; P.log_lo = c->log_lo;
         P.out = S->d_l.as<fp>(); P.c_out = S->keep_intermediates ? S->d_c.as<fp>() : nullptr;
         P.fail_flag = (int*)(ds + o_flag);
-        if ((rc = S->d_params.ensure(c, sizeof P))) return rc;
         GS_CUDA(c, cudaMemcpyAsync(S->d_params.p, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
+    }
+    // 5b-7 ---- compose + the whole FRI layer chain (second captured region)
+    std::vector<FriLayer> layers;
+    uint8_t* mb = (uint8_t*)c->mailbox;
+    const size_t MB_ROOT = 64, MB_REM = 4096;
+    int n_layers = 0;
+    for (int d = 0; d < 24; ++d) if (!S->layer_ev[d]) cudaEventCreateWithFlags(&S->layer_ev[d], cudaEventDisableTiming);
+    auto fri_region = [&]() -> int {
+        int rc;   // shadows the outer one on purpose: this lambda may run under stream capture
+        layers.clear(); n_layers = 0;
+        {
         const unsigned g = grid_for(c, N, 256);
         const int ns = S->evaluation.n_slots;
         ProfScope ps(c, "compose");
@@ -385,16 +438,8 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return c->cuda_fail(e, "compose_kernel");
         GS_CUDA(c, cudaMemcpyAsync(c->mailbox, ds + o_flag, 8, cudaMemcpyDeviceToHost, c->stream));
-    }
-
+        }
     // 7 ---- low-degree proof (LowDegreeProver.ts:39-68,176-221)
-    std::vector<FriLayer> layers;
-    {
-        long long tot_v = 0, tot_t = 0;
-        for (long long L = N; ; L >>= 2) { tot_t += 2 * (L >> 2); if (L <= 256) break; tot_v += L >> 2; }
-        if ((rc = S->d_fri.ensure(c, (size_t)(tot_v + 4) * sizeof(fp)))) return rc;
-        if ((rc = S->d_fri_trees.ensure(c, (size_t)tot_t * 32))) return rc;
-    }
     const u128 iota_inv = h_inv(c->root_of_order(2));
     const u128 quarter_inv = h_inv(4);
     fp* d_special = S->d_fri.as<fp>();            // slot 0..3 reserved for the challenge
@@ -403,9 +448,6 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     fp* v_cur = S->d_l.as<fp>();
     // The whole layer chain is enqueued without host round trips: each challenge x* = prng(root_d) is derived on
     // the device; roots are copied to mailbox slots as they appear and the host plans the queries behind them.
-    uint8_t* mb = (uint8_t*)c->mailbox;
-    const size_t MB_ROOT = 64, MB_REM = 4096;
-    int n_layers = 0;
     for (int depth = 0;; ++depth) {
         const long long L = N >> (2 * depth), Q = L >> 2;
         FriLayer ly; ly.v = v_cur; ly.len = L; ly.tree = t_next; t_next += (size_t)2 * Q * 8;
@@ -414,7 +456,6 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         if ((rc = merkle_build(c, S->hash_alg, ly.tree, Q))) return rc;
         if (depth >= 24) return c->fail(GS_E_UNSUPPORTED, "too many FRI layers");
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_ROOT + 32 * depth, ly.tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
-        if (!S->layer_ev[depth]) cudaEventCreateWithFlags(&S->layer_ev[depth], cudaEventDisableTiming);
         cudaEventRecord(S->layer_ev[depth], c->stream);
         layers.push_back(ly); ++n_layers;
         if (L <= 256) {
@@ -429,6 +470,20 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
           fri_fold_kernel<<<grid_for(c, Q, 256), 256, 0, c->stream>>>(F); }
         c->launches += 2;
         v_cur = v_next; v_next += Q;
+    }
+        return GS_OK;
+    };
+    if ((rc = run_region(S, S->g_fri, gkey ^ 0x9E3779B97F4A7C15ull, graphs, fri_region))) return rc;
+    if (graphs && layers.empty()) {
+        // replayed graph: rebuild the layer table (pure pointer arithmetic, no launches)
+        fp* vc = S->d_l.as<fp>(); fp* vn = S->d_fri.as<fp>() + 4; uint32_t* tn = S->d_fri_trees.as<uint32_t>();
+        for (int depth = 0;; ++depth) {
+            const long long L = N >> (2 * depth), Q = L >> 2;
+            FriLayer ly; ly.v = vc; ly.len = L; ly.tree = tn; tn += (size_t)2 * Q * 8;
+            layers.push_back(ly); ++n_layers;
+            if (L <= 256) break;
+            vc = vn; vn += Q;
+        }
     }
     cudaEventRecord(S->ev1, c->stream);     // end of the enqueued chain (remainder copy included)
 
@@ -516,6 +571,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     cudaEventSynchronize(S->ev1);
     cudaEventElapsedTime(&S->last_device_ms, S->ev0, S->ev1);
     S->trace_resident = true;
+    S->proves_done++;
     if (c->profiling) c->prof_collect();
     {
         const uint8_t* mb = (const uint8_t*)c->mailbox + 4096 + 4096;
