@@ -3,6 +3,7 @@
 // 32-byte Merkle roots (for Fiat-Shamir), the <= 256-value FRI remainder and the queried rows.
 #pragma once
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include "core.cuh"
@@ -60,7 +61,7 @@ struct Stark : public AirHost {
     unsigned long long proves_done = 0;
     GraphSlot g_commit, g_fri;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t layer_ev[24] = {nullptr};   // root of FRI layer d is in the mailbox
+    DevBuf d_epoch;                         // prove counter, copied behind each FRI root so the host can poll for it
     float last_device_ms = 0;         // CUDA-event time from the first enqueue to the last kernel of prove()
     double last_host_ms = 0;          // wall clock of the whole call
     ~Stark() {
@@ -71,7 +72,7 @@ struct Stark : public AirHost {
         if (g_fri.exec) cudaGraphExecDestroy(g_fri.exec);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        for (auto& e : layer_ev) if (e) cudaEventDestroy(e);
+        d_epoch.release();
     }
 };
 
@@ -251,7 +252,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         (rc = S->d_work.ensure(c, (size_t)wrows * N * sizeof(fp))) || (rc = S->d_tree.ensure(c, (size_t)2 * N * 32)) ||
         (rc = S->d_l.ensure(c, (size_t)N * sizeof(fp))) || (rc = S->d_fri.ensure(c, (size_t)(fri_tot_v + 4) * sizeof(fp))) ||
         (rc = S->d_fri_trees.ensure(c, (size_t)fri_tot_t * 32)) || (rc = S->d_params.ensure(c, sizeof(ComposeParams))) ||
-        (rc = S->d_small.ensure(c, 1 << 20))) return rc;
+        (rc = S->d_small.ensure(c, 1 << 20)) || (rc = S->d_epoch.ensure(c, 16))) return rc;
     if (n_in > 0 && ((rc = S->d_in_trace.ensure(c, in_bytes)) || (rc = S->d_in_poly.ensure(c, in_bytes)) || (rc = S->d_in_e.ensure(c, (size_t)n_in * N * sizeof(fp))))) return rc;
     if (S->keep_intermediates && (rc = S->d_c.ensure(c, (size_t)N * sizeof(fp)))) return rc;
     if (!reuse_trace) {
@@ -272,7 +273,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     // any reallocation changes a pointer below and invalidates the captured graphs
     unsigned long long gkey = 1469598103934665603ull;
     for (const DevBuf* b : {&S->d_trace, &S->d_poly, &S->d_pe, &S->d_work, &S->d_tree, &S->d_l, &S->d_fri, &S->d_fri_trees, &S->d_params,
-                            &S->d_small, &S->d_in_trace, &S->d_in_poly, &S->d_in_e, &S->d_c, &S->d_u, &S->d_cyc, &S->d_instrs, &S->d_consts})
+                            &S->d_small, &S->d_in_trace, &S->d_in_poly, &S->d_in_e, &S->d_c, &S->d_u, &S->d_cyc, &S->d_instrs, &S->d_consts, &S->d_epoch})
         gkey = (gkey ^ (unsigned long long)(uintptr_t)b->p) * 1099511628211ull;
     gkey = (gkey ^ (unsigned long long)S->keep_intermediates) * 1099511628211ull;
     auto commit_region = [&]() -> int {
@@ -420,9 +421,12 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     // 5b-7 ---- compose + the whole FRI layer chain (second captured region)
     std::vector<FriLayer> layers;
     uint8_t* mb = (uint8_t*)c->mailbox;
-    const size_t MB_ROOT = 64, MB_REM = 4096;
+    const size_t MB_FLAG = 16, MB_ROOT = 128, MB_REM = 4096;
     int n_layers = 0;
-    for (int d = 0; d < 24; ++d) if (!S->layer_ev[d]) cudaEventCreateWithFlags(&S->layer_ev[d], cudaEventDisableTiming);
+    // epoch flag: the chain copies it to the mailbox right behind each layer root; the host polls for it
+    // (events recorded inside a captured graph cannot be synchronised from the host)
+    const uint32_t epoch = (uint32_t)(S->proves_done + 1);
+    GS_CUDA(c, cudaMemcpyAsync(S->d_epoch.p, &epoch, 4, cudaMemcpyHostToDevice, c->stream));
     auto fri_region = [&]() -> int {
         int rc;   // shadows the outer one on purpose: this lambda may run under stream capture
         layers.clear(); n_layers = 0;
@@ -456,7 +460,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         if ((rc = merkle_build(c, S->hash_alg, ly.tree, Q))) return rc;
         if (depth >= 24) return c->fail(GS_E_UNSUPPORTED, "too many FRI layers");
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_ROOT + 32 * depth, ly.tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
-        cudaEventRecord(S->layer_ev[depth], c->stream);
+        GS_CUDA(c, cudaMemcpyAsync(mb + MB_FLAG + 4 * depth, S->d_epoch.p, 4, cudaMemcpyDeviceToHost, c->stream));
         layers.push_back(ly); ++n_layers;
         if (L <= 256) {
             GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM, v_cur, L * sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
@@ -510,7 +514,21 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     struct Comp { const uint8_t* root; PlannedProof column, poly; };
     std::vector<Comp> comps(layers.size() - 1);
     for (int d = 0; d < n_layers; ++d) {
-        GS_CUDA(c, cudaEventSynchronize(S->layer_ev[d]));
+        {
+            volatile const uint32_t* flag = (volatile const uint32_t*)(mb + MB_FLAG + 4 * d);
+            unsigned spins = 0;
+            while (*flag != epoch) {
+                _mm_pause();
+                if ((++spins & 0xFFFF) == 0) {
+                    const cudaError_t q = cudaStreamQuery(c->stream);
+                    if (q != cudaErrorNotReady && *flag != epoch) {      // chain finished (or failed) without the flag
+                        if (q != cudaSuccess) return c->cuda_fail(q, "FRI chain");
+                        if (*flag != epoch) return c->fail(GS_E_CUDA, "FRI layer %d never signalled", d);
+                    }
+                }
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+        }
         memcpy(layers[d].root, mb + MB_ROOT + 32 * d, 32);
         if (d == 0) {
             const int* fl = (const int*)c->mailbox;
