@@ -230,9 +230,9 @@ def run_ours(args, rank, local_rank, world):
     launches_per_step = (ctx.launch_count - launches0) // args.steps
     stage_times = st.stage_times()
 
-    # ---- resident leg: trace already in HBM; CUDA events on the prover stream; per-class kernel events
+    # ---- resident leg: trace already in HBM; CUDA events on the prover stream around the whole device part
+    st.prove_bytes(assertions, [], seed, _reuse_resident_trace=True)
     barrier()
-    L.gs_ctx_profile(ctx.handle, 1)
     dev_ms = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -240,6 +240,14 @@ def run_ours(args, rank, local_rank, world):
         dev_ms.append(st.last_timing()[0])
     barrier()
     wall_resident = (time.perf_counter() - t0) * 1e3 / args.steps
+    # ---- same K steps again with CUDA events around every kernel class (CUDA graphs off while profiling, so
+    # this leg is a little slower than the one above; it provides the per-kernel times of the roofline)
+    L.gs_ctx_profile(ctx.handle, 1)
+    prof_dev = []
+    for _ in range(args.steps):
+        st.prove_bytes(assertions, [], seed, _reuse_resident_trace=True)
+        prof_dev.append(st.last_timing()[0])
+    barrier()
     prof = json.loads(L.gs_ctx_profile_report(ctx.handle).decode())
     L.gs_ctx_profile(ctx.handle, 0)
     sampler.stop_flag = True
@@ -305,7 +313,7 @@ def run_ours(args, rank, local_rank, world):
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
                 'traffic': traffic, 'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs)',
                 'kernel_ms_per_step': grouped[dom], 'algorithmic_bytes_per_step': alg,
-                'share_of_step': grouped[dom] / ms_step,
+                'share_of_step': grouped[dom] / (sum(prof_dev) / len(prof_dev)),
                 'note': '128-bit modular arithmetic on 32-bit integer pipes: every kernel here is issue-bound, not HBM-bound'}
 
     cpu = None
@@ -342,7 +350,7 @@ def run_ours(args, rank, local_rank, world):
         'roofline': roofline,
         'cpu_baseline': cpu,
         'kernels_ms_per_step': {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
-        'resident_wall_ms': wall_resident,
+        'resident_wall_ms': wall_resident, 'profiled_leg_ms_per_step': sum(prof_dev) / len(prof_dev),
         'ntt': ntt,
         'clocks': sampler.summary(),
     }

@@ -33,7 +33,9 @@ struct ComposeParams {
     // transition part: q_k * (dk[k] + dk_adj[k] * x^incr[pow_idx[k]])
     int n_constraints;
     const fp* dk; const fp* dk_adj; const int* pow_idx;      // device arrays [K]
-    int n_powers; unsigned long long pow_incr[GS_MAX_POWERS]; // x^incr, incr < N
+    // every degree increment is a multiple of T (comb = cT, group degrees d*T, delta = compDeg - T), so
+    // x^incr = w^(i*incr) depends on i mod E only: tables of E entries, pow_tab[g*E + (i mod E)]
+    int n_powers; const fp* pow_tab; const fp* delta_tab;
     // zero polynomial: D = qc * (x - x_last) * inv_num[i mod E]
     fp x_last; const fp* inv_num;
     // boundary part: for asserted register slot b: (P_reg - I(x)) / Z_b(x) * (bk[b] + bk_adj[b] * x^delta).
@@ -74,11 +76,12 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeParams* __res
         fp slot[NSLOT];
         // powers of x used by this point
         const fp x = root_pow(P, (unsigned long long)i);
+        const unsigned ie = (unsigned)i & (E - 1);
         fp xpow[GS_MAX_POWERS];
 #pragma unroll 1
-        for (int g = 0; g < P.n_powers; ++g) xpow[g] = root_pow(P, ((unsigned long long)i * P.pow_incr[g]) & nmask);
+        for (int g = 0; g < P.n_powers; ++g) xpow[g] = ldg_fp(P.pow_tab + (g << P.log_e) + ie);
         fp xdelta = fp_one();
-        if (P.delta) xdelta = root_pow(P, ((unsigned long long)i * P.delta) & nmask);
+        if (P.delta) xdelta = ldg_fp(P.delta_tab + ie);
 
         // ---- transition constraints, combined on the fly
         fp acc = fp_zero();

@@ -130,8 +130,15 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const NttPassParams P)
     const unsigned tile = blockIdx.x;
     if (!P.final_pass) {
         const int log_tiles_per_pre = P.log_m - P.log_c;
-        pre = tile >> log_tiles_per_pre;
-        col0 = (tile & ((1u << log_tiles_per_pre) - 1u)) << P.log_c;
+        if (P.coset_log_ntot > 0) {
+            // pruned LDE pass: the E cosets of one coefficient tile run in adjacent CTAs so the tile is read from
+            // HBM once and served to the other cosets by L2
+            pre = tile & ((1u << P.log_npre) - 1u);
+            col0 = (tile >> P.log_npre) << P.log_c;
+        } else {
+            pre = tile >> log_tiles_per_pre;
+            col0 = (tile & ((1u << log_tiles_per_pre) - 1u)) << P.log_c;
+        }
         src_base = (long long)pre * P.src_prefix_stride + col0;
         dst_base = ((long long)pre << P.log_nsub) + col0;
     } else {

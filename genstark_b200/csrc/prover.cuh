@@ -380,6 +380,17 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         u128 acc = 1;
         for (long long j = 0; j < E; ++j) { inv_num[j] = fp_from_u128(h_inv(h_sub(acc, 1))); acc = h_mul(acc, w_e); }
     }
+    // x^incr and x^delta over the evaluation domain: E-entry tables (see compose.cuh)
+    std::vector<fp> pow_tab(pow_incr.size() * E), delta_tab(E, fp_one());
+    for (size_t g = 0; g < pow_incr.size(); ++g) {
+        if (pow_incr[g] % (unsigned long long)T) return c->fail(GS_E_UNSUPPORTED, "degree increment is not a multiple of the trace length");
+        const u128 base = h_pow(w_n, (u128)(pow_incr[g] % (unsigned long long)N));
+        u128 a = 1; for (long long j = 0; j < E; ++j) { pow_tab[g * E + j] = fp_from_u128(a); a = h_mul(a, base); }
+    }
+    if (delta > 0) {
+        const u128 base = h_pow(w_n, (u128)((unsigned long long)delta % (unsigned long long)N));
+        u128 a = 1; for (long long j = 0; j < E; ++j) { delta_tab[j] = fp_from_u128(a); a = h_mul(a, base); }
+    }
     // small-object upload: one packed buffer
     std::vector<uint8_t> small;
     auto put = [&](const void* p, size_t n) { size_t off = (small.size() + 15) & ~(size_t)15; small.resize(off + n); memcpy(small.data() + off, p, n); return off; };
@@ -389,6 +400,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     const size_t o_ip = put(ipoly.data(), ipoly.size() * 16), o_pc = put(pf_coef.data(), pf_coef.size() * 16), o_ps = put(pf_shift.data(), pf_shift.size() * 4);
     const size_t o_io = put(ioff.data(), nB * 4), o_il = put(ilen.data(), nB * 4), o_po = put(pfoff.data(), nB * 4), o_pl = put(pflen.data(), nB * 4);
     const size_t o_br = put(breg.data(), nB * 4);
+    const size_t o_pt = put(pow_tab.data(), pow_tab.size() * 16), o_dt = put(delta_tab.data(), delta_tab.size() * 16);
     const size_t o_lk = put(lk.data(), n_lc * 16), o_lka = put(lk_adj.data(), n_lc * 16), o_in = put(inv_num.data(), E * 16);
     if (small.size() + 64 > S->d_small.cap) return c->fail(GS_E_UNSUPPORTED, "too many assertions / constraints for the parameter block");
     uint8_t* ds = S->d_small.as<uint8_t>();
@@ -404,7 +416,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             else { P.stat[k] = in_cols[k]; P.stat_mask[k] = 0xFFFFFFFFu; }
         }
         P.n_constraints = K; P.dk = (const fp*)(ds + o_dk); P.dk_adj = (const fp*)(ds + o_dka); P.pow_idx = (const int*)(ds + o_pi);
-        P.n_powers = (int)pow_incr.size(); for (size_t g = 0; g < pow_incr.size(); ++g) P.pow_incr[g] = pow_incr[g] & (unsigned long long)(N - 1);
+        P.n_powers = (int)pow_incr.size(); P.pow_tab = (const fp*)(ds + o_pt); P.delta_tab = (const fp*)(ds + o_dt);
         P.x_last = fp_from_u128(h_pow(w_n, (u128)(T - 1) * (u128)E)); P.inv_num = (const fp*)(ds + o_in);
         P.n_boundary = nB; P.b_reg = (const int*)(ds + o_br); P.b_ipoly_off = (const int*)(ds + o_io); P.b_ipoly_len = (const int*)(ds + o_il);
         P.b_ipoly = (const fp*)(ds + o_ip);
