@@ -209,6 +209,38 @@ __global__ void __launch_bounds__(256) merkle_level_kernel(uint32_t* __restrict_
     }
 }
 
+// LEVELS levels of the subtree below node (top_count + blockIdx.x) inside one block: its 2^LEVELS descendants are
+// staged in shared memory once and every intermediate node is written out.  Used for the latency-bound middle of
+// a tree (<= 2^16 nodes per level), where one launch per level costs ~6 us regardless of its size.
+template <int ALG, int LEVELS>
+__global__ void __launch_bounds__(1024) merkle_subtree_kernel(uint32_t* __restrict__ nodes, long long top_count) {
+    extern __shared__ __align__(16) unsigned char sub_raw[];
+    uint4* s = reinterpret_cast<uint4*>(sub_raw);                      // 2^LEVELS digests = 2 x uint4 each
+    const long long top = top_count + blockIdx.x;
+    const uint4* src = reinterpret_cast<const uint4*>(nodes + 8 * (top << LEVELS));
+    for (int i = threadIdx.x; i < (2 << LEVELS); i += blockDim.x) s[i] = src[i];
+    __syncthreads();
+    for (int l = LEVELS - 1; l >= 0; --l) {
+        const int cnt = 1 << l;
+        uint32_t d[8]; bool active = false;
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x) {          // cnt <= blockDim.x: at most one iteration
+            uint32_t m[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { uint4 t = s[4 * j + q]; m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
+            auto getm = [&](int w) -> uint32_t { return m[w]; };
+            hash_words<ALG>(getm, 16, d);
+            active = true;
+        }
+        __syncthreads();
+        if (active) {
+            const int j = threadIdx.x;
+            s[2 * j] = make_uint4(d[0], d[1], d[2], d[3]); s[2 * j + 1] = make_uint4(d[4], d[5], d[6], d[7]);
+            store_digest(nodes + 8 * ((top << l) + j), d);
+        }
+        __syncthreads();
+    }
+}
+
 // all levels from `count` parents down to the root inside one block
 template <int ALG>
 __global__ void __launch_bounds__(1024) merkle_tail_kernel(uint32_t* __restrict__ nodes, int count) {
@@ -286,12 +318,25 @@ static inline int merkle_build(Ctx* c, int alg, uint32_t* nodes, long long n) {
     if (alg != HASH_BLAKE2S && alg != HASH_SHA256) return c->fail(GS_E_ARG, "unknown hash algorithm");
     long long count = n >> 1;
     ProfScope ps(c, "merkle_build");
-    while (count > 1024) {
+    while (count > 32768) {                    // throughput-bound levels: one launch each
         const unsigned g = grid_for(c, count, 256);
         if (alg == HASH_BLAKE2S) merkle_level_kernel<HASH_BLAKE2S><<<g, 256, 0, c->stream>>>(nodes, count);
         else merkle_level_kernel<HASH_SHA256><<<g, 256, 0, c->stream>>>(nodes, count);
         c->launches++;
         count >>= 1;
+    }
+    if (count >= 2048) {                       // latency-bound middle: 11 levels per block in shared memory
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(merkle_subtree_kernel<HASH_BLAKE2S, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(merkle_subtree_kernel<HASH_SHA256, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            attr = true;
+        }
+        const long long blocks = count >> 10;  // the level with 2*count nodes splits into 2048-node subtrees
+        if (alg == HASH_BLAKE2S) merkle_subtree_kernel<HASH_BLAKE2S, 11><<<(unsigned)blocks, 1024, 64 * 1024, c->stream>>>(nodes, blocks);
+        else merkle_subtree_kernel<HASH_SHA256, 11><<<(unsigned)blocks, 1024, 64 * 1024, c->stream>>>(nodes, blocks);
+        c->launches++;
+        count = blocks >> 1;
     }
     if (count >= 1) {
         if (alg == HASH_BLAKE2S) merkle_tail_kernel<HASH_BLAKE2S><<<1, 1024, 0, c->stream>>>(nodes, (int)count);

@@ -3,6 +3,7 @@
 // sequential stage of prove() gets plain g++ -O3 code generation.
 #pragma once
 #include <array>
+#include <functional>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -227,9 +228,12 @@ struct TransitionRunner {
 
 
 // generateExecutionTrace (lib/Stark.ts:97): R x T, row = register; canonical residues
-void generate_trace(const AirHost* S, const u128* init_state, const fp* input_traces, fp* tr);
+// on_chunk(first_step, end_step) is called whenever another block of steps is final (the prover starts their
+// host->device copy while the next block is being generated)
+typedef std::function<void(long long, long long)> TraceChunkFn;
+void generate_trace(const AirHost* S, const u128* init_state, const fp* input_traces, fp* tr, const TraceChunkFn* on_chunk = nullptr);
 #ifdef GS_HOSTAIR_IMPL
-void generate_trace(const AirHost* S, const u128* init_state, const fp* input_traces, fp* tr) {
+void generate_trace(const AirHost* S, const u128* init_state, const fp* input_traces, fp* tr, const TraceChunkFn* on_chunk) {
     const int R = S->R; const long long T = 1ll << S->log_t;
     TransitionRunner run; run.init(S->transition, R, (int)S->statics.size());
     for (int r = 0; r < R; ++r) run.buf[0][r] = w_from(init_state[r]);
@@ -247,7 +251,9 @@ void generate_trace(const AirHost* S, const u128* init_state, const fp* input_tr
             }
             run.step(p);
         }
+        if (on_chunk && ((s + 1) & 0xFFFF) == 0) (*on_chunk)(s + 1 - 0x10000, s + 1);
     }
+    if (on_chunk && (T & 0xFFFF)) (*on_chunk)(T & ~0xFFFFll, T);
 }
 #endif
 

@@ -102,8 +102,8 @@ GS_D void dif_butterfly(fp (&x)[1 << S], const fp* tw, int log_r) {
     }
 }
 
-template <int LOG_R1, int LOG_R2>
-__global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const NttPassParams P) {
+template <int LOG_R1, int LOG_R2, int MINB>
+__global__ void __launch_bounds__(256, MINB) ntt_pass_kernel(const NttPassParams P) {
     constexpr int R1 = 1 << LOG_R1, R2 = 1 << LOG_R2, LOG_R = LOG_R1 + LOG_R2, R = 1 << LOG_R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fp* s_tw = reinterpret_cast<fp*>(smem_raw);     // R entries: w_R^i
@@ -130,15 +130,8 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const NttPassParams P)
     const unsigned tile = blockIdx.x;
     if (!P.final_pass) {
         const int log_tiles_per_pre = P.log_m - P.log_c;
-        if (P.coset_log_ntot > 0) {
-            // pruned LDE pass: the E cosets of one coefficient tile run in adjacent CTAs so the tile is read from
-            // HBM once and served to the other cosets by L2
-            pre = tile & ((1u << P.log_npre) - 1u);
-            col0 = (tile >> P.log_npre) << P.log_c;
-        } else {
-            pre = tile >> log_tiles_per_pre;
-            col0 = (tile & ((1u << log_tiles_per_pre) - 1u)) << P.log_c;
-        }
+        pre = tile >> log_tiles_per_pre;
+        col0 = (tile & ((1u << log_tiles_per_pre) - 1u)) << P.log_c;
         src_base = (long long)pre * P.src_prefix_stride + col0;
         dst_base = ((long long)pre << P.log_nsub) + col0;
     } else {

@@ -1,6 +1,7 @@
 // Host-side planning and launch of the K1 passes (see ntt.cuh for the decomposition).
 #pragma once
 #include "core.cuh"
+#include <cstdlib>
 #include "ntt.cuh"
 
 namespace gs {
@@ -25,15 +26,28 @@ static inline NttPlan ntt_plan(int log_n, bool pruned) {
     return p;
 }
 
-template <int A, int B>
-static inline cudaError_t launch_pass_t(const NttPassParams& P, dim3 grid, int threads, size_t smem, cudaStream_t s) {
+static inline int ntt_minb() {          // experiment knob: GS_NTT_MINB = 2 (default) | 3 | 4 resident CTAs per SM
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GS_NTT_MINB"); v = e ? atoi(e) : 2; if (v < 2 || v > 4) v = 2; }
+    return v;
+}
+template <int A, int B, int M>
+static inline cudaError_t launch_pass_m(const NttPassParams& P, dim3 grid, int threads, size_t smem, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(ntt_pass_kernel<A, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(ntt_pass_kernel<A, B, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_set = true;
     }
-    ntt_pass_kernel<A, B><<<grid, threads, smem, s>>>(P);
+    ntt_pass_kernel<A, B, M><<<grid, threads, smem, s>>>(P);
     return cudaGetLastError();
+}
+template <int A, int B>
+static inline cudaError_t launch_pass_t(const NttPassParams& P, dim3 grid, int threads, size_t smem, cudaStream_t s) {
+    switch (ntt_minb()) {
+        case 3: return launch_pass_m<A, B, 3>(P, grid, threads, smem, s);
+        case 4: return launch_pass_m<A, B, 4>(P, grid, threads, smem, s);
+        default: return launch_pass_m<A, B, 2>(P, grid, threads, smem, s);
+    }
 }
 
 static inline cudaError_t launch_pass(int log_r, const NttPassParams& P, dim3 grid, int threads, size_t smem, cudaStream_t s) {

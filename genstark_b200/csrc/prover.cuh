@@ -231,7 +231,13 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     }
     {
         fp* tr = (fp*)S->h_trace;
-        generate_trace(S, init_state, input_traces, tr);
+        // the device copy of finished 2^16-step blocks is enqueued while the next block is being generated
+        if ((rc = S->d_trace.ensure(c, trace_bytes))) return rc;
+        const TraceChunkFn on_chunk = [&](long long s0, long long s1) {
+            for (int r = 0; r < R; ++r)
+                cudaMemcpyAsync(S->d_trace.as<fp>() + (size_t)r * T + s0, tr + (size_t)r * T + s0, (size_t)(s1 - s0) * sizeof(fp), cudaMemcpyHostToDevice, c->stream);
+        };
+        generate_trace(S, init_state, input_traces, tr, &on_chunk);
         for (int a = 0; a < n_assert; ++a) {
             if ((int)asserts[a].reg >= R) return c->fail(GS_E_STARK, "Failed to generate the execution trace: Invalid assertion: register %u is outside of register bank", asserts[a].reg);
             if (asserts[a].step >= (uint64_t)T) return c->fail(GS_E_STARK, "Failed to generate the execution trace: Invalid assertion: step %u is outside of execution trace", asserts[a].step);
@@ -256,7 +262,6 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     if (n_in > 0 && ((rc = S->d_in_trace.ensure(c, in_bytes)) || (rc = S->d_in_poly.ensure(c, in_bytes)) || (rc = S->d_in_e.ensure(c, (size_t)n_in * N * sizeof(fp))))) return rc;
     if (S->keep_intermediates && (rc = S->d_c.ensure(c, (size_t)N * sizeof(fp)))) return rc;
     if (!reuse_trace) {
-        GS_CUDA(c, cudaMemcpyAsync(S->d_trace.p, S->h_trace, trace_bytes, cudaMemcpyHostToDevice, c->stream));
         if (n_in > 0) GS_CUDA(c, cudaMemcpyAsync(S->d_in_trace.p, input_traces, in_bytes, cudaMemcpyHostToDevice, c->stream));
     }
     std::vector<const fp*> e_cols;            // eVectors: trace rows then secret rows (Stark.ts:113-114)
