@@ -54,7 +54,7 @@ struct ComposeParams {
     const fp* tw_lo; const fp* tw_hi; int log_g, log_lo;
     fp* out;                     // L(x) over N
     fp* c_out;                   // optional: C(x) over N (stage-level parity tests); may be null
-    int* fail_flag;              // [0] = 1 + constraint index, [1] = step, when a constraint is non-zero on a trace step
+    int* fail_flag;              // min over violations of (step << 6 | constraint); INT_MAX when the trace satisfies the AIR
 };
 
 GS_D fp root_pow(const ComposeParams& P, unsigned long long e_n) {
@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeParams* __res
                     const fp qv = slot[a];
                     // the reference (air-assembly) refuses a trace that violates a constraint: positions that
                     // are trace steps (i % E == 0) other than the last step must evaluate to zero
-                    if (((unsigned)i & (E - 1)) == 0 && i < P.n - E && !fp_is_zero(qv)) {
-                        if (atomicCAS(P.fail_flag, 0, 1 + (int)d) == 0) P.fail_flag[1] = (int)(i >> P.log_e);
-                    }
+                    // (the first violating step, then the lowest constraint index, as the sequential reference reports)
+                    if (((unsigned)i & (E - 1)) == 0 && i < P.n - E && !fp_is_zero(qv))
+                        atomicMin(P.fail_flag, (int)(((unsigned)(i >> P.log_e) << 6) | d));
                     fp coef = ldg_fp(P.dk + d);
                     const int pi = __ldg(P.pow_idx + d);
                     if (pi >= 0) coef = fp_add(coef, fp_mul(ldg_fp(P.dk_adj + d), xpow[pi]));

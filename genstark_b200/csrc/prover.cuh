@@ -399,7 +399,8 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     // small-object upload: one packed buffer
     std::vector<uint8_t> small;
     auto put = [&](const void* p, size_t n) { size_t off = (small.size() + 15) & ~(size_t)15; small.resize(off + n); memcpy(small.data() + off, p, n); return off; };
-    const size_t o_flag = put("\0\0\0\0\0\0\0\0", 8);        // fixed offset 0: the captured graph copies it back
+    const int flag_init[2] = {0x7FFFFFFF, 0};
+    const size_t o_flag = put(flag_init, 8);        // fixed offset 0: the captured graph copies it back
     const size_t o_dk = put(dk.data(), K * 16), o_dka = put(dk_adj.data(), K * 16), o_pi = put(pow_idx.data(), K * 4);
     const size_t o_bk = put(bk.data(), nB * 16), o_bka = put(bk_adj.data(), nB * 16);
     const size_t o_ip = put(ipoly.data(), ipoly.size() * 16), o_pc = put(pf_coef.data(), pf_coef.size() * 16), o_ps = put(pf_shift.data(), pf_shift.size() * 4);
@@ -549,7 +550,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         memcpy(layers[d].root, mb + MB_ROOT + 32 * d, 32);
         if (d == 0) {
             const int* fl = (const int*)c->mailbox;
-            if (fl[0] != 0) { cudaStreamSynchronize(c->stream); return c->fail(GS_E_STARK, "Failed to evaluate transition constraints: Constraint %d didn't evaluate to 0 at step %d", fl[0] - 1, fl[1]); }
+            if (fl[0] != 0x7FFFFFFF) { cudaStreamSynchronize(c->stream); return c->fail(GS_E_STARK, "Failed to evaluate transition constraints: Constraint %d didn't evaluate to 0 at step %d", fl[0] & 63, fl[0] >> 6); }
             // lcProof and the trace queries depend on root_0 only (LowDegreeProver.ts:50-54, Stark.ts:147-151)
             std::vector<uint32_t> exe_pos;
             if (pseudorandom_indexes(layers[0].root, (int)std::min<long long>(S->exe_queries, N - N / E), (uint64_t)N, (uint64_t)E, exe_pos, err) != 0) {
