@@ -72,19 +72,40 @@ def test_single_assertion_and_many_assertions_on_one_register():
     _same_bytes(air, opts, many, inputs, seed)
 
 
-def test_mixed_degree_constraints_use_degree_adjustment():
-    """two constraints of different degree (1 and 3): the lower-degree group gets its x^incr copy."""
+def _mixed_air(second_degree):
     p = P128
     t = ProgramBuilder(p)
-    t.out(0, t.exp(t.cur(0), 3) + t.static(0)); t.out(1, t.cur(1) + t.cur(0))
     e = ProgramBuilder(p)
-    e.out(0, e.nxt(0) - (e.exp(e.cur(0), 3) + e.static(0))); e.out(1, e.nxt(1) - (e.cur(1) + e.cur(0)))
+    t.out(0, t.exp(t.cur(0), 3) + t.static(0))
+    e.out(0, e.nxt(0) - (e.exp(e.cur(0), 3) + e.static(0)))
+    if second_degree == 2:
+        t.out(1, t.cur(1) * t.cur(0) + 1); e.out(1, e.nxt(1) - (e.cur(1) * e.cur(0) + 1))
+    else:
+        t.out(1, t.cur(1) + t.cur(0)); e.out(1, e.nxt(1) - (e.cur(1) + e.cur(0)))
     air = AirModule('mixed', p, 2, 128, t.build(), e.build(), [StaticRegister('cycle', [5, 7, 11, 13])], init=lambda i, s: [3, 4])
-    assert air.constraint_degrees == [3, 1]
     from oracle.air import ProvingContext
     tr = ProvingContext(air, [], []).generate_execution_trace()
     a = [dict(step=127, register=0, value=tr[0][127]), dict(step=127, register=1, value=tr[1][127]), dict(step=0, register=1, value=4)]
-    _same_bytes(air, dict(hashAlgorithm='blake2s256', extensionFactor=8, exeQueryCount=40, friQueryCount=20), a, [], [])
+    return air, dict(hashAlgorithm='blake2s256', extensionFactor=8, exeQueryCount=40, friQueryCount=20), a
+
+
+def test_mixed_degree_constraints_use_degree_adjustment():
+    """two constraint groups (degrees 3 and 2): each lower-than-combination group gets its own x^incr copy and
+    coefficient, in first-appearance order (CompositionPolynomial.ts:88-100,206-225)."""
+    air, opts, a = _mixed_air(2)
+    assert air.constraint_degrees == [3, 2]
+    _same_bytes(air, opts, a, [], [])
+
+
+def test_degree_one_constraint_next_to_cubic_overshoots_like_the_restated_protocol():
+    """a degree-1 constraint raised by x^(3T) and divided by Z(x) has degree exactly 3T = compositionDegree, one more
+    than FRI allows: the restated protocol rejects its own proof, and the GPU prover fails with the same text."""
+    air, opts, a = _mixed_air(1)
+    assert air.constraint_degrees == [3, 1]
+    with pytest.raises(Exception, match='Remainder is not a valid degree 95 polynomial'):
+        OracleStark(air, opts).prove(a, [], [])
+    with pytest.raises(StarkError, match='Low degree proof failed: Remainder is not a valid degree 95 polynomial'):
+        Stark(air, opts).prove_bytes(a, [], [])
 
 
 def test_repeated_proves_with_different_assertions_reuse_the_instance():
