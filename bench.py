@@ -50,20 +50,30 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
 
     def run(self):
         q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(',')])
-            except Exception:
-                pass
-            time.sleep(0.1)
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-lms', '20'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        for line in self.proc.stdout:
+            if self.stop_flag:
+                break
+            line = line.strip()
+            if line:
+                self.samples.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        self.stop_flag = True
+        try:
+            self.proc.terminate()
+        except Exception:
+            pass
+        self.join(timeout=2)
 
     def summary(self):
         sm, mx, reasons = [], 0, set()
@@ -250,8 +260,7 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     prof = json.loads(L.gs_ctx_profile_report(ctx.handle).decode())
     L.gs_ctx_profile(ctx.handle, 0)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.stop()
 
     ms_step = sum(dev_ms) / len(dev_ms)
     if dist is not None:
@@ -360,7 +369,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     args = ap.parse_args()
