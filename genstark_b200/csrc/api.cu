@@ -58,8 +58,31 @@ void gs_ctx_destroy(gs_ctx* c) {
     cudaFree(c->tw_lo); cudaFree(c->tw_hi); cudaFree(c->tw_small);
     if (c->scratch) cudaFree(c->scratch);
     if (c->mailbox) cudaFreeHost(c->mailbox);
+    if (c->comm) nccl().CommDestroy(c->comm);
     cudaStreamDestroy(c->stream);
     delete c;
+}
+
+int gs_comm_unique_id(uint8_t out128[128]) {
+    if (!out128) return GS_E_ARG;
+    if (!nccl().load()) { g_null_error = nccl().error; return GS_E_UNSUPPORTED; }
+    NcclUniqueId id;
+    const int rc = nccl().GetUniqueId(&id);
+    if (rc != 0) { g_null_error = std::string("ncclGetUniqueId: ") + nccl().GetErrorString(rc); return GS_E_CUDA; }
+    memcpy(out128, &id, 128);
+    return GS_OK;
+}
+
+int gs_ctx_comm_init(gs_ctx* c, int rank, int world, const uint8_t id128[128]) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world || (world & (world - 1))) return c ? c->fail(GS_E_ARG, "bad rank / world size (power of two required)") : GS_E_ARG;
+    if (world == 1) { c->rank = 0; c->world = 1; return GS_OK; }
+    if (!nccl().load()) return c->fail(GS_E_UNSUPPORTED, "%s", nccl().error.c_str());
+    cudaSetDevice(c->device);
+    NcclUniqueId id; memcpy(&id, id128, 128);
+    const int rc = nccl().CommInitRank(&c->comm, world, id, rank);
+    if (rc != 0) return c->fail(GS_E_CUDA, "ncclCommInitRank: %s", nccl().GetErrorString(rc));
+    c->rank = rank; c->world = world;
+    return GS_OK;
 }
 
 const char* gs_last_error(gs_ctx* c) { return c ? c->last_error.c_str() : g_null_error.c_str(); }
@@ -278,6 +301,7 @@ int gs_fri_fold(gs_ctx* c, const gs_mat* v, int log2_domain, int depth, const ui
     FriFoldParams F; F.v = v->data; F.out = (*column)->data; F.quarter = L >> 2; F.special_x = (const fp*)c->scratch;
     F.tw_lo = c->tw_lo; F.tw_hi = c->tw_hi; F.log_g = c->log_g; F.log_lo = c->log_lo;
     F.x_shift = 2 * depth + (c->log_g - log2_domain);
+    F.log_e = 0; F.log_el = 0; F.j0 = 0;          // single GPU: local row index = global row index
     F.iota_inv = fp_from_u128(h_inv(c->root_of_order(2))); F.quarter_inv = fp_from_u128(h_inv(4));
     fri_fold_kernel<<<grid_for(c, L >> 2, 256), 256, 0, c->stream>>>(F);
     c->launches++;
@@ -467,11 +491,16 @@ int gs_stark_create(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int has
     }
     // u[j] = 1/(w_N^j - 1) over the evaluation domain (boundary constraints by partial fractions, compose.cuh)
     {
-        const int log_n = S->log_t + S->log_e; const long long N = 1ll << log_n;
+        const int log_n = S->log_t + S->log_e;
         if (log_n > c->log_g) return c->fail(GS_E_UNSUPPORTED, "evaluation domain 2^%d exceeds 2^%d", log_n, c->log_g);
+        // coset sharding: this rank owns E / world consecutive cosets
+        int log_w = 0; while ((1 << log_w) < c->world) ++log_w;
+        if (log_w > S->log_e) return c->fail(GS_E_UNSUPPORTED, "more ranks (%d) than cosets (%d)", c->world, 1 << S->log_e);
+        S->shard.rank = c->rank; S->shard.world = c->world; S->shard.log_e = S->log_e; S->shard.log_el = S->log_e - log_w;
+        const long long N = (1ll << S->log_t) << S->shard.log_el;          // local positions
         if ((rc = S->d_u.ensure(c, (size_t)N * sizeof(fp)))) return rc;
         if ((rc = c->ensure_scratch((size_t)N * sizeof(fp)))) return rc;
-        UTableParams U; U.n = N; U.log_n = log_n; U.tw_lo = c->tw_lo; U.tw_hi = c->tw_hi; U.log_g = c->log_g; U.log_lo = c->log_lo; U.out = S->d_u.as<fp>();
+        UTableParams U; U.n_loc = N; U.log_n = log_n; U.log_e = S->log_e; U.log_el = S->shard.log_el; U.j0 = S->shard.j0(); U.tw_lo = c->tw_lo; U.tw_hi = c->tw_hi; U.log_g = c->log_g; U.log_lo = c->log_lo; U.out = S->d_u.as<fp>();
         u_table_kernel<<<grid_for(c, N, 256), 256, 0, c->stream>>>(U);
         c->launches++;
         if ((rc = batch_inverse(c, S->d_u.as<fp>(), S->d_u.as<fp>(), (fp*)c->scratch, N))) return rc;

@@ -22,8 +22,11 @@ namespace gs {
 #define GS_MAX_POWERS 8
 
 struct ComposeParams {
-    long long n;                 // evaluation domain size N
+    long long n;                 // evaluation domain size N (global)
     int log_n, log_e;            // N = 2^log_n, E = 2^log_e
+    // coset sharding: this launch covers the n_loc positions of cosets [j0, j0 + 2^log_el); local index
+    // i_loc = q * 2^log_el + (j - j0) for global position i = q * E + j.  Single GPU: log_el = log_e, j0 = 0.
+    long long n_loc; int log_el, j0;
     // program
     const uint4* instrs; int n_instr; const fp* consts; int n_slots;
     // trace columns (LDE over N)
@@ -69,10 +72,12 @@ template <int NSLOT>
 __global__ void __launch_bounds__(256) compose_kernel(const ComposeParams* __restrict__ Pp) {
     const ComposeParams& P = *Pp;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const unsigned long long nmask = (unsigned long long)P.n - 1ull;
-    const unsigned E = 1u << P.log_e;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        const long long inext = (i + E) & (long long)nmask;
+    const unsigned long long lmask = (unsigned long long)P.n_loc - 1ull;
+    const unsigned E = 1u << P.log_e, EL = 1u << P.log_el;
+    for (long long il = (long long)blockIdx.x * blockDim.x + threadIdx.x; il < P.n_loc; il += stride) {
+        // all per-position data (trace, inputs, u table, outputs) is indexed locally; the domain point is global
+        const long long i = ((il >> P.log_el) << P.log_e) + P.j0 + (il & (EL - 1));
+        const long long inext = (il + EL) & (long long)lmask;
         fp slot[NSLOT];
         // powers of x used by this point
         const fp x = root_pow(P, (unsigned long long)i);
@@ -91,9 +96,9 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeParams* __res
             const unsigned op = ins.x, d = ins.y, a = ins.z, b = ins.w;
             switch (op) {
                 case OP_CONST: slot[d] = ldg_fp(P.consts + a); break;
-                case OP_CUR: slot[d] = ld_fp(P.trace[a] + i); break;
+                case OP_CUR: slot[d] = ld_fp(P.trace[a] + il); break;
                 case OP_NEXT: slot[d] = ld_fp(P.trace[a] + inext); break;
-                case OP_STATIC: slot[d] = ld_fp(P.stat[a] + ((unsigned long long)i & P.stat_mask[a])); break;
+                case OP_STATIC: slot[d] = ld_fp(P.stat[a] + (P.stat_mask[a] == 0xFFFFFFFFu ? (unsigned long long)il : ((unsigned long long)i & P.stat_mask[a]))); break;
                 case OP_ADD: slot[d] = fp_add(slot[a], slot[b]); break;
                 case OP_SUB: slot[d] = fp_sub(slot[a], slot[b]); break;
                 case OP_MUL: slot[d] = fp_mul(slot[a], slot[b]); break;
@@ -123,14 +128,15 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeParams* __res
             const int off = P.b_ipoly_off[bi], len = P.b_ipoly_len[bi];
             fp iv = ldg_fp(P.b_ipoly + off + len - 1);
             for (int k = len - 2; k >= 0; --k) iv = fp_add(fp_mul(iv, x), ldg_fp(P.b_ipoly + off + k));
-            const fp pv = ld_fp(P.trace[P.b_reg[bi]] + i);
+            const fp pv = ld_fp(P.trace[P.b_reg[bi]] + il);
             fp zinv = fp_zero();
             bool at_root = false;
             const int po = P.b_pf_off[bi], pl = P.b_pf_len[bi];
             for (int k = 0; k < pl; ++k) {
                 const unsigned sh = P.b_pf_shift[po + k];
                 at_root |= ((unsigned)i == sh);
-                const unsigned long long j = ((unsigned long long)i - sh) & nmask;
+                // (i - sh) mod N stays in the same coset: locally it is a shift by (sh / E) rows
+                const unsigned long long j = ((unsigned long long)il - ((unsigned long long)(sh >> P.log_e) << P.log_el)) & lmask;
                 zinv = fp_add(zinv, fp_mul(ldg_fp(P.b_pf_coef + po + k), ld_fp(P.u_table + j)));
             }
             if (at_root) zinv = fp_zero();
@@ -139,28 +145,29 @@ __global__ void __launch_bounds__(256) compose_kernel(const ComposeParams* __res
             if (P.delta) coef = fp_add(coef, fp_mul(ldg_fp(P.bk_adj + bi), xdelta));
             c = fp_add(c, fp_mul(bv, coef));
         }
-        if (P.c_out) st_fp(P.c_out + i, c);
+        if (P.c_out) st_fp(P.c_out + il, c);
         // ---- linear combination with P(x) and S(x)
         fp l = c;
 #pragma unroll 1
         for (int j = 0; j < P.n_lc; ++j) {
             fp coef = ldg_fp(P.lk + j);
             if (P.delta) coef = fp_add(coef, fp_mul(ldg_fp(P.lk_adj + j), xdelta));
-            l = fp_add(l, fp_mul(ld_fp(P.lc_col[j] + i), coef));
+            l = fp_add(l, fp_mul(ld_fp(P.lc_col[j] + il), coef));
         }
-        st_fp(P.out + i, l);
+        st_fp(P.out + il, l);
     }
 }
 
 // u[j] = w_N^j - 1 (inverted afterwards by K3; u[0] stays 0)
-struct UTableParams { long long n; int log_n; const fp* tw_lo; const fp* tw_hi; int log_g, log_lo; fp* out; };
+struct UTableParams { long long n_loc; int log_n, log_e, log_el, j0; const fp* tw_lo; const fp* tw_hi; int log_g, log_lo; fp* out; };
 __global__ void __launch_bounds__(256) u_table_kernel(const UTableParams P) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+    for (long long il = (long long)blockIdx.x * blockDim.x + threadIdx.x; il < P.n_loc; il += stride) {
+        const long long i = ((il >> P.log_el) << P.log_e) + P.j0 + (il & ((1ll << P.log_el) - 1));
         const unsigned e = (unsigned)((unsigned long long)i << (P.log_g - P.log_n));
         fp x = ldg_fp(P.tw_lo + (e & ((1u << P.log_lo) - 1u)));
         if (P.log_g > P.log_lo) x = fp_mul(x, ldg_fp(P.tw_hi + (e >> P.log_lo)));
-        st_fp(P.out + i, fp_sub(x, fp_one()));
+        st_fp(P.out + il, fp_sub(x, fp_one()));
     }
 }
 

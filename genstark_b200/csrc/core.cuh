@@ -8,6 +8,7 @@
 #include <map>
 #include <cuda_runtime.h>
 #include "fp128.cuh"
+#include "comm.h"
 #include "../../include/genstark_b200.h"
 
 namespace gs {
@@ -30,6 +31,9 @@ struct Ctx {
     void* mailbox = nullptr;
     size_t mailbox_bytes = 0;
     int sm_count = 148;
+    // coset-sharded multi-GPU prover: one process per GPU, NCCL communicator over all ranks of the box
+    int rank = 0, world = 1;
+    NcclComm comm = nullptr;
     unsigned long long launches = 0;   // kernels launched through this context (bench.py gpu_launches)
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     // per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)

@@ -20,7 +20,8 @@ struct FriFoldParams {
     long long quarter;    // L/4
     const fp* special_x;  // device pointer to the challenge (so the host need not sync to launch)
     const fp* tw_lo; const fp* tw_hi; int log_g, log_lo;
-    int x_shift;          // exponent of x_i in units of w_G:  e = i << x_shift  (= 4^d * G/N)
+    int x_shift;          // exponent of x_i in units of w_G:  e = i << x_shift  (= 4^d * G/N), i = GLOBAL row index
+    int log_e, log_el, j0;   // coset sharding (see ComposeParams): local row il <-> global row i
     fp iota_inv;          // w^(-N/4)
     fp quarter_inv;       // 4^-1
 };
@@ -33,7 +34,8 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const FriFoldParams P) {
         const fp y0 = ld_fp(P.v + i), y1 = ld_fp(P.v + i + P.quarter);
         const fp y2 = ld_fp(P.v + i + 2 * P.quarter), y3 = ld_fp(P.v + i + 3 * P.quarter);
         // t = x* * x_i^-1,  x_i^-1 = w_G^(G - e)
-        const unsigned e = (0u - ((unsigned)i << P.x_shift)) & g_mask;
+        const unsigned ig = (unsigned)(((i >> P.log_el) << P.log_e) + P.j0 + (i & ((1ll << P.log_el) - 1)));
+        const unsigned e = (0u - (ig << P.x_shift)) & g_mask;
         fp xinv = ldg_fp(P.tw_lo + (e & ((1u << P.log_lo) - 1u)));
         if (P.log_g > P.log_lo) xinv = fp_mul(xinv, ldg_fp(P.tw_hi + (e >> P.log_lo)));
         const fp t = fp_mul(xs, xinv);
@@ -75,6 +77,27 @@ __global__ void gather_digests_kernel(const uint32_t* __restrict__ nodes, const 
 __global__ void gather_chunks_kernel(const unsigned long long* __restrict__ addr, int n, uint4* __restrict__ out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) out[t] = *reinterpret_cast<const uint4*>(addr[t]);
+}
+
+// natural[q*E + r*El + jl] = gathered[r][q*El + jl]  (32-byte digests): puts the all-gathered per-rank digests of a
+// commit into leaf order
+__global__ void permute_digests_kernel(const uint4* __restrict__ gathered, uint4* __restrict__ natural, long long n_loc, int log_el, int log_w) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;          // one thread per 16-byte half digest
+    const long long total = (n_loc << log_w) * 2;
+    if (t >= total) return;
+    const long long d = t >> 1; const int half = (int)(t & 1);
+    const long long r = d / n_loc, il = d % n_loc;
+    const long long q = il >> log_el, jl = il & ((1ll << log_el) - 1);
+    const long long i = (q << (log_el + log_w)) + (r << log_el) + jl;
+    natural[2 * i + half] = gathered[2 * d + half];
+}
+// same permutation for 16-byte field elements (the FRI remainder)
+__global__ void permute_elems_kernel(const uint4* __restrict__ gathered, uint4* __restrict__ natural, long long n_loc, int log_el, int log_w) {
+    const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= (n_loc << log_w)) return;
+    const long long r = d / n_loc, il = d % n_loc;
+    const long long q = il >> log_el, jl = il & ((1ll << log_el) - 1);
+    natural[(q << (log_el + log_w)) + (r << log_el) + jl] = gathered[d];
 }
 
 }  // namespace gs

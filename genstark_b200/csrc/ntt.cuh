@@ -41,7 +41,8 @@ struct NttPassParams {
     int log_m;                    // remaining size m_p (row stride); 0 for final pass
     long long src_prefix_stride;  // 0 when the pass reads the shared coefficient vector (pruned LDE pass)
     int log_nsub;                 // log2(R * m): sub-problem size, inter-pass twiddle = w_nsub^(r*k)
-    int coset_log_ntot;           // >0: multiply input at position pos of prefix j by w_ntot^(pos*j)
+    int coset_log_ntot;           // >0: multiply input at position pos of prefix j by w_ntot^(pos*(coset_base+j))
+    int coset_base;               // first coset computed by this call (sharded LDE: a rank owns a range of cosets)
     // final pass
     int log_npre;                 // log2(number of prefixes)
     int log_d0, log_d1, log_d2;   // radices of the prefix digits, most significant first
@@ -162,12 +163,12 @@ __global__ void __launch_bounds__(256, MINB) ntt_pass_kernel(const NttPassParams
                                          : (src + src_base + ((long long)row << P.log_m) + c);
             x[a] = ld_fp(ptr);
         }
-        if (P.coset_log_ntot > 0 && pre != 0) {
+        if (P.coset_log_ntot > 0 && (pre + (unsigned)P.coset_base) != 0) {
             // w_ntot^(pos * j), pos = row*m + col
 #pragma unroll
             for (int a = 0; a < R1; ++a) {
                 const unsigned pos = ((unsigned)(a * R2 + r) << P.log_m) + col0 + c;
-                const unsigned e = (pos * pre) << (P.log_g - P.coset_log_ntot);
+                const unsigned e = (pos * (pre + (unsigned)P.coset_base)) << (P.log_g - P.coset_log_ntot);
                 x[a] = fp_mul(x[a], tw_lookup(P, e));
             }
         }

@@ -76,16 +76,20 @@ static inline int pass_log_r1(int log_r) {
 // src: rows x 2^log_t (row stride src_stride), dst: rows x 2^(log_t+log_e) (row stride dst_stride).
 // work: rows x 2^(log_t+log_e) scratch (may be null when a single pass suffices).
 static inline int ntt_run(Ctx* c, const fp* src, long long src_stride, fp* dst, long long dst_stride,
-                          fp* work, long long work_stride, int rows, int log_t, int log_e, bool inverse) {
+                          fp* work, long long work_stride, int rows, int log_t, int log_e, bool inverse,
+                          int coset_base = 0, int log_e_total = -1) {
+    // sharded LDE: this call computes 2^log_e cosets starting at coset_base of a domain with 2^log_e_total cosets
+    if (log_e_total < 0) log_e_total = log_e;
     const int log_ntot = log_t + log_e;
+    if (log_t + log_e_total > c->log_g) return c->fail(GS_E_UNSUPPORTED, "domain 2^%d exceeds root table 2^%d", log_t + log_e_total, c->log_g);
     if (log_ntot > c->log_g) return c->fail(GS_E_UNSUPPORTED, "domain 2^%d exceeds root table 2^%d", log_ntot, c->log_g);
     if (log_t < 1) {
         // length-1 polynomials: constant on every coset
         return c->fail(GS_E_UNSUPPORTED, "transform length must be >= 2");
     }
-    if (log_e > 0 && log_t < 2) return c->fail(GS_E_UNSUPPORTED, "LDE needs at least 4 coefficients");
-    if (log_e > 0 && inverse) return c->fail(GS_E_UNSUPPORTED, "inverse coset transform");
-    NttPlan plan = ntt_plan(log_t, log_e > 0);
+    if (log_e_total > 0 && log_t < 2) return c->fail(GS_E_UNSUPPORTED, "LDE needs at least 4 coefficients");
+    if (log_e_total > 0 && inverse) return c->fail(GS_E_UNSUPPORTED, "inverse coset transform");
+    NttPlan plan = ntt_plan(log_t, log_e_total > 0);
     if (plan.n_pass > 1 && work == nullptr) return c->fail(GS_E_ARG, "work buffer required");
     int log_m = log_t;
     int log_npre = log_e;                     // prefixes so far (coset digit)
@@ -103,7 +107,8 @@ static inline int ntt_run(Ctx* c, const fp* src, long long src_stride, fp* dst, 
         P.final_pass = fin ? 1 : 0;
         P.log_ntot = log_ntot;
         P.log_npre = log_npre;
-        P.coset_log_ntot = (p == 0 && log_e > 0) ? log_ntot : 0;
+        P.coset_log_ntot = (p == 0 && log_e_total > 0 && plan.n_pass > 1) ? log_t + log_e_total : 0;
+        P.coset_base = coset_base;
         // source / destination of this pass
         const bool first = (p == 0);
         P.src = first ? src : work;
@@ -115,7 +120,7 @@ static inline int ntt_run(Ctx* c, const fp* src, long long src_stride, fp* dst, 
         if (!fin) {
             P.log_m = log_m;
             P.log_nsub = lr + log_m;
-            P.src_prefix_stride = (first && log_e > 0) ? 0 : (1ll << P.log_nsub);
+            P.src_prefix_stride = (first && log_e_total > 0) ? 0 : (1ll << P.log_nsub);
             log_c = 12 - lr; if (log_c > log_m) log_c = log_m; if (log_c > 5) log_c = 5;
             grid = dim3(1u << (log_npre + log_m - log_c), rows);
         } else {

@@ -60,6 +60,8 @@ struct Stark : public AirHost {
     bool use_graphs = true;           // CUDA graphs for the launch-bound chains (off while profiling / stage timing)
     unsigned long long proves_done = 0;
     GraphSlot g_commit, g_fri;
+    Shard shard;                      // coset sharding over the ranks of the context (world == 1: everything local)
+    DevBuf d_dig_loc, d_dig_all;      // commit boundary: local digests / all-gathered digests before the permutation
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf d_epoch;                         // prove counter, copied behind each FRI root so the host can poll for it
     float last_device_ms = 0;         // CUDA-event time from the first enqueue to the last kernel of prove()
@@ -72,7 +74,7 @@ struct Stark : public AirHost {
         if (g_fri.exec) cudaGraphExecDestroy(g_fri.exec);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        d_epoch.release();
+        d_epoch.release(); d_dig_loc.release(); d_dig_all.release();
     }
 };
 
@@ -102,6 +104,23 @@ static inline u128 h_eval_poly(const std::vector<u128>& poly, u128 x) {
 }
 
 struct Assertion { uint32_t reg, step; u128 value; };
+
+// Merkle commit boundary of the sharded prover: every rank hashed the rows it owns; all-gather the digests over
+// NVLink (NCCL) and put them in leaf order.  world == 1: the caller hashed straight into the tree.
+static inline int commit_gather(Stark* S, const uint32_t* d_local, long long n_loc, uint32_t* leaves_out) {
+    Ctx* c = S->ctx;
+    const Shard& sh = S->shard;
+    int log_w = 0; while ((1 << log_w) < sh.world) ++log_w;
+    int rc;
+    if ((rc = S->d_dig_all.ensure(c, (size_t)(n_loc << log_w) * 32))) return rc;
+    { ProfScope ps(c, "nccl_allgather_digests");
+      const int nr = nccl().AllGather(d_local, S->d_dig_all.p, (size_t)n_loc * 32, GS_NCCL_UINT8, c->comm, c->stream);
+      if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllGather: %s", nccl().GetErrorString(nr)); }
+    const long long total = (n_loc << log_w) * 2;
+    permute_digests_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(S->d_dig_all.as<uint4>(), reinterpret_cast<uint4*>(leaves_out), n_loc, sh.log_el, log_w);
+    c->launches++;
+    return GS_OK;
+}
 
 // run `fn` (which only enqueues work on the context stream) directly, or capture it once and replay it
 template <typename F>
@@ -213,6 +232,11 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     const int R = S->R, K = S->K, log_t = S->log_t, log_e = S->log_e, log_n = log_t + log_e;
     const long long T = 1ll << log_t, N = 1ll << log_n, E = 1ll << log_e;
     const int n_in = S->n_secret + S->n_public;
+    const Shard sh = S->shard;
+    const bool sharded = sh.world > 1;
+    const int log_el = sh.log_el;
+    const long long NL = T << log_el;            // evaluation positions owned by this rank (= N when world == 1)
+    if (sharded && S->keep_intermediates) return c->fail(GS_E_UNSUPPORTED, "intermediates are only kept on a single GPU");
     if (log_n > c->log_g) return c->fail(GS_E_UNSUPPORTED, "evaluation domain 2^%d exceeds 2^%d", log_n, c->log_g);
     // getComponentCount quirk (LowDegreeProver.ts:287-291): N < 128 throws RangeError in the reference
     if (N < 128) return c->fail(GS_E_STARK, "Low degree proof failed: Invalid array length");
@@ -254,27 +278,28 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     const size_t in_bytes = (size_t)n_in * T * sizeof(fp);
     long long fri_tot_v = 0, fri_tot_t = 0;
     for (long long L = N; ; L >>= 2) { fri_tot_t += 2 * (L >> 2); if (L <= 256) break; fri_tot_v += L >> 2; }
-    if ((rc = S->d_trace.ensure(c, trace_bytes)) || (rc = S->d_poly.ensure(c, trace_bytes)) || (rc = S->d_pe.ensure(c, (size_t)R * N * sizeof(fp))) ||
-        (rc = S->d_work.ensure(c, (size_t)wrows * N * sizeof(fp))) || (rc = S->d_tree.ensure(c, (size_t)2 * N * 32)) ||
-        (rc = S->d_l.ensure(c, (size_t)N * sizeof(fp))) || (rc = S->d_fri.ensure(c, (size_t)(fri_tot_v + 4) * sizeof(fp))) ||
+    if ((rc = S->d_trace.ensure(c, trace_bytes)) || (rc = S->d_poly.ensure(c, trace_bytes)) || (rc = S->d_pe.ensure(c, (size_t)R * NL * sizeof(fp))) ||
+        (rc = S->d_work.ensure(c, (size_t)wrows * NL * sizeof(fp))) || (rc = S->d_tree.ensure(c, (size_t)2 * N * 32)) ||
+        (rc = S->d_l.ensure(c, (size_t)NL * sizeof(fp))) || (rc = S->d_fri.ensure(c, (size_t)((fri_tot_v >> (log_e - log_el)) + 4 + 256) * sizeof(fp))) ||
         (rc = S->d_fri_trees.ensure(c, (size_t)fri_tot_t * 32)) || (rc = S->d_params.ensure(c, sizeof(ComposeParams))) ||
-        (rc = S->d_small.ensure(c, 1 << 20)) || (rc = S->d_epoch.ensure(c, 16))) return rc;
-    if (n_in > 0 && ((rc = S->d_in_trace.ensure(c, in_bytes)) || (rc = S->d_in_poly.ensure(c, in_bytes)) || (rc = S->d_in_e.ensure(c, (size_t)n_in * N * sizeof(fp))))) return rc;
+        (rc = S->d_small.ensure(c, 1 << 20)) || (rc = S->d_epoch.ensure(c, 64))) return rc;
+    if (sharded && (rc = S->d_dig_loc.ensure(c, (size_t)NL * 32))) return rc;
+    if (n_in > 0 && ((rc = S->d_in_trace.ensure(c, in_bytes)) || (rc = S->d_in_poly.ensure(c, in_bytes)) || (rc = S->d_in_e.ensure(c, (size_t)n_in * NL * sizeof(fp))))) return rc;
     if (S->keep_intermediates && (rc = S->d_c.ensure(c, (size_t)N * sizeof(fp)))) return rc;
     if (!reuse_trace) {
         if (n_in > 0) GS_CUDA(c, cudaMemcpyAsync(S->d_in_trace.p, input_traces, in_bytes, cudaMemcpyHostToDevice, c->stream));
     }
     std::vector<const fp*> e_cols;            // eVectors: trace rows then secret rows (Stark.ts:113-114)
-    for (int r = 0; r < R; ++r) e_cols.push_back(S->d_pe.as<fp>() + (size_t)r * N);
+    for (int r = 0; r < R; ++r) e_cols.push_back(S->d_pe.as<fp>() + (size_t)r * NL);
     std::vector<const fp*> in_cols(S->statics.size(), nullptr);
     {
         int ii = 0;
-        for (size_t k = 0; k < S->statics.size(); ++k) if (S->statics[k].kind != 0) in_cols[k] = S->d_in_e.as<fp>() + (size_t)(ii++) * N;
+        for (size_t k = 0; k < S->statics.size(); ++k) if (S->statics[k].kind != 0) in_cols[k] = S->d_in_e.as<fp>() + (size_t)(ii++) * NL;
         for (size_t k = 0; k < S->statics.size(); ++k) if (S->statics[k].kind == 1) e_cols.push_back(in_cols[k]);
     }
     if (e_cols.size() > GS_MAX_HASH_COLS) return c->fail(GS_E_UNSUPPORTED, "more than %d committed registers", GS_MAX_HASH_COLS);
     uint32_t* e_tree = S->d_tree.as<uint32_t>();
-    const bool graphs = S->use_graphs && !c->profiling && !timing && S->proves_done > 0;
+    const bool graphs = S->use_graphs && !c->profiling && !timing && S->proves_done > 0 && !sharded;
     // any reallocation changes a pointer below and invalidates the captured graphs
     unsigned long long gkey = 1469598103934665603ull;
     for (const DevBuf* b : {&S->d_trace, &S->d_poly, &S->d_pe, &S->d_work, &S->d_tree, &S->d_l, &S->d_fri, &S->d_fri_trees, &S->d_params,
@@ -285,15 +310,20 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         int r2;
         if ((r2 = ntt_run(c, S->d_trace.as<fp>(), T, S->d_poly.as<fp>(), T, S->d_work.as<fp>(), T, R, log_t, 0, true))) return r2;
         if (timing) mark("Computed execution trace polynomials P(x)", true);
-        if ((r2 = ntt_run(c, S->d_poly.as<fp>(), T, S->d_pe.as<fp>(), N, S->d_work.as<fp>(), N, R, log_t, log_e, false))) return r2;
+        // each rank extends onto the cosets it owns (all of them on a single GPU)
+        if ((r2 = ntt_run(c, S->d_poly.as<fp>(), T, S->d_pe.as<fp>(), NL, S->d_work.as<fp>(), NL, R, log_t, log_el, false, sh.j0(), log_e))) return r2;
         if (n_in > 0) {      // input registers (secret: committed; public: only feed the constraints)
             if ((r2 = ntt_run(c, S->d_in_trace.as<fp>(), T, S->d_in_poly.as<fp>(), T, S->d_work.as<fp>(), T, n_in, log_t, 0, true))) return r2;
-            if ((r2 = ntt_run(c, S->d_in_poly.as<fp>(), T, S->d_in_e.as<fp>(), N, S->d_work.as<fp>(), N, n_in, log_t, log_e, false))) return r2;
+            if ((r2 = ntt_run(c, S->d_in_poly.as<fp>(), T, S->d_in_e.as<fp>(), NL, S->d_work.as<fp>(), NL, n_in, log_t, log_el, false, sh.j0(), log_e))) return r2;
         }
         if (timing) mark("Low-degree extended P(x) polynomials over evaluation domain", true);
         HashCols hc; hc.ncols = (int)e_cols.size();
         for (size_t i = 0; i < e_cols.size(); ++i) hc.col[i] = e_cols[i];
-        if ((r2 = hash_columns(c, S->hash_alg, hc, N, e_tree + 8 * N))) return r2;
+        if (!sharded) { if ((r2 = hash_columns(c, S->hash_alg, hc, N, e_tree + 8 * N))) return r2; }
+        else {
+            if ((r2 = hash_columns(c, S->hash_alg, hc, NL, S->d_dig_loc.as<uint32_t>()))) return r2;
+            if ((r2 = commit_gather(S, S->d_dig_loc.as<uint32_t>(), NL, e_tree + 8 * N))) return r2;
+        }
         if (timing) mark("Serialized evaluations of P(x) and S(x) polynomials", true);
         if ((r2 = merkle_build(c, S->hash_alg, e_tree, N))) return r2;
         GS_CUDA(c, cudaMemcpyAsync(c->mailbox, e_tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
@@ -413,9 +443,9 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     GS_CUDA(c, cudaMemcpyAsync(ds, small.data(), small.size(), cudaMemcpyHostToDevice, c->stream));
     {
         ComposeParams P; memset(&P, 0, sizeof P);
-        P.n = N; P.log_n = log_n; P.log_e = log_e;
+        P.n = N; P.log_n = log_n; P.log_e = log_e; P.n_loc = NL; P.log_el = log_el; P.j0 = sh.j0();
         P.instrs = S->d_instrs.as<uint4>(); P.n_instr = (int)S->evaluation.instrs.size(); P.consts = S->d_consts.as<fp>(); P.n_slots = S->evaluation.n_slots;
-        P.n_trace = R; for (int r = 0; r < R; ++r) P.trace[r] = S->d_pe.as<fp>() + (size_t)r * N;
+        P.n_trace = R; for (int r = 0; r < R; ++r) P.trace[r] = S->d_pe.as<fp>() + (size_t)r * NL;
         P.n_static = (int)S->statics.size();
         for (size_t k = 0; k < S->statics.size(); ++k) {
             if (S->statics[k].kind == 0) { P.stat[k] = S->d_cyc.as<fp>() + S->cyc_off[k]; P.stat_mask[k] = S->cyc_mask[k]; }
@@ -445,11 +475,12 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     // (events recorded inside a captured graph cannot be synchronised from the host)
     const uint32_t epoch = (uint32_t)(S->proves_done + 1);
     GS_CUDA(c, cudaMemcpyAsync(S->d_epoch.p, &epoch, 4, cudaMemcpyHostToDevice, c->stream));
+    GS_CUDA(c, cudaMemsetAsync(S->d_epoch.as<uint8_t>() + 32, 0, 16, c->stream));
     auto fri_region = [&]() -> int {
         int rc;   // shadows the outer one on purpose: this lambda may run under stream capture
         layers.clear(); n_layers = 0;
         {
-        const unsigned g = grid_for(c, N, 256);
+        const unsigned g = grid_for(c, NL, 256);
         const int ns = S->evaluation.n_slots;
         ProfScope ps(c, "compose");
         if (ns <= 8) compose_kernel<8><<<g, 256, 0, c->stream>>>(S->d_params.as<ComposeParams>());
@@ -472,26 +503,44 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     // the device; roots are copied to mailbox slots as they appear and the host plans the queries behind them.
     for (int depth = 0;; ++depth) {
         const long long L = N >> (2 * depth), Q = L >> 2;
+        const long long QL = (NL >> (2 * depth)) >> 2;          // rows of this layer owned by this rank
         FriLayer ly; ly.v = v_cur; ly.len = L; ly.tree = t_next; t_next += (size_t)2 * Q * 8;
-        HashCols hc; hc.ncols = 4; for (int j = 0; j < 4; ++j) hc.col[j] = v_cur + j * Q;
-        if ((rc = hash_columns(c, S->hash_alg, hc, Q, ly.tree + 8 * Q))) return rc;
+        HashCols hc; hc.ncols = 4; for (int j = 0; j < 4; ++j) hc.col[j] = v_cur + j * QL;
+        if (!sharded) { if ((rc = hash_columns(c, S->hash_alg, hc, Q, ly.tree + 8 * Q))) return rc; }
+        else {
+            if ((rc = hash_columns(c, S->hash_alg, hc, QL, S->d_dig_loc.as<uint32_t>()))) return rc;
+            if ((rc = commit_gather(S, S->d_dig_loc.as<uint32_t>(), QL, ly.tree + 8 * Q))) return rc;
+        }
         if ((rc = merkle_build(c, S->hash_alg, ly.tree, Q))) return rc;
         if (depth >= 24) return c->fail(GS_E_UNSUPPORTED, "too many FRI layers");
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_ROOT + 32 * depth, ly.tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_FLAG + 4 * depth, S->d_epoch.p, 4, cudaMemcpyDeviceToHost, c->stream));
         layers.push_back(ly); ++n_layers;
         if (L <= 256) {
-            GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM, v_cur, L * sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
+            if (!sharded) GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM, v_cur, L * sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
+            else {
+                // remainder: gather the per-rank pieces and restore position order
+                int log_w = 0; while ((1 << log_w) < sh.world) ++log_w;
+                const long long LL = L >> log_w;
+                if ((rc = S->d_dig_all.ensure(c, (size_t)L * 16 * 2))) return rc;
+                const int nr = nccl().AllGather(v_cur, S->d_dig_all.p, (size_t)LL * 16, GS_NCCL_UINT8, c->comm, c->stream);
+                if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllGather: %s", nccl().GetErrorString(nr));
+                uint4* nat = S->d_dig_all.as<uint4>() + L;
+                permute_elems_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(S->d_dig_all.as<uint4>(), nat, LL, log_el, log_w);
+                c->launches++;
+                GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM, nat, L * sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
+            }
             break;
         }
         { ProfScope ps(c, "fri_fold");
           fri_challenge_kernel<<<1, 1, 0, c->stream>>>(ly.tree + 8, d_special + (depth & 3));
-          FriFoldParams F; F.v = v_cur; F.out = v_next; F.quarter = Q; F.special_x = d_special + (depth & 3);
+          FriFoldParams F; F.v = v_cur; F.out = v_next; F.quarter = QL; F.special_x = d_special + (depth & 3);
+          F.log_e = log_e; F.log_el = log_el; F.j0 = sh.j0();
           F.tw_lo = c->tw_lo; F.tw_hi = c->tw_hi; F.log_g = c->log_g; F.log_lo = c->log_lo;
           F.x_shift = 2 * depth + (c->log_g - log_n); F.iota_inv = fp_from_u128(iota_inv); F.quarter_inv = fp_from_u128(quarter_inv);
-          fri_fold_kernel<<<grid_for(c, Q, 256), 256, 0, c->stream>>>(F); }
+          fri_fold_kernel<<<grid_for(c, QL, 256), 256, 0, c->stream>>>(F); }
         c->launches += 2;
-        v_cur = v_next; v_next += Q;
+        v_cur = v_next; v_next += QL;
     }
         return GS_OK;
     };
@@ -513,13 +562,21 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     std::string err;
     std::vector<unsigned long long> g_addr;
     auto add_chunk = [&](const void* p) { g_addr.push_back((unsigned long long)(uintptr_t)p); return g_addr.size() - 1; };
+    // sharded: tree nodes are contributed by rank 0 only and row values by the rank that owns the row; everything else
+    // reads a zero block, and one all-reduce (integer sum) of the gathered buffer gives every rank the full query data
+    const void* zero_block = S->d_epoch.as<uint8_t>() + 32;
+    auto node_ptr = [&](const uint32_t* p) -> const void* { return (!sharded || sh.rank == 0) ? (const void*)p : zero_block; };
     struct PlannedProof { BatchProof bp; std::vector<size_t> node_chunk; std::vector<size_t> value_chunk; int chunks_per_value = 0; };
     auto plan_proof = [&](PlannedProof& pp, const uint32_t* tree, uint64_t n, const std::vector<uint32_t>& idx,
                           const std::vector<const fp*>& cols) -> int {
         if (merkle_prove_plan(idx, n, pp.bp, err) != 0) return c->fail(GS_E_STARK, "%s", err.c_str());
-        for (auto& col : pp.bp.node_ids) for (uint32_t id : col) { pp.node_chunk.push_back(add_chunk(tree + 8ull * id)); add_chunk(tree + 8ull * id + 4); }
+        for (auto& col : pp.bp.node_ids) for (uint32_t id : col) { pp.node_chunk.push_back(add_chunk(node_ptr(tree + 8ull * id))); add_chunk(node_ptr(tree + 8ull * id + 4)); }
         pp.chunks_per_value = (int)cols.size();
-        for (uint32_t i : idx) for (const fp* cp : cols) pp.value_chunk.push_back(add_chunk(cp + i));
+        for (uint32_t i : idx) {
+            const bool mine = !sharded || sh.owner(i) == sh.rank;
+            const long long il = sharded ? sh.to_local(i) : (long long)i;
+            for (const fp* cp : cols) pp.value_chunk.push_back(add_chunk(mine ? (const void*)(cp + il) : zero_block));
+        }
         return GS_OK;
     };
     auto aug4 = [&](const std::vector<uint32_t>& p, long long column_length) {
@@ -527,7 +584,8 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         for (size_t i = 0; i < p.size(); ++i) m[i] = p[i] % row_len;
         return first_seen_unique(m);
     };
-    auto row_cols = [&](const FriLayer& ly) { std::vector<const fp*> cols; for (int j = 0; j < 4; ++j) cols.push_back(ly.v + j * (ly.len >> 2)); return cols; };
+    int log_w_q = 0; while ((1 << log_w_q) < sh.world) ++log_w_q;
+    auto row_cols = [&](const FriLayer& ly) { std::vector<const fp*> cols; for (int j = 0; j < 4; ++j) cols.push_back(ly.v + j * ((ly.len >> log_w_q) >> 2)); return cols; };
     PlannedProof lc_pp, ev_pp;
     struct Comp { const uint8_t* root; PlannedProof column, poly; };
     std::vector<Comp> comps(layers.size() - 1);
@@ -601,6 +659,10 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         { ProfScope ps(c, "gather_queries");
           gather_chunks_kernel<<<(unsigned)((nch + 255) / 256), 256, 0, c->stream>>>(S->d_idx.as<unsigned long long>(), (int)nch, S->d_gather.as<uint4>()); }
         c->launches++;
+        if (sharded) {
+            const int nr = nccl().AllReduce(S->d_gather.p, S->d_gather.p, nch * 4, GS_NCCL_UINT32, GS_NCCL_SUM, c->comm, c->stream);
+            if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllReduce: %s", nccl().GetErrorString(nr));
+        }
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM + 4096, S->d_gather.p, nch * 16, cudaMemcpyDeviceToHost, c->stream));
     }
     cudaEventRecord(S->ev1, c->stream);

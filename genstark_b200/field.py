@@ -28,6 +28,20 @@ class Context:
     def check(self, rc: int):
         _native.check(self.handle, rc)
 
+    # multi-GPU: one process per GPU; rank 0 creates the id, every rank joins with it
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        lib = _native.lib()
+        buf = C.create_string_buffer(128)
+        rc = lib.gs_comm_unique_id(buf)
+        if rc != 0:
+            raise _native.NativeError(rc, lib.gs_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        self.check(self._lib.gs_ctx_comm_init(self.handle, rank, world, unique_id))
+        self.rank, self.world = rank, world
+
     def sync(self):
         self.check(self._lib.gs_ctx_sync(self.handle))
 

@@ -44,6 +44,11 @@ int gs_ctx_create(int device, gs_ctx** out);
 void gs_ctx_destroy(gs_ctx* ctx);
 const char* gs_last_error(gs_ctx* ctx);
 int gs_ctx_sync(gs_ctx* ctx);
+/* multi-GPU (one process per GPU): coset-sharded proving.  Rank 0 obtains an id (gs_comm_unique_id), every rank
+ * receives it out of band and joins.  A Stark created on a context with world > 1 shards the E cosets of the
+ * evaluation domain over the ranks; every rank must call gs_stark_prove with the same arguments and gets the same proof. */
+int gs_comm_unique_id(uint8_t out128[128]);
+int gs_ctx_comm_init(gs_ctx* ctx, int rank, int world, const uint8_t id128[128]);
 /* number of kernels launched through this context so far */
 uint64_t gs_ctx_launch_count(gs_ctx* ctx);
 /* createPrimeField(modulus): 0 when the modulus has the native fast path (isOptimized) */
