@@ -35,6 +35,7 @@ def lib() -> C.CDLL:
         'gs_ctx_sync': (i32, [vp]),
         'gs_comm_unique_id': (i32, [C.c_char_p]),
         'gs_ctx_comm_init': (i32, [vp, i32, i32, cp]),
+        'gs_shard_map': (i32, [i32, i32, i32, i64, i32, P(i64), P(i32)]),
         'gs_ctx_launch_count': (u64, [vp]),
         'gs_field_supported': (i32, [cp, C.c_size_t]),
         'gs_field_root_of_unity': (i32, [i32, C.c_char_p]),

@@ -85,6 +85,16 @@ int gs_ctx_comm_init(gs_ctx* c, int rank, int world, const uint8_t id128[128]) {
     return GS_OK;
 }
 
+/* the coset-sharding index map (host logic of the multi-GPU prover): position i = q*E + j is owned by rank j / (E/world) */
+int gs_shard_map(int world, int rank, int log2_e, int64_t index, int to_local, int64_t* out_index, int* out_owner) {
+    int log_w = 0; while ((1 << log_w) < world) ++log_w;
+    if (world < 1 || (1 << log_w) != world || log_w > log2_e || rank < 0 || rank >= world || index < 0) return GS_E_ARG;
+    Shard sh; sh.rank = rank; sh.world = world; sh.log_e = log2_e; sh.log_el = log2_e - log_w;
+    if (to_local) { if (out_owner) *out_owner = sh.owner(index); if (out_index) *out_index = sh.to_local(index); }
+    else { if (out_owner) *out_owner = rank; if (out_index) *out_index = sh.to_global(index); }
+    return GS_OK;
+}
+
 const char* gs_last_error(gs_ctx* c) { return c ? c->last_error.c_str() : g_null_error.c_str(); }
 
 int gs_ctx_sync(gs_ctx* c) {

@@ -49,6 +49,9 @@ int gs_ctx_sync(gs_ctx* ctx);
  * evaluation domain over the ranks; every rank must call gs_stark_prove with the same arguments and gets the same proof. */
 int gs_comm_unique_id(uint8_t out128[128]);
 int gs_ctx_comm_init(gs_ctx* ctx, int rank, int world, const uint8_t id128[128]);
+/* the sharding map itself (host logic): to_local = 0: local index of `rank` -> global position; to_local = 1: global
+ * position -> (owner rank, local index there).  E = 2^log2_e cosets dealt to the ranks in contiguous ranges. */
+int gs_shard_map(int world, int rank, int log2_e, int64_t index, int to_local, int64_t* out_index, int* out_owner);
 /* number of kernels launched through this context so far */
 uint64_t gs_ctx_launch_count(gs_ctx* ctx);
 /* createPrimeField(modulus): 0 when the modulus has the native fast path (isOptimized) */
