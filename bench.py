@@ -304,6 +304,9 @@ def run_ours(args, rank, local_rank, world):
             L.gs_mat_free(dst); L.gs_mat_free(work); src.free()
 
     if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
 
     peaks, peak_kind = measured_peaks()
@@ -369,10 +372,18 @@ def run_ours(args, rank, local_rank, world):
         'ntt': ntt,
         'clocks': sampler.summary(),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL prints its version banner on the first
+    # communicator) are sent to stderr, and the line is written to the real stdout at the end
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, 'w')
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
