@@ -20,6 +20,10 @@ struct Nccl {
     int (*CommDestroy)(NcclComm) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     std::string error;
     bool load() {
@@ -28,6 +32,7 @@ struct Nccl {
         if (!handle) { error = std::string("cannot load NCCL: ") + dlerror(); return false; }
 #define GS_SYM(field, sym) field = reinterpret_cast<decltype(field)>(dlsym(handle, sym)); if (!field) { error = std::string("NCCL symbol missing: ") + sym; return false; }
         GS_SYM(GetUniqueId, "ncclGetUniqueId") GS_SYM(CommInitRank, "ncclCommInitRank") GS_SYM(CommDestroy, "ncclCommDestroy")
+        GS_SYM(Send, "ncclSend") GS_SYM(Recv, "ncclRecv") GS_SYM(GroupStart, "ncclGroupStart") GS_SYM(GroupEnd, "ncclGroupEnd")
         GS_SYM(AllGather, "ncclAllGather") GS_SYM(AllReduce, "ncclAllReduce") GS_SYM(GetErrorString, "ncclGetErrorString")
 #undef GS_SYM
         return true;

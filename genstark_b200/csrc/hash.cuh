@@ -193,11 +193,12 @@ __global__ void __launch_bounds__(256) hash_rows_kernel(const uint32_t* __restri
 }
 
 // parents [count, 2*count) <- H(children)
+// parents [count + first, count + first + cnt) of the level with `count` parents (first = 0, cnt = count: whole level)
 template <int ALG>
-__global__ void __launch_bounds__(256) merkle_level_kernel(uint32_t* __restrict__ nodes, long long count) {
+__global__ void __launch_bounds__(256) merkle_level_kernel(uint32_t* __restrict__ nodes, long long count, long long first, long long cnt) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
-        const long long i = count + j;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += stride) {
+        const long long i = count + first + j;
         const uint4* ch = reinterpret_cast<const uint4*>(nodes + 16 * i);     // nodes[2i], nodes[2i+1]
         uint32_t m[16];
 #pragma unroll
@@ -213,10 +214,10 @@ __global__ void __launch_bounds__(256) merkle_level_kernel(uint32_t* __restrict_
 // staged in shared memory once and every intermediate node is written out.  Used for the latency-bound middle of
 // a tree (<= 2^16 nodes per level), where one launch per level costs ~6 us regardless of its size.
 template <int ALG, int LEVELS>
-__global__ void __launch_bounds__(1024) merkle_subtree_kernel(uint32_t* __restrict__ nodes, long long top_count) {
+__global__ void __launch_bounds__(1024) merkle_subtree_kernel(uint32_t* __restrict__ nodes, long long top_count, long long block0) {
     extern __shared__ __align__(16) unsigned char sub_raw[];
     uint4* s = reinterpret_cast<uint4*>(sub_raw);                      // 2^LEVELS digests = 2 x uint4 each
-    const long long top = top_count + blockIdx.x;
+    const long long top = top_count + block0 + blockIdx.x;
     const uint4* src = reinterpret_cast<const uint4*>(nodes + 8 * (top << LEVELS));
     for (int i = threadIdx.x; i < (2 << LEVELS); i += blockDim.x) s[i] = src[i];
     __syncthreads();
@@ -280,6 +281,27 @@ __global__ void fri_challenge_kernel(const uint32_t* __restrict__ root, fp* __re
     st_fp(out, fp_add(lo, fp_mul(hi, c9)));
 }
 
+// sharded tree: this rank's slice of every level from `count_local` parents per rank down to its sub-tree root
+// (node 2^log_w + rank), inside one block
+template <int ALG>
+__global__ void __launch_bounds__(1024) merkle_tail_range_kernel(uint32_t* __restrict__ nodes, int count_local, int log_w, int rank) {
+    for (int cl = count_local; cl >= 1; cl >>= 1) {
+        const long long base = ((long long)cl << log_w) + (long long)rank * cl;
+        for (int j = threadIdx.x; j < cl; j += blockDim.x) {
+            const long long i = base + j;
+            const uint4* ch = reinterpret_cast<const uint4*>(nodes + 16 * i);
+            uint32_t m[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { uint4 t = ch[q]; m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
+            uint32_t d[8];
+            auto getm = [&](int w) -> uint32_t { return m[w]; };
+            hash_words<ALG>(getm, 16, d);
+            store_digest(nodes + 8 * i, d);
+        }
+        __syncthreads();
+    }
+}
+
 static inline unsigned grid_for(Ctx* c, long long n, int threads, int waves = 8) {
     long long blocks = (n + threads - 1) / threads;
     const long long cap = (long long)c->sm_count * waves;
@@ -313,19 +335,21 @@ static inline int hash_rows(Ctx* c, int alg, const void* buf, int row_bytes, lon
     return GS_OK;
 }
 
-// nodes: 2n digests with the leaves already at [n, 2n)
-static inline int merkle_build(Ctx* c, int alg, uint32_t* nodes, long long n) {
+// nodes: 2n digests with the leaves already at [n, 2n).  log_w > 0: this rank builds only its 1/W slice of every
+// level down to its sub-tree root (node W + rank); the caller gathers the W roots and finishes the top.
+static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long n, int log_w, int rank) {
     if (alg != HASH_BLAKE2S && alg != HASH_SHA256) return c->fail(GS_E_ARG, "unknown hash algorithm");
-    long long count = n >> 1;
+    long long count = n >> 1;                  // parents of the current level (whole level)
     ProfScope ps(c, "merkle_build");
-    while (count > 32768) {                    // throughput-bound levels: one launch each
-        const unsigned g = grid_for(c, count, 256);
-        if (alg == HASH_BLAKE2S) merkle_level_kernel<HASH_BLAKE2S><<<g, 256, 0, c->stream>>>(nodes, count);
-        else merkle_level_kernel<HASH_SHA256><<<g, 256, 0, c->stream>>>(nodes, count);
+    while ((count >> log_w) > 32768) {         // throughput-bound levels: one launch each
+        const long long cl = count >> log_w;
+        const unsigned g = grid_for(c, cl, 256);
+        if (alg == HASH_BLAKE2S) merkle_level_kernel<HASH_BLAKE2S><<<g, 256, 0, c->stream>>>(nodes, count, rank * cl, cl);
+        else merkle_level_kernel<HASH_SHA256><<<g, 256, 0, c->stream>>>(nodes, count, rank * cl, cl);
         c->launches++;
         count >>= 1;
     }
-    if (count >= 2048) {                       // latency-bound middle: 11 levels per block in shared memory
+    if ((count >> log_w) >= 2048) {            // latency-bound middle: 11 levels per block in shared memory
         static bool attr = false;
         if (!attr) {
             cudaFuncSetAttribute(merkle_subtree_kernel<HASH_BLAKE2S, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -333,18 +357,36 @@ static inline int merkle_build(Ctx* c, int alg, uint32_t* nodes, long long n) {
             attr = true;
         }
         const long long blocks = count >> 10;  // the level with 2*count nodes splits into 2048-node subtrees
-        if (alg == HASH_BLAKE2S) merkle_subtree_kernel<HASH_BLAKE2S, 11><<<(unsigned)blocks, 1024, 64 * 1024, c->stream>>>(nodes, blocks);
-        else merkle_subtree_kernel<HASH_SHA256, 11><<<(unsigned)blocks, 1024, 64 * 1024, c->stream>>>(nodes, blocks);
+        const long long bl = blocks >> log_w;
+        if (alg == HASH_BLAKE2S) merkle_subtree_kernel<HASH_BLAKE2S, 11><<<(unsigned)bl, 1024, 64 * 1024, c->stream>>>(nodes, blocks, rank * bl);
+        else merkle_subtree_kernel<HASH_SHA256, 11><<<(unsigned)bl, 1024, 64 * 1024, c->stream>>>(nodes, blocks, rank * bl);
         c->launches++;
         count = blocks >> 1;
     }
-    if (count >= 1) {
-        if (alg == HASH_BLAKE2S) merkle_tail_kernel<HASH_BLAKE2S><<<1, 1024, 0, c->stream>>>(nodes, (int)count);
-        else merkle_tail_kernel<HASH_SHA256><<<1, 1024, 0, c->stream>>>(nodes, (int)count);
+    if (log_w == 0) {
+        if (count >= 1) {
+            if (alg == HASH_BLAKE2S) merkle_tail_kernel<HASH_BLAKE2S><<<1, 1024, 0, c->stream>>>(nodes, (int)count);
+            else merkle_tail_kernel<HASH_SHA256><<<1, 1024, 0, c->stream>>>(nodes, (int)count);
+            c->launches++;
+        }
+    } else {
+        const int cl = (int)(count >> log_w);
+        if (cl < 1) return c->fail(GS_E_ARG, "tree too small to shard");
+        if (alg == HASH_BLAKE2S) merkle_tail_range_kernel<HASH_BLAKE2S><<<1, 1024, 0, c->stream>>>(nodes, cl, log_w, rank);
+        else merkle_tail_range_kernel<HASH_SHA256><<<1, 1024, 0, c->stream>>>(nodes, cl, log_w, rank);
         c->launches++;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return c->cuda_fail(e, "merkle kernels");
+    return GS_OK;
+}
+static inline int merkle_build(Ctx* c, int alg, uint32_t* nodes, long long n) { return merkle_build_range(c, alg, nodes, n, 0, 0); }
+// top of a sharded tree once the W sub-tree roots sit at nodes[W .. 2W)
+static inline int merkle_build_top(Ctx* c, int alg, uint32_t* nodes, int world) {
+    if (world < 2) return GS_OK;
+    if (alg == HASH_BLAKE2S) merkle_tail_kernel<HASH_BLAKE2S><<<1, 1024, 0, c->stream>>>(nodes, world >> 1);
+    else merkle_tail_kernel<HASH_SHA256><<<1, 1024, 0, c->stream>>>(nodes, world >> 1);
+    c->launches++;
     return GS_OK;
 }
 

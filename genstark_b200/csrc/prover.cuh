@@ -122,6 +122,46 @@ static inline int commit_gather(Stark* S, const uint32_t* d_local, long long n_l
     return GS_OK;
 }
 
+// Merkle commit of the sharded prover for a large tree: instead of gathering all n digests everywhere and building the
+// tree W times, the digests are exchanged all-to-all into contiguous leaf ranges (1/W of the volume per rank), every
+// rank builds the sub-tree over its range, the W sub-tree roots are all-gathered (W x 32 bytes) and the top log2(W)
+// levels are computed everywhere.  d_local: the n/W digests this rank produced, layout [q][local coset].
+static inline int commit_split_tree(Stark* S, const uint32_t* d_local, long long n, uint32_t* tree) {
+    Ctx* c = S->ctx;
+    const Shard& sh = S->shard;
+    int log_w = 0; while ((1 << log_w) < sh.world) ++log_w;
+    const int W = sh.world, El = 1 << sh.log_el;
+    const long long rows = n >> sh.log_e;                 // q values of this commit
+    const long long rows_r = rows >> log_w;                // q range owned as LEAVES by one rank
+    const long long blk = rows_r * El;                     // digests sent to each peer
+    int rc;
+    if ((rc = S->d_dig_all.ensure(c, (size_t)(blk * W) * 32))) return rc;
+    { ProfScope ps(c, "nccl_alltoall_digests");
+      int nr = nccl().GroupStart();
+      for (int peer = 0; peer < W && nr == 0; ++peer) {
+          nr = nccl().Send(d_local + 8 * (peer * blk), (size_t)blk * 32, GS_NCCL_UINT8, peer, c->comm, c->stream);
+          if (nr == 0) nr = nccl().Recv(S->d_dig_all.as<uint32_t>() + 8 * (peer * blk), (size_t)blk * 32, GS_NCCL_UINT8, peer, c->comm, c->stream);
+      }
+      const int ne = nccl().GroupEnd();
+      if (nr != 0 || ne != 0) return c->fail(GS_E_CUDA, "NCCL all-to-all: %s", nccl().GetErrorString(nr ? nr : ne)); }
+    // leaves of this rank's range, in leaf order: leaf[(q - q0) * E + s * El + jl] = recv[s][(q - q0) * El + jl]
+    uint32_t* leaves = tree + 8 * (n + (long long)sh.rank * (n >> log_w));
+    const long long total = (blk << log_w) * 2;
+    permute_digests_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(S->d_dig_all.as<uint4>(), reinterpret_cast<uint4*>(leaves), blk, sh.log_el, log_w);
+    c->launches++;
+    if ((rc = merkle_build_range(c, S->hash_alg, tree, n, log_w, sh.rank))) return rc;
+    { ProfScope ps(c, "nccl_allgather_roots");
+      const int nr = nccl().AllGather(tree + 8 * (W + sh.rank), tree + 8 * W, 32, GS_NCCL_UINT8, c->comm, c->stream);
+      if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllGather: %s", nccl().GetErrorString(nr)); }
+    return merkle_build_top(c, S->hash_alg, tree, W);
+}
+// owner of tree node `id` in a split tree (nodes above the sub-tree roots are everywhere: rank 0 speaks for them)
+static inline int split_tree_owner(unsigned long long id, int log_w) {
+    if (id < (2ull << log_w)) return 0;
+    int lvl = 63 - __builtin_clzll(id);                  // level with 2^lvl nodes
+    return (int)((id - (1ull << lvl)) >> (lvl - log_w));
+}
+
 // run `fn` (which only enqueues work on the context stream) directly, or capture it once and replay it
 template <typename F>
 static inline int run_region(Stark* S, GraphSlot& slot, unsigned long long key, bool allow_graph, F&& fn) {
@@ -149,6 +189,7 @@ static inline int run_region(Stark* S, GraphSlot& slot, unsigned long long key, 
 
 struct FriLayer {
     fp* v; long long len; uint32_t* tree; uint8_t root[32];
+    bool split;        // sharded prover: the tree is split into W sub-trees (one per rank) below the level with W nodes
 };
 
 static inline double now_ms() {
@@ -306,6 +347,9 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
                             &S->d_small, &S->d_in_trace, &S->d_in_poly, &S->d_in_e, &S->d_c, &S->d_u, &S->d_cyc, &S->d_instrs, &S->d_consts, &S->d_epoch})
         gkey = (gkey ^ (unsigned long long)(uintptr_t)b->p) * 1099511628211ull;
     gkey = (gkey ^ (unsigned long long)S->keep_intermediates) * 1099511628211ull;
+    // trees with at least 2^14 leaves per ... are split across the ranks; small ones are replicated
+    auto split_ok = [&](long long n) { return sharded && n >= (16384ll * sh.world) && (n >> log_e) >= sh.world; };
+    const bool e_split = split_ok(N);
     auto commit_region = [&]() -> int {
         int r2;
         if ((r2 = ntt_run(c, S->d_trace.as<fp>(), T, S->d_poly.as<fp>(), T, S->d_work.as<fp>(), T, R, log_t, 0, true))) return r2;
@@ -322,10 +366,11 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         if (!sharded) { if ((r2 = hash_columns(c, S->hash_alg, hc, N, e_tree + 8 * N))) return r2; }
         else {
             if ((r2 = hash_columns(c, S->hash_alg, hc, NL, S->d_dig_loc.as<uint32_t>()))) return r2;
-            if ((r2 = commit_gather(S, S->d_dig_loc.as<uint32_t>(), NL, e_tree + 8 * N))) return r2;
+            if (e_split) { if ((r2 = commit_split_tree(S, S->d_dig_loc.as<uint32_t>(), N, e_tree))) return r2; }
+            else if ((r2 = commit_gather(S, S->d_dig_loc.as<uint32_t>(), NL, e_tree + 8 * N))) return r2;
         }
         if (timing) mark("Serialized evaluations of P(x) and S(x) polynomials", true);
-        if ((r2 = merkle_build(c, S->hash_alg, e_tree, N))) return r2;
+        if (!e_split && (r2 = merkle_build(c, S->hash_alg, e_tree, N))) return r2;
         GS_CUDA(c, cudaMemcpyAsync(c->mailbox, e_tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
         return GS_OK;
     };
@@ -504,14 +549,15 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     for (int depth = 0;; ++depth) {
         const long long L = N >> (2 * depth), Q = L >> 2;
         const long long QL = (NL >> (2 * depth)) >> 2;          // rows of this layer owned by this rank
-        FriLayer ly; ly.v = v_cur; ly.len = L; ly.tree = t_next; t_next += (size_t)2 * Q * 8;
+        FriLayer ly; ly.v = v_cur; ly.len = L; ly.tree = t_next; ly.split = false; t_next += (size_t)2 * Q * 8;
         HashCols hc; hc.ncols = 4; for (int j = 0; j < 4; ++j) hc.col[j] = v_cur + j * QL;
         if (!sharded) { if ((rc = hash_columns(c, S->hash_alg, hc, Q, ly.tree + 8 * Q))) return rc; }
         else {
             if ((rc = hash_columns(c, S->hash_alg, hc, QL, S->d_dig_loc.as<uint32_t>()))) return rc;
-            if ((rc = commit_gather(S, S->d_dig_loc.as<uint32_t>(), QL, ly.tree + 8 * Q))) return rc;
+            if (split_ok(Q)) { ly.split = true; if ((rc = commit_split_tree(S, S->d_dig_loc.as<uint32_t>(), Q, ly.tree))) return rc; }
+            else if ((rc = commit_gather(S, S->d_dig_loc.as<uint32_t>(), QL, ly.tree + 8 * Q))) return rc;
         }
-        if ((rc = merkle_build(c, S->hash_alg, ly.tree, Q))) return rc;
+        if (!ly.split && (rc = merkle_build(c, S->hash_alg, ly.tree, Q))) return rc;
         if (depth >= 24) return c->fail(GS_E_UNSUPPORTED, "too many FRI layers");
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_ROOT + 32 * depth, ly.tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_FLAG + 4 * depth, S->d_epoch.p, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -550,7 +596,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         fp* vc = S->d_l.as<fp>(); fp* vn = S->d_fri.as<fp>() + 4; uint32_t* tn = S->d_fri_trees.as<uint32_t>();
         for (int depth = 0;; ++depth) {
             const long long L = N >> (2 * depth), Q = L >> 2;
-            FriLayer ly; ly.v = vc; ly.len = L; ly.tree = tn; tn += (size_t)2 * Q * 8;
+            FriLayer ly; ly.v = vc; ly.len = L; ly.tree = tn; ly.split = false; tn += (size_t)2 * Q * 8;
             layers.push_back(ly); ++n_layers;
             if (L <= 256) break;
             vc = vn; vn += Q;
@@ -565,12 +611,16 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     // sharded: tree nodes are contributed by rank 0 only and row values by the rank that owns the row; everything else
     // reads a zero block, and one all-reduce (integer sum) of the gathered buffer gives every rank the full query data
     const void* zero_block = S->d_epoch.as<uint8_t>() + 32;
-    auto node_ptr = [&](const uint32_t* p) -> const void* { return (!sharded || sh.rank == 0) ? (const void*)p : zero_block; };
+    int log_w_n = 0; while ((1 << log_w_n) < sh.world) ++log_w_n;
+    auto node_ptr = [&](const uint32_t* tree, unsigned long long id, bool split, int half) -> const void* {
+        const int owner = (sharded && split) ? split_tree_owner(id, log_w_n) : 0;
+        return (!sharded || sh.rank == owner) ? (const void*)(tree + 8ull * id + 4 * half) : zero_block;
+    };
     struct PlannedProof { BatchProof bp; std::vector<size_t> node_chunk; std::vector<size_t> value_chunk; int chunks_per_value = 0; };
     auto plan_proof = [&](PlannedProof& pp, const uint32_t* tree, uint64_t n, const std::vector<uint32_t>& idx,
-                          const std::vector<const fp*>& cols) -> int {
+                          const std::vector<const fp*>& cols, bool split) -> int {
         if (merkle_prove_plan(idx, n, pp.bp, err) != 0) return c->fail(GS_E_STARK, "%s", err.c_str());
-        for (auto& col : pp.bp.node_ids) for (uint32_t id : col) { pp.node_chunk.push_back(add_chunk(node_ptr(tree + 8ull * id))); add_chunk(node_ptr(tree + 8ull * id + 4)); }
+        for (auto& col : pp.bp.node_ids) for (uint32_t id : col) { pp.node_chunk.push_back(add_chunk(node_ptr(tree, id, split, 0))); add_chunk(node_ptr(tree, id, split, 1)); }
         pp.chunks_per_value = (int)cols.size();
         for (uint32_t i : idx) {
             const bool mine = !sharded || sh.owner(i) == sh.rank;
@@ -613,18 +663,18 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             std::vector<uint32_t> exe_pos;
             if (pseudorandom_indexes(layers[0].root, (int)std::min<long long>(S->exe_queries, N - N / E), (uint64_t)N, (uint64_t)E, exe_pos, err) != 0) {
                 cudaStreamSynchronize(c->stream); return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str()); }
-            if ((rc = plan_proof(lc_pp, layers[0].tree, (uint64_t)(N >> 2), aug4(exe_pos, N), row_cols(layers[0])))) return rc;
+            if ((rc = plan_proof(lc_pp, layers[0].tree, (uint64_t)(N >> 2), aug4(exe_pos, N), row_cols(layers[0]), layers[0].split))) return rc;
             std::vector<uint32_t> m;
             for (uint32_t p : exe_pos) { m.push_back(p); m.push_back((uint32_t)((p + E) % N)); }
-            if ((rc = plan_proof(ev_pp, e_tree, (uint64_t)N, first_seen_unique(m), e_cols))) return rc;
+            if ((rc = plan_proof(ev_pp, e_tree, (uint64_t)N, first_seen_unique(m), e_cols, e_split))) return rc;
         } else {
             const FriLayer& pl = layers[d - 1]; const FriLayer& cl = layers[d];
             std::vector<uint32_t> positions;
             if (pseudorandom_indexes(cl.root, S->fri_queries, (uint64_t)cl.len, (uint64_t)E, positions, err) != 0) {
                 cudaStreamSynchronize(c->stream); return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str()); }
             comps[d - 1].root = cl.root;
-            if ((rc = plan_proof(comps[d - 1].column, cl.tree, (uint64_t)(cl.len >> 2), aug4(positions, cl.len), row_cols(cl)))) return rc;
-            if ((rc = plan_proof(comps[d - 1].poly, pl.tree, (uint64_t)(pl.len >> 2), positions, row_cols(pl)))) return rc;
+            if ((rc = plan_proof(comps[d - 1].column, cl.tree, (uint64_t)(cl.len >> 2), aug4(positions, cl.len), row_cols(cl), cl.split))) return rc;
+            if ((rc = plan_proof(comps[d - 1].poly, pl.tree, (uint64_t)(pl.len >> 2), positions, row_cols(pl), pl.split))) return rc;
         }
     }
     const uint8_t* lc_root = layers[0].root;
