@@ -67,6 +67,7 @@ def lib() -> C.CDLL:
         'gs_stark_create': (i32, [vp, cp, C.c_size_t, i32, i32, i32, P(vp)]),
         'gs_stark_destroy': (None, [vp]),
         'gs_air_generate_trace': (i32, [cp, C.c_size_t, cp, cp, vp]),
+        'gs_trace_backend': (C.c_char_p, []),
         'gs_stark_prove': (i32, [vp, cp, i32, cp, cp, cp, C.c_size_t, P(P(C.c_uint8)), P(C.c_size_t)]),
         'gs_stark_prove_ex': (i32, [vp, cp, i32, cp, cp, cp, C.c_size_t, i32, P(P(C.c_uint8)), P(C.c_size_t)]),
         'gs_stark_last_timing': (i32, [vp, P(C.c_float), P(C.c_double)]),

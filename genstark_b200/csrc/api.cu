@@ -516,6 +516,7 @@ int gs_stark_create(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int has
         if ((rc = batch_inverse(c, S->d_u.as<fp>(), S->d_u.as<fp>(), (fp*)c->scratch, N))) return rc;
         GS_CUDA(c, cudaStreamSynchronize(c->stream));
     }
+    trace_prepare(S.get());     // the transition function as native code (hostjit.h); the interpreter if that is not possible
     *out = S.release();
     return GS_OK;
 }

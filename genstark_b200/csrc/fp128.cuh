@@ -20,16 +20,30 @@
 #define GS_ALIGN16 alignas(16)
 #endif
 
+// Code that exists twice from one spelling: compiled into the library and kept as text for the run-time
+// specialised kernels (devjit.cuh hands it to NVRTC together with the code generated for an AIR).
+#ifndef GS_DUAL_SOURCE
+#define GS_DUAL_SOURCE(name, ...) __VA_ARGS__ static const char name[] = #__VA_ARGS__;
+#endif
+#ifdef __CUDA_ARCH__
+#define GS_DEVICE_DUAL_SOURCE(name, ...) __VA_ARGS__
+#else
+#define GS_DEVICE_DUAL_SOURCE(name, ...) static const char name[] = #__VA_ARGS__;
+#endif
+
 namespace gs {
 
+GS_DUAL_SOURCE(GS_FP_TYPE_SRC,
 struct GS_ALIGN16 fp {
     uint32_t v[4];
 };
+)
 
 // p and 2^128 - p
 static constexpr uint32_t P0 = 0x00000001u, P1 = 0xFFFFFFF7u, P2 = 0xFFFFFFFFu, P3 = 0xFFFFFFFFu;
 static constexpr uint32_t C0 = 0xFFFFFFFFu, C1 = 0x00000008u;   // 2^128 - p = 9*2^32 - 1
 
+GS_DUAL_SOURCE(GS_FP_BASIC_SRC,
 GS_HD fp fp_zero() { fp r; r.v[0] = r.v[1] = r.v[2] = r.v[3] = 0; return r; }
 GS_HD fp fp_one() { fp r; r.v[0] = 1; r.v[1] = r.v[2] = r.v[3] = 0; return r; }
 GS_HD fp fp_from_u64(uint64_t x) { fp r; r.v[0] = (uint32_t)x; r.v[1] = (uint32_t)(x >> 32); r.v[2] = r.v[3] = 0; return r; }
@@ -37,6 +51,7 @@ GS_HD bool fp_is_zero(const fp& a) { return (a.v[0] | a.v[1] | a.v[2] | a.v[3]) 
 GS_HD bool fp_eq(const fp& a, const fp& b) {
     return ((a.v[0] ^ b.v[0]) | (a.v[1] ^ b.v[1]) | (a.v[2] ^ b.v[2]) | (a.v[3] ^ b.v[3])) == 0;
 }
+)
 
 // ------------------------------------------------------------------------------------------------ host
 // Host-side twin used by the prover's control path (twiddle roots, challenges, trace generation).
@@ -96,8 +111,8 @@ static inline u128 h_root_of_unity(int log_order) {
     }
 }
 
-#ifdef __CUDA_ARCH__
 // ---------------------------------------------------------------------------------------------- device
+GS_DEVICE_DUAL_SOURCE(GS_FP_DEVICE_SRC,
 GS_D fp d_add(const fp& a, const fp& b) {
     uint32_t s0, s1, s2, s3, c, t0, t1, t2, t3, k;
     asm("add.cc.u32 %0, %5, %9;\n\t"
@@ -259,8 +274,18 @@ GS_D fp d_mul(const fp& a, const fp& b) {
     return d_reduce256(r);
 }
 
-
-#endif
+GS_D fp d_inv(const fp& a) {
+    const uint32_t e[4] = {0xFFFFFFFFu, 0xFFFFFFF6u, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    fp r = fp_one();
+    for (int w = 3; w >= 0; --w) {
+        for (int bit = 31; bit >= 0; --bit) {
+            r = d_mul(r, r);
+            if ((e[w] >> bit) & 1u) r = d_mul(r, a);
+        }
+    }
+    return r;
+}
+)
 
 // dispatch: PTX on the device, u128 on the host ------------------------------------------------------
 GS_HD fp fp_add(const fp& a, const fp& b) {

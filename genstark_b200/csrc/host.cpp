@@ -1,6 +1,7 @@
 // Host-only translation unit (g++): AIR parsing and execution-trace generation.
 #define GS_HOSTAIR_IMPL
 #include "hostair.h"
+#include "hostjit.h"
 #include "verifier.h"
 
 extern "C" int gs_stark_verify(const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,
@@ -23,3 +24,6 @@ extern "C" int gs_stark_verify(const uint8_t* air_blob, size_t blob_len, int has
     if (err_buf && err_cap) err_buf[0] = 0;
     return GS_OK;
 }
+
+/* which trace generator the last generate_trace of this thread used: "jit <hash>" or "interpreter (<reason>)" */
+extern "C" const char* gs_trace_backend(void) { return gs::trace_backend_status(); }

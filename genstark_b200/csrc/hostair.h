@@ -232,29 +232,9 @@ struct TransitionRunner {
 // host->device copy while the next block is being generated)
 typedef std::function<void(long long, long long)> TraceChunkFn;
 void generate_trace(const AirHost* S, const u128* init_state, const fp* input_traces, fp* tr, const TraceChunkFn* on_chunk = nullptr);
-#ifdef GS_HOSTAIR_IMPL
-void generate_trace(const AirHost* S, const u128* init_state, const fp* input_traces, fp* tr, const TraceChunkFn* on_chunk) {
-    const int R = S->R; const long long T = 1ll << S->log_t;
-    TransitionRunner run; run.init(S->transition, R, (int)S->statics.size());
-    for (int r = 0; r < R; ++r) run.buf[0][r] = w_from(init_state[r]);
-    const size_t n_stat = S->statics.size();
-    int p = 0;
-    for (long long s = 0; s < T; ++s, p ^= 1) {
-        const std::vector<w128>& cur = run.buf[p];
-        for (int r = 0; r < R; ++r) tr[(size_t)r * T + s] = fp_from_u128(w_canon(cur[r]));
-        if (s + 1 < T) {
-            int ii = 0;
-            for (size_t k = 0; k < n_stat; ++k) {
-                const StaticReg& sr = S->statics[k];
-                if (sr.kind == 0) run.stat[k] = w_from(sr.values[s & (sr.values.size() - 1)]);
-                else run.stat[k] = w_from(fp_to_u128(input_traces[(size_t)(ii++) * T + s]));
-            }
-            run.step(p);
-        }
-        if (on_chunk && ((s + 1) & 0xFFFF) == 0) (*on_chunk)(s + 1 - 0x10000, s + 1);
-    }
-    if (on_chunk && (T & 0xFFFF)) (*on_chunk)(T & ~0xFFFFll, T);
-}
-#endif
+// (implementation: hostjit.h -- compiled transition function, or the interpreter above)
+const char* trace_backend_status();
+// compile (or load from the cache) the native transition function ahead of the first prove
+void trace_prepare(const AirHost* S);
 
 }  // namespace gs

@@ -4,10 +4,16 @@
 // of the residue); only the copy stored into the trace is canonicalised, off the dependency chain.
 // 2^128 = c9 = 9*2^32 - 1 (mod p): the high half of a product is folded by one 64x36-bit multiply.
 #pragma once
+// The arithmetic below exists twice from one spelling: compiled into the library (interpreter, verifier) and
+// as text (GS_HOSTFIELD_SRC) that hostjit.h prepends to the C++ it generates for an AIR's transition function.
 #include <cstdint>
 #include <x86intrin.h>
 
+#define GS_DUAL_SOURCE(name, ...) __VA_ARGS__ static const char name[] = #__VA_ARGS__;
+
 namespace gs {
+
+GS_DUAL_SOURCE(GS_HOSTFIELD_SRC,
 
 typedef unsigned long long u64_t;
 struct w128 { u64_t lo, hi; };
@@ -60,5 +66,16 @@ static inline unsigned __int128 w_canon(w128 x) {
     return v >= p ? v - p : v;
 }
 static inline w128 w_from(unsigned __int128 v) { return {(u64_t)v, (u64_t)(v >> 64)}; }
+static inline w128 w_pow(w128 b, u64_t elo, u64_t ehi) {
+    w128 r = {1, 0};
+    while (elo | ehi) {
+        if (elo & 1) r = w_mul(r, b);
+        b = w_mul(b, b);
+        elo = (elo >> 1) | (ehi << 63); ehi >>= 1;
+    }
+    return r;
+}
+static inline w128 w_inv(w128 a) { return w_pow(a, 0xFFFFFFF6FFFFFFFFull, 0xFFFFFFFFFFFFFFFFull); }
+)
 
 }  // namespace gs

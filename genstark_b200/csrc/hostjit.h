@@ -1,0 +1,246 @@
+// Specialised execution-trace generation: the AIR's transition function is emitted as straight-line C++ over
+// the weakly reduced host arithmetic (hostfield.h), compiled once per distinct program with the host compiler
+// and loaded with dlopen -- the native counterpart of what the reference does at instantiate() time, where
+// air-assembly generates JavaScript source for the transition function and evaluates it (called from
+// lib/Stark.ts:97 as context.generateExecutionTrace()).  The compiled loop keeps the state in registers across
+// steps, so a MiMC chain runs at the latency of its two dependent modular multiplications instead of at
+// interpreter speed.  No compiler, GS_TRACE_JIT=0, or any failure => the interpreter in hostair.h (same results;
+// tests/test_trace_jit.py compares them).
+#pragma once
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include "hostair.h"
+#include "hostcrypto.h"
+#include "hostfield_fast.h"
+
+namespace gs {
+
+struct JitArgs {
+    w128* state;                    // R values, in/out (weakly reduced)
+    const w128* const* stat;        // per static register: table of values (cycle values or a T-length input column)
+    const u64_t* stat_mask;         // index = step & mask
+    w128* trace;                    // R x T canonical residues
+    long long T, s0, s1;            // writes rows s0..s1-1; applies the transition after each of them except step T-1
+};
+typedef void (*JitTraceFn)(const JitArgs*);
+
+struct TraceJit {
+    void* dl = nullptr;
+    JitTraceFn fn = nullptr;
+    std::string status;             // "jit <hash>" or the reason the interpreter is used
+    ~TraceJit() { /* handles stay loaded for the life of the process (shared by every Stark with this program) */ }
+};
+
+static inline std::string jit_hex_u64(u64_t v) { char b[32]; snprintf(b, sizeof b, "0x%llxull", v); return b; }
+
+// C++ source of the block function for this transition program.  Straight-line SSA over the flat program; products
+// that feed exactly one further multiplication or addition are fused with it (f_mul3_add / f_mul_add,
+// hostfield_fast.h), which removes a modular reduction from the dependency chain of S-boxes such as x^3 + k.
+static inline std::string jit_emit_source(const HostProgram& pr, int R, int n_static) {
+    const size_t n = pr.instrs.size();
+    // definitions: which instruction defines each operand, and how often each definition is read
+    std::vector<int> def_of_slot(pr.n_slots + 1, -1), da(n, -1), db(n, -1), uses(n, 0);
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t op = pr.instrs[i][0];
+        const bool bin = (op == OP_ADD || op == OP_SUB || op == OP_MUL), un = (op == OP_NEG || op == OP_INV || op == OP_EXP || op == OP_OUT);
+        if (bin) { da[i] = def_of_slot[pr.instrs[i][2]]; db[i] = def_of_slot[pr.instrs[i][3]]; if (da[i] < 0 || db[i] < 0) return ""; uses[da[i]]++; uses[db[i]]++; }
+        if (un) { da[i] = def_of_slot[pr.instrs[i][2]]; if (da[i] < 0) return ""; uses[da[i]]++; }
+        if (op == OP_NEXT || op > OP_OUT) return "";
+        if (op != OP_OUT) def_of_slot[pr.instrs[i][1]] = (int)i;
+    }
+    // fusion: child[j] = the product folded into instruction j; that product is not emitted on its own
+    std::vector<int> child(n, -1), other(n, -1); std::vector<char> deferred(n, 0);
+    auto is_mul = [&](int d) { return d >= 0 && pr.instrs[d][0] == OP_MUL; };
+    for (size_t j = 0; j < n; ++j) {
+        const uint32_t op = pr.instrs[j][0];
+        if (op != OP_MUL && op != OP_ADD) continue;
+        if (da[j] == db[j]) continue;                                       // x*x, x+x: nothing to fold
+        for (int side = 0; side < 2 && child[j] < 0; ++side) {
+            const int d = side ? db[j] : da[j], o = side ? da[j] : db[j];
+            if (!is_mul(d) || uses[d] != 1 || deferred[d]) continue;
+            if (op == OP_MUL && child[d] >= 0) continue;                     // a product of at most three factors
+            child[j] = d; other[j] = o; deferred[d] = 1;
+        }
+    }
+    std::ostringstream o;
+    o << "#include <x86intrin.h>\n" << GS_HOSTFIELD_SRC << "\n" << GS_HOSTFIELD_FAST_SRC << "\n";
+    o << "struct JitArgs { w128* state; const w128* const* stat; const u64_t* stat_mask; w128* trace; long long T, s0, s1; };\n";
+    o << "static const w128 k_zero = {0, 0};\n";
+    for (size_t i = 0; i < pr.consts.size(); ++i)
+        o << "static const w128 k" << i << " = {" << jit_hex_u64((u64_t)pr.consts[i]) << ", " << jit_hex_u64((u64_t)(pr.consts[i] >> 64)) << "};\n";
+    o << "extern \"C\" void gs_trace_block(const JitArgs* a) {\n";
+    o << "  const long long T = a->T; w128* const tr = a->trace;\n";
+    for (int r = 0; r < R; ++r) o << "  w128 s" << r << " = a->state[" << r << "];\n";
+    for (int k = 0; k < n_static; ++k) o << "  const w128* const st" << k << " = a->stat[" << k << "]; const u64_t m" << k << " = a->stat_mask[" << k << "];\n";
+    o << "  for (long long s = a->s0; s < a->s1; ++s) {\n";
+    for (int r = 0; r < R; ++r) o << "    tr[" << r << " * T + s] = w_from(w_canon(s" << r << "));\n";
+    o << "    if (s + 1 == T) break;\n";
+    std::vector<std::string> name(n);            // expression naming each definition's value
+    std::vector<std::string> nxt(R);
+    auto operands = [&](int d) { return name[da[d]] + ", " + name[db[d]]; };      // of a product
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t op = pr.instrs[i][0], d = pr.instrs[i][1], x = pr.instrs[i][2], y = pr.instrs[i][3];
+        const std::string v = "v" + std::to_string(i);
+        if (deferred[i]) continue;
+        switch (op) {
+            case OP_CONST: if (x >= pr.consts.size()) return ""; name[i] = "k" + std::to_string(x); break;
+            case OP_CUR: if ((int)x >= R) return ""; name[i] = "s" + std::to_string(x); break;
+            case OP_STATIC: if ((int)x >= n_static) return ""; o << "    const w128 " << v << " = st" << x << "[(u64_t)s & m" << x << "];\n"; name[i] = v; break;
+            case OP_ADD:
+                if (child[i] >= 0) {
+                    const int m = child[i];
+                    if (child[m] >= 0) o << "    const w128 " << v << " = f_mul3_add(" << operands(child[m]) << ", " << name[other[m]] << ", " << name[other[i]] << ");\n";
+                    else o << "    const w128 " << v << " = f_mul_add(" << operands(m) << ", " << name[other[i]] << ");\n";
+                } else o << "    const w128 " << v << " = w_add(" << name[da[i]] << ", " << name[db[i]] << ");\n";
+                name[i] = v; break;
+            case OP_MUL:
+                if (child[i] >= 0) o << "    const w128 " << v << " = f_mul3_add(" << operands(child[i]) << ", " << name[other[i]] << ", k_zero);\n";
+                else o << "    const w128 " << v << " = f_mul_add(" << name[da[i]] << ", " << name[db[i]] << ", k_zero);\n";
+                name[i] = v; break;
+            case OP_SUB: o << "    const w128 " << v << " = w_sub(" << name[da[i]] << ", " << name[db[i]] << ");\n"; name[i] = v; break;
+            case OP_NEG: o << "    const w128 " << v << " = w_sub(k_zero, " << name[da[i]] << ");\n"; name[i] = v; break;
+            case OP_INV: o << "    const w128 " << v << " = w_inv(" << name[da[i]] << ");\n"; name[i] = v; break;
+            case OP_EXP: {
+                if (y >= pr.consts.size()) return "";
+                const u128 e = pr.consts[y];
+                o << "    const w128 " << v << " = w_pow(" << name[da[i]] << ", " << jit_hex_u64((u64_t)e) << ", " << jit_hex_u64((u64_t)(e >> 64)) << ");\n";
+                name[i] = v; break;
+            }
+            case OP_OUT: if ((int)d < R) nxt[d] = name[da[i]]; break;
+            default: return "";
+        }
+    }
+    for (int r = 0; r < R; ++r) if (nxt[r].empty()) return "";
+    // the new state is assigned after every output is computed (outputs may read the old state)
+    for (int r = 0; r < R; ++r) o << "    const w128 n" << r << " = " << nxt[r] << ";\n";
+    for (int r = 0; r < R; ++r) o << "    s" << r << " = n" << r << ";\n";
+    o << "  }\n";
+    for (int r = 0; r < R; ++r) o << "  a->state[" << r << "] = s" << r << ";\n";
+    o << "}\n";
+    return o.str();
+}
+
+static inline std::string jit_cache_dir() {
+    if (const char* e = getenv("GS_JIT_CACHE")) return e;
+    std::string base;
+    if (const char* x = getenv("XDG_CACHE_HOME")) base = x;
+    else if (const char* h = getenv("HOME")) base = std::string(h) + "/.cache";
+    else base = "/tmp";
+    return base + "/genstark_b200";
+}
+
+static inline bool jit_mkdirs(const std::string& dir) {
+    std::string cur;
+    for (size_t i = 0; i <= dir.size(); ++i) {
+        if (i == dir.size() || dir[i] == '/') { if (!cur.empty()) mkdir(cur.c_str(), 0700); }
+        if (i < dir.size()) cur += dir[i];
+    }
+    struct stat st;
+    return stat(dir.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+
+// compile (or reuse) the block function of a transition program; never throws, never fails the prove
+std::shared_ptr<TraceJit> jit_get(const HostProgram& pr, int R, int n_static);
+#ifdef GS_HOSTAIR_IMPL
+std::shared_ptr<TraceJit> jit_get(const HostProgram& pr, int R, int n_static) {
+    static std::mutex mu;
+    static std::map<std::string, std::shared_ptr<TraceJit>> cache;
+    auto interp = [](const std::string& why) { auto j = std::make_shared<TraceJit>(); j->status = "interpreter (" + why + ")"; return j; };
+    if (const char* e = getenv("GS_TRACE_JIT")) if (e[0] == '0') return interp("GS_TRACE_JIT=0");
+    const std::string src = jit_emit_source(pr, R, n_static);
+    if (src.empty()) return interp("program not supported by the code generator");
+    uint8_t dg[32]; sha256_bytes((const uint8_t*)src.data(), src.size(), dg);
+    char hex[33]; for (int i = 0; i < 16; ++i) snprintf(hex + 2 * i, 3, "%02x", dg[i]);
+    const std::string key(hex);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    auto done = [&](std::shared_ptr<TraceJit> j) { cache[key] = j; return j; };
+    const std::string dir = jit_cache_dir();
+    if (!jit_mkdirs(dir)) return done(interp("cannot create " + dir));
+    const std::string so = dir + "/trace_" + key + ".so";
+    struct stat st;
+    if (stat(so.c_str(), &st) != 0) {
+        const std::string tag = dir + "/trace_" + key + "." + std::to_string((long)getpid());
+        const std::string cpp = tag + ".cpp", tmp = tag + ".so.tmp", log = tag + ".log";
+        FILE* f = fopen(cpp.c_str(), "w");
+        if (!f) return done(interp("cannot write " + cpp));
+        fwrite(src.data(), 1, src.size(), f); fclose(f);
+        const char* cxx = getenv("GS_JIT_CXX"); if (!cxx) cxx = getenv("CXX"); if (!cxx) cxx = "g++";
+        // -march=native: the code runs on the machine that compiles it (mulx / adx shorten the carry chains)
+        const std::string cmd = std::string(cxx) + " -O3 -march=native -std=c++17 -fPIC -shared -o '" + tmp + "' '" + cpp + "' > '" + log + "' 2>&1";
+        const int rc = system(cmd.c_str());
+        if (rc != 0 || rename(tmp.c_str(), so.c_str()) != 0) { unlink(tmp.c_str()); return done(interp("host compiler failed: " + cmd)); }
+        unlink(cpp.c_str()); unlink(log.c_str());
+    }
+    auto j = std::make_shared<TraceJit>();
+    j->dl = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!j->dl) return done(interp(std::string("dlopen: ") + dlerror()));
+    j->fn = (JitTraceFn)dlsym(j->dl, "gs_trace_block");
+    if (!j->fn) return done(interp("gs_trace_block missing in " + so));
+    j->status = "jit " + key;
+    return done(j);
+}
+#endif
+
+#ifdef GS_HOSTAIR_IMPL
+static thread_local std::string g_trace_backend = "not run";
+const char* trace_backend_status() { return g_trace_backend.c_str(); }
+
+void trace_prepare(const AirHost* S) { g_trace_backend = jit_get(S->transition, S->R, (int)S->statics.size())->status; }
+
+void generate_trace(const AirHost* S, const u128* init_state, const fp* input_traces, fp* tr, const TraceChunkFn* on_chunk) {
+    const int R = S->R; const long long T = 1ll << S->log_t;
+    const size_t n_stat = S->statics.size();
+    const std::shared_ptr<TraceJit> jit = jit_get(S->transition, R, (int)n_stat);
+    g_trace_backend = jit->status;
+    if (jit->fn) {
+        std::vector<w128> state(R);
+        for (int r = 0; r < R; ++r) state[r] = w_from(init_state[r]);
+        std::vector<const w128*> stat(n_stat + 1, nullptr);
+        std::vector<u64_t> mask(n_stat + 1, 0);
+        int ii = 0;
+        for (size_t k = 0; k < n_stat; ++k) {
+            const StaticReg& sr = S->statics[k];
+            // u128 and fp are both 16 little-endian bytes: the tables are read in place
+            if (sr.kind == 0) { stat[k] = reinterpret_cast<const w128*>(sr.values.data()); mask[k] = sr.values.size() - 1; }
+            else { stat[k] = reinterpret_cast<const w128*>(input_traces + (size_t)(ii++) * T); mask[k] = ~0ull; }
+        }
+        JitArgs a{state.data(), stat.data(), mask.data(), reinterpret_cast<w128*>(tr), T, 0, 0};
+        for (long long s0 = 0; s0 < T; s0 += 0x10000) {
+            a.s0 = s0; a.s1 = s0 + 0x10000 < T ? s0 + 0x10000 : T;
+            jit->fn(&a);
+            if (on_chunk) (*on_chunk)(a.s0, a.s1);
+        }
+        return;
+    }
+    TransitionRunner run; run.init(S->transition, R, (int)n_stat);
+    for (int r = 0; r < R; ++r) run.buf[0][r] = w_from(init_state[r]);
+    int p = 0;
+    for (long long s = 0; s < T; ++s, p ^= 1) {
+        const std::vector<w128>& cur = run.buf[p];
+        for (int r = 0; r < R; ++r) tr[(size_t)r * T + s] = fp_from_u128(w_canon(cur[r]));
+        if (s + 1 < T) {
+            int ii = 0;
+            for (size_t k = 0; k < n_stat; ++k) {
+                const StaticReg& sr = S->statics[k];
+                if (sr.kind == 0) run.stat[k] = w_from(sr.values[s & (sr.values.size() - 1)]);
+                else run.stat[k] = w_from(fp_to_u128(input_traces[(size_t)(ii++) * T + s]));
+            }
+            run.step(p);
+        }
+        if (on_chunk && ((s + 1) & 0xFFFF) == 0) (*on_chunk)(s + 1 - 0x10000, s + 1);
+    }
+    if (on_chunk && (T & 0xFFFF)) (*on_chunk)(T & ~0xFFFFll, T);
+}
+#endif
+
+}  // namespace gs

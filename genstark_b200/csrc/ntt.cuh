@@ -51,6 +51,7 @@ struct NttPassParams {
     fp scale;                     // multiplied into every output of the final pass (n^-1 for inverse)
 };
 
+GS_DUAL_SOURCE(GS_FP_LDST_SRC,
 GS_D fp ldg_fp(const fp* p) {
     uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
     fp r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
@@ -64,6 +65,7 @@ GS_D fp ld_fp(const fp* p) {
 GS_D void st_fp(fp* p, const fp& a) {
     *reinterpret_cast<uint4*>(p) = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
 }
+)
 
 // w_G^e from the two-level table (e < G)
 GS_D fp tw_lookup(const NttPassParams& P, unsigned e) {

@@ -417,15 +417,14 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         for (size_t g = 0; g < group_deg.size(); ++g) {
             if (group_deg[g] == comb_degree) continue;                                    // :89
             const unsigned long long incr = (unsigned long long)(comb_degree - group_deg[g]);
-            if (pow_incr.size() >= GS_MAX_POWERS) return c->fail(GS_E_UNSUPPORTED, "more than %d distinct constraint degrees", GS_MAX_POWERS);
-            pow_incr.push_back(incr);
+                        pow_incr.push_back(incr);
             for (int k : group_idx[g]) { dk_adj[k] = fp_from_u128(coeffs[next++]); pow_idx[k] = (int)pow_incr.size() - 1; }
         }
     }
     std::vector<fp> bk(nB), bk_adj(nB, fp_zero());
     for (int b = 0; b < nB; ++b) { bk[b] = fp_from_u128(coeffs[d_count + b]); if (comp_degree > T) bk_adj[b] = fp_from_u128(coeffs[d_count + nB + b]); }
     // I(x) per asserted register, and the partial-fraction form of 1/Z_b(x) (see compose.cuh)
-    std::vector<fp> ipoly, pf_coef; std::vector<unsigned> pf_shift; std::vector<int> ioff(nB), ilen(nB), pfoff(nB), pflen(nB), breg(nB);
+    std::vector<fp> ipoly; std::vector<u128> pf_coef; std::vector<int> pf_owner; std::vector<unsigned> pf_shift; std::vector<int> ioff(nB), ilen(nB), pfoff(nB), pflen(nB), breg(nB);
     {
         std::vector<std::vector<unsigned>> b_steps(nB);
         for (int a = 0; a < n_assert; ++a) { size_t b = 0; for (; b < b_regs.size(); ++b) if (b_regs[b] == asserts[a].reg) break; b_steps[b].push_back(asserts[a].step); }
@@ -440,8 +439,9 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
                     den = h_mul(den, h_sub(b_xs[b][k], b_xs[b][m]));
                 }
                 // c_k * X_k^-1
-                pf_coef.push_back(fp_from_u128(h_mul(h_inv(den), h_inv(b_xs[b][k]))));
+                pf_coef.push_back(h_mul(h_inv(den), h_inv(b_xs[b][k])));
                 pf_shift.push_back((unsigned)((unsigned long long)b_steps[b][k] * (unsigned long long)E));
+                pf_owner.push_back(b);
             }
             breg[b] = (int)b_regs[b];
         }
@@ -453,36 +453,53 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     const std::vector<u128> lc_all = prng_many(ev_root, 32, d_count + b_count + lc_total);
     std::vector<fp> lk(n_lc), lk_adj(n_lc, fp_zero());
     for (int j = 0; j < n_lc; ++j) { lk[j] = fp_from_u128(lc_all[d_count + b_count + j]); if (delta > 0) lk_adj[j] = fp_from_u128(lc_all[d_count + b_count + n_lc + j]); }
-    // inverse numerators of Z(x): num_i = w^(i*T) - 1 depends on i mod E (ZeroPolynomial.ts:40-41)
-    std::vector<fp> inv_num(E);
+    // E-periodic factors: 1/(x^T - 1) (num_i = w^(i*T) - 1 depends on i mod E, ZeroPolynomial.ts:40-41; inv(0) = 0 at
+    // i mod E == 0), x^incr per constraint group and x^delta (every increment is a multiple of T).  The random
+    // coefficients are folded with them into E-entry tables here, once per proof (compose.cuh).
+    std::vector<u128> inv_num(E);
     {
         const u128 w_e = c->root_of_order(log_e);        // w^T
         u128 acc = 1;
-        for (long long j = 0; j < E; ++j) { inv_num[j] = fp_from_u128(h_inv(h_sub(acc, 1))); acc = h_mul(acc, w_e); }
+        for (long long j = 0; j < E; ++j) { inv_num[j] = h_inv(h_sub(acc, 1)); acc = h_mul(acc, w_e); }
     }
-    // x^incr and x^delta over the evaluation domain: E-entry tables (see compose.cuh)
-    std::vector<fp> pow_tab(pow_incr.size() * E), delta_tab(E, fp_one());
+    std::vector<u128> pow_tab(pow_incr.size() * E), delta_tab(E, 1);
     for (size_t g = 0; g < pow_incr.size(); ++g) {
         if (pow_incr[g] % (unsigned long long)T) return c->fail(GS_E_UNSUPPORTED, "degree increment is not a multiple of the trace length");
         const u128 base = h_pow(w_n, (u128)(pow_incr[g] % (unsigned long long)N));
-        u128 a = 1; for (long long j = 0; j < E; ++j) { pow_tab[g * E + j] = fp_from_u128(a); a = h_mul(a, base); }
+        u128 a = 1; for (long long j = 0; j < E; ++j) { pow_tab[g * E + j] = a; a = h_mul(a, base); }
     }
     if (delta > 0) {
         const u128 base = h_pow(w_n, (u128)((unsigned long long)delta % (unsigned long long)N));
-        u128 a = 1; for (long long j = 0; j < E; ++j) { delta_tab[j] = fp_from_u128(a); a = h_mul(a, base); }
+        u128 a = 1; for (long long j = 0; j < E; ++j) { delta_tab[j] = a; a = h_mul(a, base); }
     }
+    std::vector<fp> cd_tab((size_t)K * E), pf_tab(pf_coef.size() * E), lk_tab((size_t)n_lc * E);
+    for (int k = 0; k < K; ++k)
+        for (long long j = 0; j < E; ++j) {
+            u128 v = fp_to_u128(dk[k]);
+            if (pow_idx[k] >= 0) v = h_add(v, h_mul(fp_to_u128(dk_adj[k]), pow_tab[(size_t)pow_idx[k] * E + j]));
+            cd_tab[(size_t)k * E + j] = fp_from_u128(h_mul(v, inv_num[j]));
+        }
+    for (size_t a = 0; a < pf_coef.size(); ++a)
+        for (long long j = 0; j < E; ++j) {
+            u128 v = fp_to_u128(bk[pf_owner[a]]);
+            if (delta > 0) v = h_add(v, h_mul(fp_to_u128(bk_adj[pf_owner[a]]), delta_tab[j]));
+            pf_tab[a * E + j] = fp_from_u128(h_mul(v, pf_coef[a]));
+        }
+    for (int q = 0; q < n_lc; ++q)
+        for (long long j = 0; j < E; ++j) {
+            u128 v = fp_to_u128(lk[q]);
+            if (delta > 0) v = h_add(v, h_mul(fp_to_u128(lk_adj[q]), delta_tab[j]));
+            lk_tab[(size_t)q * E + j] = fp_from_u128(v);
+        }
     // small-object upload: one packed buffer
     std::vector<uint8_t> small;
     auto put = [&](const void* p, size_t n) { size_t off = (small.size() + 15) & ~(size_t)15; small.resize(off + n); memcpy(small.data() + off, p, n); return off; };
     const int flag_init[2] = {0x7FFFFFFF, 0};
     const size_t o_flag = put(flag_init, 8);        // fixed offset 0: the captured graph copies it back
-    const size_t o_dk = put(dk.data(), K * 16), o_dka = put(dk_adj.data(), K * 16), o_pi = put(pow_idx.data(), K * 4);
-    const size_t o_bk = put(bk.data(), nB * 16), o_bka = put(bk_adj.data(), nB * 16);
-    const size_t o_ip = put(ipoly.data(), ipoly.size() * 16), o_pc = put(pf_coef.data(), pf_coef.size() * 16), o_ps = put(pf_shift.data(), pf_shift.size() * 4);
+    const size_t o_cd = put(cd_tab.data(), cd_tab.size() * 16), o_pf = put(pf_tab.data(), pf_tab.size() * 16), o_lk = put(lk_tab.data(), lk_tab.size() * 16);
+    const size_t o_ip = put(ipoly.data(), ipoly.size() * 16), o_ps = put(pf_shift.data(), pf_shift.size() * 4);
     const size_t o_io = put(ioff.data(), nB * 4), o_il = put(ilen.data(), nB * 4), o_po = put(pfoff.data(), nB * 4), o_pl = put(pflen.data(), nB * 4);
     const size_t o_br = put(breg.data(), nB * 4);
-    const size_t o_pt = put(pow_tab.data(), pow_tab.size() * 16), o_dt = put(delta_tab.data(), delta_tab.size() * 16);
-    const size_t o_lk = put(lk.data(), n_lc * 16), o_lka = put(lk_adj.data(), n_lc * 16), o_in = put(inv_num.data(), E * 16);
     if (small.size() + 64 > S->d_small.cap) return c->fail(GS_E_UNSUPPORTED, "too many assertions / constraints for the parameter block");
     uint8_t* ds = S->d_small.as<uint8_t>();
     GS_CUDA(c, cudaMemcpyAsync(ds, small.data(), small.size(), cudaMemcpyHostToDevice, c->stream));
@@ -496,16 +513,14 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             if (S->statics[k].kind == 0) { P.stat[k] = S->d_cyc.as<fp>() + S->cyc_off[k]; P.stat_mask[k] = S->cyc_mask[k]; }
             else { P.stat[k] = in_cols[k]; P.stat_mask[k] = 0xFFFFFFFFu; }
         }
-        P.n_constraints = K; P.dk = (const fp*)(ds + o_dk); P.dk_adj = (const fp*)(ds + o_dka); P.pow_idx = (const int*)(ds + o_pi);
-        P.n_powers = (int)pow_incr.size(); P.pow_tab = (const fp*)(ds + o_pt); P.delta_tab = (const fp*)(ds + o_dt);
-        P.x_last = fp_from_u128(h_pow(w_n, (u128)(T - 1) * (u128)E)); P.inv_num = (const fp*)(ds + o_in);
+        P.n_constraints = K; P.cd_tab = (const fp*)(ds + o_cd);
+        P.x_last = fp_from_u128(h_pow(w_n, (u128)(T - 1) * (u128)E));
         P.n_boundary = nB; P.b_reg = (const int*)(ds + o_br); P.b_ipoly_off = (const int*)(ds + o_io); P.b_ipoly_len = (const int*)(ds + o_il);
         P.b_ipoly = (const fp*)(ds + o_ip);
-        P.b_pf_off = (const int*)(ds + o_po); P.b_pf_len = (const int*)(ds + o_pl); P.b_pf_coef = (const fp*)(ds + o_pc); P.b_pf_shift = (const unsigned*)(ds + o_ps);
-        P.u_table = S->d_u.as<fp>(); P.bk = (const fp*)(ds + o_bk); P.bk_adj = (const fp*)(ds + o_bka);
+        P.b_pf_off = (const int*)(ds + o_po); P.b_pf_len = (const int*)(ds + o_pl); P.pf_tab = (const fp*)(ds + o_pf); P.b_pf_shift = (const unsigned*)(ds + o_ps);
+        P.u_table = S->d_u.as<fp>();
         P.n_lc = n_lc; for (int j = 0; j < n_lc; ++j) P.lc_col[j] = e_cols[j];
-        P.lk = (const fp*)(ds + o_lk); P.lk_adj = (const fp*)(ds + o_lka);
-        P.delta = (unsigned long long)delta;
+        P.lk_tab = (const fp*)(ds + o_lk);
         P.tw_lo = c->tw_lo; P.tw_hi = c->tw_hi; P.log_g = c->log_g; P.log_lo = c->log_lo;
         P.out = S->d_l.as<fp>(); P.c_out = S->keep_intermediates ? S->d_c.as<fp>() : nullptr;
         P.fail_flag = (int*)(ds + o_flag);

@@ -126,6 +126,10 @@ class Stark:
         """lib/Stark.ts:81-163 -> StarkProof {evRoot, evProof, ldProof, iShapes}"""
         return self.parse(self.prove_bytes(assertions, inputs, seed))
 
+    def generateExecutionTrace(self, inputs=None, seed=None) -> List[List[int]]:
+        """lib/Stark.ts:252-257: the execution trace as register rows (host only)."""
+        return generate_execution_trace(self.air, inputs, seed)
+
     def last_timing(self):
         """(CUDA-event ms of the device part, host wall-clock ms) of the last prove"""
         d, h = C.c_float(), C.c_double()
@@ -298,6 +302,31 @@ def verify_proof(air: AirModule, options: dict, assertions: Sequence[dict], proo
     if rc != 0:
         raise StarkError(err.value.decode() or f'verification failed (status {rc})')
     return True
+
+
+def generate_execution_trace(air: AirModule, inputs=None, seed=None) -> List[List[int]]:
+    """context.generateExecutionTrace() (lib/Stark.ts:97,252-257) without a device: gs_air_generate_trace runs the
+    AIR's transition function compiled to native code (or interpreted: gs_trace_backend says which)."""
+    lib = _native.lib()
+    p = air.modulus
+    init = [int(v) % p for v in air.init(inputs or [], seed or [])]
+    if len(init) != air.trace_register_count:
+        raise StarkError('Failed to generate the execution trace: initial state has the wrong width')
+    traces = air.expand_inputs(inputs or [])
+    in_blob = b''.join((int(v) % p).to_bytes(16, 'little') for t in traces for v in t) if traces else None
+    blob = pack_air(air)
+    r, t = air.trace_register_count, air.trace_length
+    out = C.create_string_buffer(16 * r * t)
+    rc = lib.gs_air_generate_trace(blob, len(blob), b''.join(v.to_bytes(16, 'little') for v in init), in_blob, out)
+    if rc != 0:
+        raise StarkError(f'Failed to generate the execution trace (status {rc})')
+    raw = out.raw
+    return [[int.from_bytes(raw[16 * (k * t + i):16 * (k * t + i) + 16], 'little') for i in range(t)] for k in range(r)]
+
+
+def trace_backend() -> str:
+    """'jit <hash>' or 'interpreter (<reason>)' for the calling thread's last trace generation"""
+    return (_native.lib().gs_trace_backend() or b'').decode()
 
 
 def instantiate(air: AirModule, options: Optional[dict] = None, logger=None) -> Stark:

@@ -133,6 +133,10 @@ void gs_stark_destroy(gs_stark* s);
 /* Stark.generateExecutionTrace (lib/Stark.ts:252-257): host only; out_trace: R x T x 16 bytes, row = register */
 int gs_air_generate_trace(const uint8_t* air_blob, size_t blob_len, const uint8_t* init_state16,
                           const uint8_t* input_traces, uint8_t* out_trace);
+/* which generator the calling thread's last trace generation used: "jit <hash>" (the transition function compiled
+ * to native code at first use, as air-assembly compiles it to JavaScript at instantiate()) or
+ * "interpreter (<reason>)".  GS_TRACE_JIT=0 forces the interpreter; results are identical. */
+const char* gs_trace_backend(void);
 int gs_stark_prove(gs_stark* s, const uint8_t* assertions, int n_assertions, const uint8_t* init_state16,
                    const uint8_t* input_traces, const uint8_t* shapes_blob, size_t shapes_len,
                    const uint8_t** proof_out, size_t* proof_len);

@@ -1,0 +1,69 @@
+"""Execution-trace generation on the host (lib/Stark.ts:97,252-257): the transition function compiled to native code
+at first use (hostjit.h) and the interpreter (hostair.h) both reproduce the oracle's trace, for every AIR family of
+the BASELINE configs.  Host only: no device needed."""
+import os
+
+import pytest
+
+import cases
+from genstark_b200 import stark as gstark
+from oracle.air import ProvingContext
+
+CASES = {
+    'mimc': lambda: cases.mimc(1 << 10, 8),
+    'rescue': lambda: cases.rescue(4),
+    'poseidon': lambda: cases.poseidon(4, 2),
+}
+
+
+def _oracle_trace(air, inputs, seed):
+    tr = ProvingContext(air, inputs, seed).generate_execution_trace()
+    return [[int(tr[r][s]) for s in range(air.trace_length)] for r in range(air.trace_register_count)]
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_compiled_and_interpreted_traces_equal_the_oracle(name, tmp_path, monkeypatch):
+    air, opts, a, inputs, seed = CASES[name]()
+    want = _oracle_trace(air, inputs, seed)
+    monkeypatch.setenv('GS_JIT_CACHE', str(tmp_path))
+    monkeypatch.setenv('GS_TRACE_JIT', '0')
+    got_i = gstark.generate_execution_trace(air, inputs, seed)
+    assert gstark.trace_backend().startswith('interpreter')
+    assert got_i == want
+    monkeypatch.setenv('GS_TRACE_JIT', '1')
+    got_j = gstark.generate_execution_trace(air, inputs, seed)
+    backend = gstark.trace_backend()
+    if not backend.startswith('jit'):
+        pytest.skip(f'no host compiler for the trace JIT: {backend}')
+    assert got_j == want
+    # the compiled object is cached on disk and in the process
+    assert any(f.name.endswith('.so') for f in tmp_path.iterdir())
+    assert gstark.generate_execution_trace(air, inputs, seed) == want
+    for x in a:
+        assert got_j[x['register']][x['step']] == x['value']
+
+
+def _quadratic_air(steps, c):
+    from genstark_b200.air import AirModule, ProgramBuilder, P128
+    t = ProgramBuilder(P128)
+    t.out(0, t.cur(0) * t.cur(0) + c)
+    e = ProgramBuilder(P128)
+    e.out(0, e.nxt(0) - (e.cur(0) * e.cur(0) + c))
+    return AirModule(name='quad', modulus=P128, trace_register_count=1, trace_length=steps, transition=t.build(),
+                     evaluation=e.build(), static_registers=[], extension_factor=4,
+                     init=lambda inputs, seed: [int(seed[0]) % P128])
+
+
+def test_jit_falls_back_to_the_interpreter_without_a_compiler(tmp_path, monkeypatch):
+    air = _quadratic_air(64, 0xB200_0001)            # a program no other test compiles (the in-process cache is per program)
+    monkeypatch.setenv('GS_JIT_CACHE', str(tmp_path))
+    monkeypatch.setenv('GS_JIT_CXX', '/nonexistent/compiler')
+    monkeypatch.setenv('GS_TRACE_JIT', '1')
+    got = gstark.generate_execution_trace(air, [], [9])
+    assert gstark.trace_backend().startswith('interpreter (host compiler failed')
+    assert got == _oracle_trace(air, [], [9])
+    x, want = 9, []
+    for _ in range(64):
+        want.append(x)
+        x = (x * x + 0xB200_0001) % air.modulus
+    assert got[0] == want
