@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
         'gs_ntt_into': (i32, [vp, vp, vp, vp, i32]),
         'gs_stark_verify': (i32, [cp, C.c_size_t, i32, i32, i32, cp, i32, cp, C.c_size_t, cp, C.c_char_p, C.c_size_t]),
         'gs_stark_stage_times': (cp, [vp]),
+        'gs_stark_compose_backend': (C.c_char_p, [vp]),
         'gs_stark_set_debug': (i32, [vp, i32]),
         'gs_stark_read_intermediate': (i32, [vp, i32, vp, C.c_size_t]),
         'gs_debug_modmul_probe': (i32, [vp, i32, i32, P(C.c_float)]),

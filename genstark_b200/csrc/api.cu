@@ -516,6 +516,7 @@ int gs_stark_create(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int has
         if ((rc = batch_inverse(c, S->d_u.as<fp>(), S->d_u.as<fp>(), (fp*)c->scratch, N))) return rc;
         GS_CUDA(c, cudaStreamSynchronize(c->stream));
     }
+    S->compose_jit = compose_jit_get(c, *S);   // K2 specialised for this AIR (NVRTC); the interpreting kernel if that is not possible
     trace_prepare(S.get());     // the transition function as native code (hostjit.h); the interpreter if that is not possible
     *out = S.release();
     return GS_OK;
@@ -627,6 +628,12 @@ int gs_ntt_into(gs_ctx* c, const gs_mat* src, gs_mat* dst, gs_mat* work, int inv
     cudaSetDevice(c->device);
     return ntt_run(c, src->data, src->cols, dst->data, dst->cols, work ? work->data : nullptr, dst->cols, (int)src->rows, log_t,
                    log_n - log_t, inverse != 0);
+}
+
+const char* gs_stark_compose_backend(gs_stark* s) {
+    static thread_local std::string out;
+    out = (s && s->compose_jit) ? s->compose_jit->status : std::string("interpreter");
+    return out.c_str();
 }
 
 const char* gs_stark_stage_times(gs_stark* s) {

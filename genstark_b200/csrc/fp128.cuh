@@ -26,7 +26,7 @@
 #define GS_DUAL_SOURCE(name, ...) __VA_ARGS__ static const char name[] = #__VA_ARGS__;
 #endif
 #ifdef __CUDA_ARCH__
-#define GS_DEVICE_DUAL_SOURCE(name, ...) __VA_ARGS__
+#define GS_DEVICE_DUAL_SOURCE(name, ...) __VA_ARGS__ static const char name[] = #__VA_ARGS__;
 #else
 #define GS_DEVICE_DUAL_SOURCE(name, ...) static const char name[] = #__VA_ARGS__;
 #endif

@@ -13,6 +13,7 @@
 #include "batchinv.cuh"
 #include "fri.cuh"
 #include "compose.cuh"
+#include "devjit.cuh"
 #include "hostcrypto.h"
 #include "hostfield.h"
 #include "hostair.h"
@@ -60,6 +61,7 @@ struct Stark : public AirHost {
     bool use_graphs = true;           // CUDA graphs for the launch-bound chains (off while profiling / stage timing)
     unsigned long long proves_done = 0;
     GraphSlot g_commit, g_fri;
+    std::shared_ptr<ComposeJit> compose_jit;   // K2 specialised for this AIR's constraints (devjit.cuh); fn == null => interpreter
     Shard shard;                      // coset sharding over the ranks of the context (world == 1: everything local)
     DevBuf d_dig_loc, d_dig_all;      // commit boundary: local digests / all-gathered digests before the permutation
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -543,7 +545,13 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         const unsigned g = grid_for(c, NL, 256);
         const int ns = S->evaluation.n_slots;
         ProfScope ps(c, "compose");
-        if (ns <= 8) compose_kernel<8><<<g, 256, 0, c->stream>>>(S->d_params.as<ComposeParams>());
+        if (S->compose_jit && S->compose_jit->fn) {
+            const ComposeParams* dp = S->d_params.as<ComposeParams>();
+            void* args[1] = {(void*)&dp};
+            const CUresult r = driver_api().LaunchKernel(S->compose_jit->fn, g, 1, 1, 256, 1, 1, 0, (CUstream)c->stream, args, nullptr);
+            if (r != CUDA_SUCCESS) return c->fail(GS_E_CUDA, "cuLaunchKernel(gs_compose_jit): error %d", (int)r);
+        }
+        else if (ns <= 8) compose_kernel<8><<<g, 256, 0, c->stream>>>(S->d_params.as<ComposeParams>());
         else if (ns <= 32) compose_kernel<32><<<g, 256, 0, c->stream>>>(S->d_params.as<ComposeParams>());
         else if (ns <= 128) compose_kernel<128><<<g, 256, 0, c->stream>>>(S->d_params.as<ComposeParams>());
         else return c->fail(GS_E_UNSUPPORTED, "evaluation program needs %d value slots (max 128)", ns);

@@ -143,6 +143,10 @@ class Stark:
         return verify_proof(self.air, dict(hashAlgorithm=self.hashAlgorithm, exeQueryCount=self.exeQueryCount,
                                            friQueryCount=self.friQueryCount), assertions, buf, publicInputs)
 
+    def compose_backend(self) -> str:
+        """'nvrtc <hash>' when the constraint evaluator was compiled for this AIR, else 'interpreter (<reason>)'"""
+        return (self._lib.gs_stark_compose_backend(self._handle) or b'').decode()
+
     def stage_times(self) -> List:
         return json.loads(self._lib.gs_stark_stage_times(self._handle).decode() or '[]')
 

@@ -154,6 +154,10 @@ int gs_stark_verify(const uint8_t* air_blob, size_t blob_len, int hash_alg, int 
                     const uint8_t* assertions, int n_assertions, const uint8_t* proof, size_t proof_len,
                     const uint8_t* public_traces, char* err_buf, size_t err_cap);
 /* per-stage host milliseconds of the last prove as JSON [[name, ms], ...] (Logger, lib/utils/Logger.ts) */
+/* which constraint-evaluation kernel this instance launches: "nvrtc <hash>" (the AIR's evaluation function compiled
+ * to sm_100a code at creation, as air-assembly compiles it to JavaScript) or "interpreter (<reason>)".
+ * GS_COMPOSE_JIT=0 forces the interpreting kernel; results are identical. */
+const char* gs_stark_compose_backend(gs_stark* s);
 const char* gs_stark_stage_times(gs_stark* s);
 /* test hooks: keep C(x) and read device-resident intermediates back (0 P evals, 1 C, 2 L, 3 P polys) */
 int gs_stark_set_debug(gs_stark* s, int keep_intermediates);
