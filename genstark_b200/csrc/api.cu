@@ -43,6 +43,7 @@ int gs_ctx_create(int device, gs_ctx** out) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
     int rc = ctx_init_tables(c);
     if (rc != GS_OK) { g_null_error = c->last_error; delete c; return rc; }
+    if (cudaMalloc(&c->counters, 256) != cudaSuccess || cudaMemset(c->counters, 0, 256) != cudaSuccess) { g_null_error = "cudaMalloc(counters)"; delete c; return GS_E_CUDA; }
     c->mailbox_bytes = 8 << 20;
     if (cudaHostAlloc(&c->mailbox, c->mailbox_bytes, cudaHostAllocDefault) != cudaSuccess) {
         g_null_error = "cudaHostAlloc(mailbox)"; delete c; return GS_E_CUDA;
@@ -57,6 +58,7 @@ void gs_ctx_destroy(gs_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->tw_lo); cudaFree(c->tw_hi); cudaFree(c->tw_small);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->counters) cudaFree(c->counters);
     if (c->mailbox) cudaFreeHost(c->mailbox);
     if (c->comm) nccl().CommDestroy(c->comm);
     cudaStreamDestroy(c->stream);

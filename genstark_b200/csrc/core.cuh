@@ -31,6 +31,7 @@ struct Ctx {
     void* mailbox = nullptr;
     size_t mailbox_bytes = 0;
     int sm_count = 148;
+    unsigned* counters = nullptr;   // zeroed device words for "last block finishes" kernels (each use leaves them zero)
     // coset-sharded multi-GPU prover: one process per GPU, NCCL communicator over all ranks of the box
     int rank = 0, world = 1;
     NcclComm comm = nullptr;

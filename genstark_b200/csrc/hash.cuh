@@ -35,14 +35,27 @@ GS_D uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 #define B2S_IV6 0x1F83D9ABu
 #define B2S_IV7 0x5BE0CD19u
 
+// Pipe balance: one blake2s compression is 320 XOR + 320 rotate (LOP3 / PRMT / SHF: ALU pipe only) + 160 two-input and
+// 160 three-input additions.  ptxas already issues the two-input additions on the FMA pipe (IMAD.IADD) but keeps the
+// three-input ones as IADD3 on the ALU pipe, which then runs at 93 % while the FMA pipe idles at 20 % (ncu, round 1).
+// Written as two multiply-adds by a 1 that ptxas cannot fold (a __constant__ word), they issue on the FMA pipe too:
+// ALU 648 / FMA 482 instructions per compression instead of 814 / 158.
+__device__ __constant__ uint32_t GS_B2S_ONE = 1u;
+GS_D uint32_t b2s_add3(uint32_t a, uint32_t b, uint32_t x, uint32_t one) {
+    uint32_t t, r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(b), "r"(one), "r"(a));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(one), "r"(t));
+    return r;
+}
 #define B2S_G(a, b, c, d, x, y)                    \
-    a = a + b + (x); d = __byte_perm(d ^ a, 0, 0x1032); \
+    a = b2s_add3(a, b, (x), one); d = __byte_perm(d ^ a, 0, 0x1032); \
     c = c + d; b = rotr32(b ^ c, 12);              \
-    a = a + b + (y); d = __byte_perm(d ^ a, 0, 0x0321); \
+    a = b2s_add3(a, b, (y), one); d = __byte_perm(d ^ a, 0, 0x0321); \
     c = c + d; b = rotr32(b ^ c, 7);
 
 // one compression; sigma is fully unrolled so message words stay in registers
 GS_D void blake2s_compress(uint32_t (&h)[8], const uint32_t (&m)[16], uint32_t t0, bool last) {
+    const uint32_t one = GS_B2S_ONE;
     uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
     uint32_t v8 = B2S_IV0, v9 = B2S_IV1, v10 = B2S_IV2, v11 = B2S_IV3;
     uint32_t v12 = B2S_IV4 ^ t0, v13 = B2S_IV5, v14 = last ? ~B2S_IV6 : B2S_IV6, v15 = B2S_IV7;
@@ -242,6 +255,56 @@ __global__ void __launch_bounds__(1024) merkle_subtree_kernel(uint32_t* __restri
     }
 }
 
+// Top of a tree in ONE launch: the level with `level_nodes` nodes (heap indices level_nodes .. 2*level_nodes) is cut into
+// 512-node subtrees, one per block, reduced in shared memory (every intermediate node is written out); the block that
+// finishes last then reduces the subtree roots to the root.  Replaces a launch per level where a level is a handful of
+// dependent ~1 us compressions and the launch gap costs more than the work.  *counter must be zero and is left zero.
+template <int ALG>
+__global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ nodes, int level_nodes, unsigned* counter) {
+    __shared__ uint4 s[1024];                                       // 512 digests
+    __shared__ int is_last;
+    const int leaves = level_nodes < 512 ? level_nodes : 512;
+    int top = level_nodes / leaves + blockIdx.x;                    // heap index of this block's subtree root
+    int n = leaves;
+    for (int pass = 0; pass < 2; ++pass) {
+        // stage the n descendants of `top` (contiguous in the heap layout); .cg: pass 1 reads what other blocks just wrote
+        int log_n = 0; while ((1 << log_n) < n) ++log_n;
+        const uint4* src = reinterpret_cast<const uint4*>(nodes + 8 * ((long long)top << log_n));
+        for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s[i] = __ldcg(src + i);
+        __syncthreads();
+        for (int l = log_n - 1; l >= 0; --l) {
+            const int cnt = 1 << l;
+            uint32_t d[8];
+            const int j = threadIdx.x;
+            if (j < cnt) {
+                uint32_t m[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { uint4 t = s[4 * j + q]; m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
+                auto getm = [&](int w) -> uint32_t { return m[w]; };
+                hash_words<ALG>(getm, 16, d);
+            }
+            __syncthreads();
+            if (j < cnt) {
+                s[2 * j] = make_uint4(d[0], d[1], d[2], d[3]); s[2 * j + 1] = make_uint4(d[4], d[5], d[6], d[7]);
+                store_digest(nodes + 8 * (((long long)top << l) + j), d);
+            }
+            __syncthreads();
+        }
+        if (pass == 1 || gridDim.x == 1) return;
+        // the last block to get here owns the remaining gridDim.x subtree roots
+        __threadfence();
+        if (threadIdx.x == 0) {
+            const unsigned ticket = atomicAdd(counter, 1u);
+            is_last = (ticket == gridDim.x - 1);
+            if (is_last) *counter = 0;
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        top = 1; n = (int)gridDim.x;
+    }
+}
+
 // all levels from `count` parents down to the root inside one block
 template <int ALG>
 __global__ void __launch_bounds__(1024) merkle_tail_kernel(uint32_t* __restrict__ nodes, int count) {
@@ -348,6 +411,17 @@ static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long
         else merkle_level_kernel<HASH_SHA256><<<g, 256, 0, c->stream>>>(nodes, count, rank * cl, cl);
         c->launches++;
         count >>= 1;
+    }
+    if (log_w == 0 && count >= 1) {
+        // the rest of the tree in one launch; the level with 2 * count nodes holds at most 2^16 of them here
+        const int level_nodes = (int)(2 * count);
+        const unsigned blocks = level_nodes <= 512 ? 1u : (unsigned)(level_nodes / 512);
+        if (alg == HASH_BLAKE2S) merkle_top_kernel<HASH_BLAKE2S><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters);
+        else merkle_top_kernel<HASH_SHA256><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters);
+        c->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return c->cuda_fail(e, "merkle_top_kernel");
+        return GS_OK;
     }
     if ((count >> log_w) >= 2048) {            // latency-bound middle: 11 levels per block in shared memory
         static bool attr = false;

@@ -377,12 +377,9 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         return GS_OK;
     };
     if ((rc = run_region(S, S->g_commit, gkey, graphs, commit_region))) return rc;
-    uint8_t ev_root[32];
-    GS_CUDA(c, cudaStreamSynchronize(c->stream));
-    memcpy(ev_root, c->mailbox, 32);
-    mark("Built evaluation merkle tree", false);
-
-    // 5 ---- composition polynomial: coefficients, boundary polynomials, fused evaluation
+    // 5 ---- composition polynomial: coefficients, boundary polynomials, fused evaluation.  Everything that does not
+    // depend on the evaluation root (degrees, interpolants, partial fractions, the E-periodic tables) is computed
+    // on the host while the commit chain is still running on the device; the root is awaited after that.
     int max_deg = 1;
     for (int d : S->degrees) if (d > max_deg) max_deg = d;
     int log_comp = 0; while ((1 << log_comp) < max_deg) ++log_comp;
@@ -409,22 +406,6 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     }
     const int nB = (int)b_regs.size();
     int b_count = nB; if (comp_degree > T) b_count *= 2;
-    const std::vector<u128> coeffs = prng_many(ev_root, 32, d_count + b_count);          // :58-60
-    // per-constraint coefficient pair and power slot
-    std::vector<fp> dk(K), dk_adj(K, fp_zero()); std::vector<int> pow_idx(K, -1);
-    std::vector<unsigned long long> pow_incr;
-    for (int k = 0; k < K; ++k) dk[k] = fp_from_u128(coeffs[k]);
-    {
-        int next = K;
-        for (size_t g = 0; g < group_deg.size(); ++g) {
-            if (group_deg[g] == comb_degree) continue;                                    // :89
-            const unsigned long long incr = (unsigned long long)(comb_degree - group_deg[g]);
-                        pow_incr.push_back(incr);
-            for (int k : group_idx[g]) { dk_adj[k] = fp_from_u128(coeffs[next++]); pow_idx[k] = (int)pow_incr.size() - 1; }
-        }
-    }
-    std::vector<fp> bk(nB), bk_adj(nB, fp_zero());
-    for (int b = 0; b < nB; ++b) { bk[b] = fp_from_u128(coeffs[d_count + b]); if (comp_degree > T) bk_adj[b] = fp_from_u128(coeffs[d_count + nB + b]); }
     // I(x) per asserted register, and the partial-fraction form of 1/Z_b(x) (see compose.cuh)
     std::vector<fp> ipoly; std::vector<u128> pf_coef; std::vector<int> pf_owner; std::vector<unsigned> pf_shift; std::vector<int> ioff(nB), ilen(nB), pfoff(nB), pflen(nB), breg(nB);
     {
@@ -448,13 +429,20 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             breg[b] = (int)b_regs[b];
         }
     }
-    // linear combination coefficients continue the same stream (LinearCombination.ts:58-59, Stark.ts:129)
+    // per-constraint power slot and the position of its second coefficient in the stream (:88-100)
+    std::vector<int> pow_idx(K, -1), adj_idx(K, -1);
+    std::vector<unsigned long long> pow_incr;
+    {
+        int next = K;
+        for (size_t g = 0; g < group_deg.size(); ++g) {
+            if (group_deg[g] == comb_degree) continue;                                    // :89
+            pow_incr.push_back((unsigned long long)(comb_degree - group_deg[g]));
+            for (int k : group_idx[g]) { adj_idx[k] = next++; pow_idx[k] = (int)pow_incr.size() - 1; }
+        }
+    }
     const int n_lc = (int)e_cols.size();
     const long long delta = comp_degree - T;
     const int lc_total = delta > 0 ? 2 * n_lc : n_lc;
-    const std::vector<u128> lc_all = prng_many(ev_root, 32, d_count + b_count + lc_total);
-    std::vector<fp> lk(n_lc), lk_adj(n_lc, fp_zero());
-    for (int j = 0; j < n_lc; ++j) { lk[j] = fp_from_u128(lc_all[d_count + b_count + j]); if (delta > 0) lk_adj[j] = fp_from_u128(lc_all[d_count + b_count + n_lc + j]); }
     // E-periodic factors: 1/(x^T - 1) (num_i = w^(i*T) - 1 depends on i mod E, ZeroPolynomial.ts:40-41; inv(0) = 0 at
     // i mod E == 0), x^incr per constraint group and x^delta (every increment is a multiple of T).  The random
     // coefficients are folded with them into E-entry tables here, once per proof (compose.cuh).
@@ -474,6 +462,21 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         const u128 base = h_pow(w_n, (u128)((unsigned long long)delta % (unsigned long long)N));
         u128 a = 1; for (long long j = 0; j < E; ++j) { delta_tab[j] = a; a = h_mul(a, base); }
     }
+    uint8_t ev_root[32];
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(ev_root, c->mailbox, 32);
+    mark("Built evaluation merkle tree", false);
+    // one draw covers the composition coefficients (:58-60) and the linear-combination coefficients, which continue
+    // the same stream (LinearCombination.ts:58-59, Stark.ts:129)
+    const std::vector<u128> lc_all = prng_many(ev_root, 32, d_count + b_count + lc_total);
+    const std::vector<u128>& coeffs = lc_all;
+    std::vector<fp> dk(K), dk_adj(K, fp_zero());
+    for (int k = 0; k < K; ++k) { dk[k] = fp_from_u128(coeffs[k]); if (adj_idx[k] >= 0) dk_adj[k] = fp_from_u128(coeffs[adj_idx[k]]); }
+    std::vector<fp> bk(nB), bk_adj(nB, fp_zero());
+    for (int b = 0; b < nB; ++b) { bk[b] = fp_from_u128(coeffs[d_count + b]); if (comp_degree > T) bk_adj[b] = fp_from_u128(coeffs[d_count + nB + b]); }
+    std::vector<fp> lk(n_lc), lk_adj(n_lc, fp_zero());
+    for (int j = 0; j < n_lc; ++j) { lk[j] = fp_from_u128(lc_all[d_count + b_count + j]); if (delta > 0) lk_adj[j] = fp_from_u128(lc_all[d_count + b_count + n_lc + j]); }
+
     std::vector<fp> cd_tab((size_t)K * E), pf_tab(pf_coef.size() * E), lk_tab((size_t)n_lc * E);
     for (int k = 0; k < K; ++k)
         for (long long j = 0; j < E; ++j) {
