@@ -230,6 +230,8 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(max(args.warmup, 3)):
         proof = st.prove_bytes(assertions, [], seed)
     proof_len = len(proof)
+    from genstark_b200.stark import trace_backend as _tb
+    trace_backend = _tb()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -335,6 +337,41 @@ def run_ours(args, rank, local_rank, world):
                 'share_of_step': grouped[dom] / (sum(prof_dev) / len(prof_dev)),
                 'note': '128-bit modular arithmetic on 32-bit integer pipes: every kernel here is issue-bound, not HBM-bound'}
 
+    # The roof that actually binds these kernels is integer issue, not HBM (profiles/): say so with numbers.
+    #  * blake2s kernels: 648 ALU-pipe instructions per compression (320 XOR + 320 rotate + address/feed-forward), the ALU
+    #    pipe retires one warp instruction every 2 cycles per SM sub-partition => compressions/s <= SMs*4*32*f / (2*648)
+    #  * modmul kernels: gs_debug_modmul_probe measures the chip's dependent-free modular-multiplication rate
+    sm_hz = (sampler.summary().get('sm_mhz') or 1965.0) * 1e6
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    comp_peak = sm_count * 4 * 32 * sm_hz / (2 * 648.0)
+    n_eval = steps * EXT
+    fri_rows, l_ = 0, n_eval
+    while True:
+        fri_rows += l_ // 4
+        if l_ <= 256:
+            break
+        l_ >>= 2
+    comp_hash_cols = n_eval + fri_rows
+    comp_merkle = (n_eval - 1) + fri_rows
+    issue_roofline = {
+        'hash_columns': {'unit': 'blake2s compressions/s', 'achieved': comp_hash_cols / (grouped.get('hash_columns', 0) * 1e-3) if grouped.get('hash_columns') else None,
+                         'peak': comp_peak, 'peak_how': 'ALU pipe: SMs*4*32 lanes*f / (2 cycles * 648 ALU instructions per compression)'},
+        'merkle_build': {'unit': 'blake2s compressions/s', 'achieved': comp_merkle / (grouped.get('merkle_build', 0) * 1e-3) if grouped.get('merkle_build') else None,
+                         'peak': comp_peak, 'peak_how': 'same ALU-pipe bound; the top levels of every tree are latency-bound'},
+    }
+    for v in issue_roofline.values():
+        v['frac'] = (v['achieved'] / v['peak']) if v['achieved'] else None
+    probe_ms = C.c_float()
+    if L.gs_debug_modmul_probe(ctx.handle, sm_count * 8, 2000, C.byref(probe_ms)) == 0 and probe_ms.value > 0:
+        modmul_peak = sm_count * 8 * 256 * 4 * 2000.0 / (probe_ms.value * 1e-3)
+        log_n = LOG_STEPS + (EXT.bit_length() - 1)
+        # K1 modular multiplications per element per pass ~ 5 (butterflies + local and inter-pass twiddles), 3 passes, last has no inter-pass twiddle
+        ntt_modmuls = (1 << log_n) * 13 + (1 << LOG_STEPS) * 13
+        issue_roofline['modmul_probe'] = {'unit': 'modmul/s', 'peak': modmul_peak, 'probe_ms': probe_ms.value}
+        if grouped.get('ntt'):
+            a = ntt_modmuls / (grouped['ntt'] * 1e-3)
+            issue_roofline['ntt'] = {'unit': 'modmul/s (multiplications only; +23 add/sub per element)', 'achieved': a, 'peak': modmul_peak, 'frac': a / modmul_peak}
+
     cpu = None
     if world == 1:
         try:
@@ -366,6 +403,8 @@ def run_ours(args, rank, local_rank, world):
                 'stages_ms': stage_times},
         'gpu_launches': int(launches_per_step),
         'roofline': roofline,
+        'issue_roofline': issue_roofline,
+        'backends': {'trace': trace_backend, 'constraints': st.compose_backend()},
         'cpu_baseline': cpu,
         'kernels_ms_per_step': {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
         'resident_wall_ms': wall_resident, 'profiled_leg_ms_per_step': sum(prof_dev) / len(prof_dev),

@@ -64,7 +64,7 @@ struct Stark : public AirHost {
     std::shared_ptr<ComposeJit> compose_jit;   // K2 specialised for this AIR's constraints (devjit.cuh); fn == null => interpreter
     Shard shard;                      // coset sharding over the ranks of the context (world == 1: everything local)
     DevBuf d_dig_loc, d_dig_all;      // commit boundary: local digests / all-gathered digests before the permutation
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     DevBuf d_epoch;                         // prove counter, copied behind each FRI root so the host can poll for it
     float last_device_ms = 0;         // CUDA-event time from the first enqueue to the last kernel of prove()
     double last_host_ms = 0;          // wall clock of the whole call
@@ -76,9 +76,25 @@ struct Stark : public AirHost {
         if (g_fri.exec) cudaGraphExecDestroy(g_fri.exec);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev2) cudaEventDestroy(ev2);
         d_epoch.release(); d_dig_loc.release(); d_dig_all.release();
     }
 };
+
+// Montgomery's trick with the reference's inv(0) = 0 (zeros are skipped)
+static inline std::vector<u128> h_batch_inverse(const std::vector<u128>& v) {
+    const size_t n = v.size();
+    std::vector<u128> pre(n), out(n, 0);
+    u128 acc = 1;
+    for (size_t i = 0; i < n; ++i) { pre[i] = acc; if (v[i] != 0) acc = h_mul(acc, v[i]); }
+    u128 inv = h_inv(acc);
+    for (size_t i = n; i > 0; --i) {
+        if (v[i - 1] == 0) continue;
+        out[i - 1] = h_mul(inv, pre[i - 1]);
+        inv = h_mul(inv, v[i - 1]);
+    }
+    return out;
+}
 
 // Lagrange interpolation on the host (BoundaryConstraints.ts:42, LowDegreeProver.ts:243), low -> high
 static inline std::vector<u128> h_interpolate(const std::vector<u128>& xs, const std::vector<u128>& ys) {
@@ -88,13 +104,18 @@ static inline std::vector<u128> h_interpolate(const std::vector<u128>& xs, const
         for (size_t k = i + 1; k > 0; --k) root[k] = h_sub(root[k - 1], h_mul(root[k], xs[i]));
         root[0] = h_sub(0, h_mul(root[0], xs[i]));
     }
-    std::vector<u128> out(n, 0), num(n);
+    // denominators first, inverted together (one field inversion for all n points; inv(0) = 0 kept per element)
+    std::vector<u128> out(n, 0), num(n), den(n, 0);
     for (size_t i = 0; i < n; ++i) {
         u128 acc = 0;
         for (size_t k = n; k > 0; --k) { acc = h_add(root[k], h_mul(acc, xs[i])); num[k - 1] = acc; }
-        u128 den = 0;
-        for (size_t k = n; k > 0; --k) den = h_add(h_mul(den, xs[i]), num[k - 1]);
-        const u128 f = h_mul(ys[i], h_inv(den));
+        for (size_t k = n; k > 0; --k) den[i] = h_add(h_mul(den[i], xs[i]), num[k - 1]);
+    }
+    const std::vector<u128> den_inv = h_batch_inverse(den);
+    for (size_t i = 0; i < n; ++i) {
+        u128 acc = 0;
+        for (size_t k = n; k > 0; --k) { acc = h_add(root[k], h_mul(acc, xs[i])); num[k - 1] = acc; }
+        const u128 f = h_mul(ys[i], den_inv[i]);
         for (size_t k = 0; k < n; ++k) out[k] = h_add(out[k], h_mul(num[k], f));
     }
     return out;
@@ -287,7 +308,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
 
     const double t_call = now_ms();
     const bool reuse_trace = (flags & 1) && S->trace_resident;
-    if (!S->ev0) { cudaEventCreate(&S->ev0); cudaEventCreate(&S->ev1); }
+    if (!S->ev0) { cudaEventCreate(&S->ev0); cudaEventCreate(&S->ev1); cudaEventCreate(&S->ev2); }
     // 1-2 ---- execution trace on the host (sequential in steps), checked against the assertions
     const size_t trace_bytes = (size_t)R * T * sizeof(fp);
     if (!reuse_trace) {
@@ -450,7 +471,8 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     {
         const u128 w_e = c->root_of_order(log_e);        // w^T
         u128 acc = 1;
-        for (long long j = 0; j < E; ++j) { inv_num[j] = h_inv(h_sub(acc, 1)); acc = h_mul(acc, w_e); }
+        for (long long j = 0; j < E; ++j) { inv_num[j] = h_sub(acc, 1); acc = h_mul(acc, w_e); }
+        inv_num = h_batch_inverse(inv_num);
     }
     std::vector<u128> pow_tab(pow_incr.size() * E), delta_tab(E, 1);
     for (size_t g = 0; g < pow_incr.size(); ++g) {
@@ -704,27 +726,6 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         }
     }
     const uint8_t* lc_root = layers[0].root;
-    // remainder (already on its way): verifyRemainder (:223-252)
-    std::vector<u128> remainder;
-    {
-        GS_CUDA(c, cudaEventSynchronize(S->ev1));
-        const int depth = n_layers - 1;
-        const long long L = layers[depth].len;
-        long long max_deg_p1 = comp_degree; for (int d = 0; d < depth; ++d) max_deg_p1 /= 4;
-        remainder.resize(L);
-        for (long long i = 0; i < L; ++i) remainder[i] = fp_to_u128(((const fp*)(mb + MB_REM))[i]);
-        const u128 rou = h_pow(w_n, (u128)1 << (2 * depth));
-        std::vector<long long> pos;
-        for (long long i = 0; i < L; ++i) if (i % E) pos.push_back(i);
-        if (max_deg_p1 > (long long)pos.size()) return c->fail(GS_E_STARK, "Low degree proof failed: remainder too short for degree %lld", max_deg_p1);
-        std::vector<u128> dom(L); { u128 a = 1; for (long long i = 0; i < L; ++i) { dom[i] = a; a = h_mul(a, rou); } }
-        std::vector<u128> xs(max_deg_p1), ys(max_deg_p1);
-        for (long long i = 0; i < max_deg_p1; ++i) { xs[i] = dom[pos[i]]; ys[i] = remainder[pos[i]]; }
-        const std::vector<u128> poly = h_interpolate(xs, ys);
-        for (size_t i = (size_t)max_deg_p1; i < pos.size(); ++i)
-            if (h_eval_poly(poly, dom[pos[i]]) != remainder[pos[i]])
-                return c->fail(GS_E_STARK, "Low degree proof failed: Remainder is not a valid degree %lld polynomial", max_deg_p1 - 1);
-    }
     if (timing) mark("Computed low-degree proof (layers)", false);
     {
         const size_t nch = g_addr.size();
@@ -740,10 +741,34 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllReduce: %s", nccl().GetErrorString(nr));
         }
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM + 4096, S->d_gather.p, nch * 16, cudaMemcpyDeviceToHost, c->stream));
+        cudaEventRecord(S->ev2, c->stream);
     }
-    cudaEventRecord(S->ev1, c->stream);
-    cudaEventSynchronize(S->ev1);
-    cudaEventElapsedTime(&S->last_device_ms, S->ev0, S->ev1);
+    // the remainder check runs on the host while the gather and its copy back are in flight
+    // verifyRemainder (:223-252)
+    std::vector<u128> remainder;
+    {
+        GS_CUDA(c, cudaEventSynchronize(S->ev1));      // end of the layer chain: the remainder is in the mailbox
+        const int depth = n_layers - 1;
+        const long long L = layers[depth].len;
+        long long max_deg_p1 = comp_degree; for (int d = 0; d < depth; ++d) max_deg_p1 /= 4;
+        remainder.resize(L);
+        for (long long i = 0; i < L; ++i) remainder[i] = fp_to_u128(((const fp*)(mb + MB_REM))[i]);
+        const u128 rou = h_pow(w_n, (u128)1 << (2 * depth));
+        std::vector<long long> pos;
+        for (long long i = 0; i < L; ++i) if (i % E) pos.push_back(i);
+        if (max_deg_p1 > (long long)pos.size()) { cudaStreamSynchronize(c->stream); return c->fail(GS_E_STARK, "Low degree proof failed: remainder too short for degree %lld", max_deg_p1); }
+        std::vector<u128> dom(L); { u128 a = 1; for (long long i = 0; i < L; ++i) { dom[i] = a; a = h_mul(a, rou); } }
+        std::vector<u128> xs(max_deg_p1), ys(max_deg_p1);
+        for (long long i = 0; i < max_deg_p1; ++i) { xs[i] = dom[pos[i]]; ys[i] = remainder[pos[i]]; }
+        const std::vector<u128> poly = h_interpolate(xs, ys);
+        for (size_t i = (size_t)max_deg_p1; i < pos.size(); ++i)
+            if (h_eval_poly(poly, dom[pos[i]]) != remainder[pos[i]]) {
+                cudaStreamSynchronize(c->stream);
+                return c->fail(GS_E_STARK, "Low degree proof failed: Remainder is not a valid degree %lld polynomial", max_deg_p1 - 1);
+            }
+    }
+    cudaEventSynchronize(S->ev2);
+    cudaEventElapsedTime(&S->last_device_ms, S->ev0, S->ev2);
     S->trace_resident = true;
     S->proves_done++;
     if (c->profiling) c->prof_collect();
