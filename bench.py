@@ -65,7 +65,7 @@ class ClockSampler(threading.Thread):
                 break
             line = line.strip()
             if line:
-                self.samples.append([x.strip() for x in line.split(',')])
+                self.samples.append([time.perf_counter()] + [x.strip() for x in line.split(',')])
 
     def stop(self):
         self.stop_flag = True
@@ -75,19 +75,25 @@ class ClockSampler(threading.Thread):
             pass
         self.join(timeout=2)
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """median SM clock and throttle reasons of the samples taken inside [t0, t1] (the timed region); nvidia-smi
+        needs about a second to start on an 8-GPU box, so the sampler is started before the warm-up"""
+        rows = [s for s in self.samples if t0 is None or t0 <= s[0] <= t1]
+        window = 'timed region'
+        if not rows:
+            rows, window = self.samples, 'whole run (no sample fell inside the timed region)'
         sm, mx, reasons = [], 0, set()
-        for s in self.samples:
+        for s in rows:
             try:
-                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+                sm.append(float(s[1])); mx = max(mx, float(s[2]))
             except Exception:
                 continue
-            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], s[3:7]):
+            for name, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], s[4:8]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         sm.sort()
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'samples': len(sm), 'window': window}
 
 
 def mimc_case(log_steps):
@@ -226,6 +232,9 @@ def run_ours(args, rank, local_rank, world):
     assertions = mimc_assertions(steps)
     seed = [3]
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
     # warm-up (also allocates every buffer)
     for _ in range(max(args.warmup, 3)):
         proof = st.prove_bytes(assertions, [], seed)
@@ -233,13 +242,11 @@ def run_ours(args, rank, local_rank, world):
     from genstark_b200.stark import trace_backend as _tb
     trace_backend = _tb()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-
     # ---- e2e leg: public API, host inputs -> host proof bytes
     barrier()
     launches0 = ctx.launch_count
     t0 = time.perf_counter()
+    t_region0 = t0
     e2e_dev = []
     for _ in range(args.steps):
         st.prove_bytes(assertions, [], seed)
@@ -269,7 +276,9 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     prof = json.loads(L.gs_ctx_profile_report(ctx.handle).decode())
     L.gs_ctx_profile(ctx.handle, 0)
+    t_region1 = time.perf_counter()
     sampler.stop()
+    clocks = sampler.summary(t_region0, t_region1)
 
     ms_step = sum(dev_ms) / len(dev_ms)
     if dist is not None:
@@ -322,13 +331,15 @@ def run_ours(args, rank, local_rank, world):
         grouped[key] = grouped.get(key, 0.0) + v
     dom = max(grouped, key=grouped.get)
     log_t, log_e = LOG_STEPS, EXT.bit_length() - 1
-    alg = algorithmic_bytes(dom, log_t, log_e, air.trace_register_count, air.secret_input_count, 1)
+    # sharded runs: kernel times are rank 0's, which holds 1/world of the evaluation domain
+    alg = algorithmic_bytes(dom, log_t, log_e, air.trace_register_count, air.secret_input_count, 1) // world
     achieved = alg / (grouped[dom] * 1e-3) / 1e9
     traffic = None
     summ = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
     if os.path.exists(summ):
         try:
             traffic = json.load(open(summ)).get(dom, {}).get('dram_bytes_per_step')
+            traffic = traffic // world if traffic else traffic
         except Exception:
             traffic = None
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
@@ -341,7 +352,7 @@ def run_ours(args, rank, local_rank, world):
     #  * blake2s kernels: 648 ALU-pipe instructions per compression (320 XOR + 320 rotate + address/feed-forward), the ALU
     #    pipe retires one warp instruction every 2 cycles per SM sub-partition => compressions/s <= SMs*4*32*f / (2*648)
     #  * modmul kernels: gs_debug_modmul_probe measures the chip's dependent-free modular-multiplication rate
-    sm_hz = (sampler.summary().get('sm_mhz') or 1965.0) * 1e6
+    sm_hz = (clocks.get('sm_mhz') or 1965.0) * 1e6
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     comp_peak = sm_count * 4 * 32 * sm_hz / (2 * 648.0)
     n_eval = steps * EXT
@@ -362,7 +373,9 @@ def run_ours(args, rank, local_rank, world):
     for v in issue_roofline.values():
         v['frac'] = (v['achieved'] / v['peak']) if v['achieved'] else None
     probe_ms = C.c_float()
-    if L.gs_debug_modmul_probe(ctx.handle, sm_count * 8, 2000, C.byref(probe_ms)) == 0 and probe_ms.value > 0:
+    if world > 1:
+        issue_roofline = None            # per-rank work counts differ per commit on the sharded path: N=1 only
+    elif L.gs_debug_modmul_probe(ctx.handle, sm_count * 8, 2000, C.byref(probe_ms)) == 0 and probe_ms.value > 0:
         modmul_peak = sm_count * 8 * 256 * 4 * 2000.0 / (probe_ms.value * 1e-3)
         log_n = LOG_STEPS + (EXT.bit_length() - 1)
         # K1 modular multiplications per element per pass ~ 5 (butterflies + local and inter-pass twiddles), 3 passes, last has no inter-pass twiddle
@@ -409,7 +422,7 @@ def run_ours(args, rank, local_rank, world):
         'kernels_ms_per_step': {k: round(v, 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1])},
         'resident_wall_ms': wall_resident, 'profiled_leg_ms_per_step': sum(prof_dev) / len(prof_dev),
         'ntt': ntt,
-        'clocks': sampler.summary(),
+        'clocks': clocks,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

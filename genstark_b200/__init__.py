@@ -3,6 +3,7 @@ from .air import AirModule, ProgramBuilder, StaticRegister, P128, P32  # noqa: F
 from . import airs  # noqa: F401
 
 
-def instantiate(air, options=None, logger=None):
+def instantiate(source, component='default', options=None, logger=None, context=None):
+    """index.ts:18-33: AirAssembly text / path of an .aa file / AirModule -> Stark"""
     from .stark import instantiate as _inst
-    return _inst(air, options, logger)
+    return _inst(source, component, options, logger, context)

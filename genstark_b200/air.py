@@ -161,7 +161,8 @@ class ProgramBuilder:
                 last[a] = i
         for k, node in self.outs.items():
             last[node.idx] = n + k
-        # dead values are dropped, live ones get slots from a free list
+        # dead values are dropped, live ones get slots from a free list; loads (no operands) are emitted right
+        # before their first use so that a front-end may create them eagerly without holding slots
         slot_of = [-1] * n
         free: List[int] = []
         n_slots = 0
@@ -170,27 +171,41 @@ class ProgramBuilder:
         for i in range(n):
             if last[i] >= 0:
                 release_at.setdefault(last[i], []).append(i)
+        leaf_ops = (OP_CONST, OP_CUR, OP_NEXT, OP_STATIC)
+
+        def take_slot():
+            nonlocal n_slots
+            if free:
+                return free.pop()
+            n_slots += 1
+            return n_slots - 1
+
+        def emit_leaf(v):
+            if slot_of[v] < 0:
+                slot_of[v] = take_slot()
+                instrs.append((self.ssa[v][0], slot_of[v], self.ssa[v][1], 0))
+
         for i, (op, a, b) in enumerate(self.ssa):
-            if last[i] < 0:
+            if last[i] < 0 or op in leaf_ops:
                 continue
             if op in (OP_ADD, OP_SUB, OP_MUL):
+                for v in (a, b):
+                    if self.ssa[v][0] in leaf_ops:
+                        emit_leaf(v)
                 ia, ib = slot_of[a], slot_of[b]
-            elif op in (OP_NEG, OP_INV):
-                ia, ib = slot_of[a], 0
-            elif op == OP_EXP:
-                ia, ib = slot_of[a], b
             else:
-                ia, ib = a, 0
+                if self.ssa[a][0] in leaf_ops:
+                    emit_leaf(a)
+                ia, ib = slot_of[a], (b if op == OP_EXP else 0)
             # operands whose last use is this instruction free their slot first (dst may alias)
             for v in release_at.get(i, []):
                 free.append(slot_of[v])
-            if free:
-                s = free.pop()
-            else:
-                s = n_slots
-                n_slots += 1
+            s = take_slot()
             slot_of[i] = s
             instrs.append((op, s, ia, ib))
+        for k in range(n_out):
+            if self.ssa[self.outs[k].idx][0] in leaf_ops:
+                emit_leaf(self.outs[k].idx)
         for k in range(n_out):
             instrs.append((OP_OUT, k, slot_of[self.outs[k].idx], 0))
         degs = [self.outs[k].degree for k in range(n_out)]

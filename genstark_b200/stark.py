@@ -333,6 +333,98 @@ def trace_backend() -> str:
     return (_native.lib().gs_trace_backend() or b'').decode()
 
 
-def instantiate(air: AirModule, options: Optional[dict] = None, logger=None) -> Stark:
-    """index.ts:18-33 with the schema already compiled to an AirModule."""
-    return Stark(air, options, logger)
+class ScriptStark:
+    """``Stark`` for an AirAssembly component whose trace length follows from the inputs (``for each`` nesting):
+    the reference builds a proving context per call (lib/Stark.ts:90); here one device instance is kept per
+    distinct input shape.  Same public surface as ``Stark``."""
+
+    def __init__(self, component, options: Optional[dict] = None, logger=None, context: Optional[Context] = None):
+        self.component, self.options, self.logger, self.context = component, dict(options or {}), logger, context
+        self._by_shape: Dict[tuple, Stark] = {}
+        self._proto: Optional[Stark] = None
+
+    def _stark_for_shapes(self, shapes) -> Stark:
+        key = tuple(tuple(s) for s in shapes)
+        st = self._by_shape.get(key)
+        if st is None:
+            air = self.component.module(shapes, self.options.get('extensionFactor'))
+            st = Stark(air, self.options, self.logger, context=self.context or (self._proto.context if self._proto else None))
+            self._by_shape[key] = st
+            self._proto = self._proto or st
+        return st
+
+    def _any(self) -> Stark:
+        if self._proto is None:
+            raise StarkError('no proof has been generated or parsed yet: the trace length follows from the inputs')
+        return self._proto
+
+    @property
+    def air(self):
+        return self._any().air
+
+    @property
+    def securityLevel(self) -> int:
+        return self._any().securityLevel
+
+    def prove_bytes(self, assertions, inputs=None, seed=None) -> bytes:
+        return self._stark_for_shapes(self.component.input_shapes(inputs or [])).prove_bytes(assertions, inputs, seed)
+
+    def prove(self, assertions, inputs=None, seed=None) -> dict:
+        st = self._stark_for_shapes(self.component.input_shapes(inputs or []))
+        return st.parse(st.prove_bytes(assertions, inputs, seed))
+
+    def generateExecutionTrace(self, inputs=None, seed=None):
+        return generate_execution_trace(self.component.module_for(inputs or [], self.options.get('extensionFactor')), inputs, seed)
+
+    def _shapes_of(self, proof) -> List[List[int]]:
+        if isinstance(proof, (bytes, bytearray)):
+            # iShapes close the wire format (Serializer.ts:66-76): walk back from the end is ambiguous, so parse with
+            # the shape-independent reader (leaf sizes do not depend on the trace length)
+            proof = _parse_with(self.component.trace_register_count, self.component.secret_input_count,
+                                max(8, (self.component.modulus.bit_length() + 7) // 8), 32, proof)
+        return [list(s) for s in proof['iShapes']]
+
+    def verify(self, assertions, proof, publicInputs=None) -> bool:
+        return self._stark_for_shapes(self._shapes_of(proof)).verify(assertions, proof, publicInputs)
+
+    def serialize(self, proof: dict) -> bytes:
+        return self._stark_for_shapes(proof['iShapes']).serialize(proof)
+
+    def parse(self, buf: bytes) -> dict:
+        return self._stark_for_shapes(self._shapes_of(buf)).parse(buf)
+
+    def sizeOf(self, proof: dict) -> int:
+        return self._stark_for_shapes(proof['iShapes']).sizeOf(proof)
+
+
+def _parse_with(registers: int, secrets: int, element_size: int, digest_size: int, buf: bytes) -> dict:
+    """Serializer.parse without an instance: only the register counts and sizes enter the wire format"""
+    class _Shim(Stark):
+        def __init__(self):                       # noqa: D401 - no device instance behind it
+            self.elementSize, self.digestSize = element_size, digest_size
+
+        def _leaf_sizes(self):
+            return (registers + secrets) * element_size, element_size * 4
+
+        def __del__(self):
+            pass
+    return Stark.parse(_Shim(), buf)
+
+
+def instantiate(source, component: str = 'default', options: Optional[dict] = None, logger=None, context: Optional[Context] = None):
+    """index.ts:18-33.  ``source``: an ``AirModule`` (already lowered), AirAssembly text (bytes / str) or the path of
+    an ``.aa`` file; ``component``: the export to prove.  For backward compatibility ``instantiate(air, options)``
+    with an ``AirModule`` accepts the options as second argument."""
+    if isinstance(source, AirModule):
+        if isinstance(component, dict) and options is None:
+            component, options = 'default', component
+        return Stark(source, options, logger, context=context)
+    from . import assembly
+    comp = assembly.compile(source).component(component)
+    if comp.modulus.bit_length() > 128 or comp.modulus != (2**128 - 9 * 2**32 + 1):
+        # the reference falls back to JS bigint arithmetic for such fields (README.md:118,224); there is no such
+        # fallback here: the device path is p128 only
+        raise StarkError(f'field modulus {comp.modulus} is not supported by the B200 backend (p128 only)')
+    if comp.input_count == 0:
+        return Stark(comp.module([], (options or {}).get('extensionFactor')), options, logger, context=context)
+    return ScriptStark(comp, options, logger, context=context)
