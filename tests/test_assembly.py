@@ -27,7 +27,8 @@ def test_sexpr_parser_handles_comments_and_nesting():
         assembly.parse_sexpr('(a))')
 
 
-def test_mimc_module_equals_the_hand_built_air():
+def test_mimc_module_equals_the_hand_built_air(monkeypatch):
+    monkeypatch.setenv('GS_TRACE_JIT', '0')       # interpreter: tests/test_trace_jit.py owns the compiled MiMC program
     steps = 256
     m = assembly.compile(MIMC_SOURCE.replace('STEPS', str(steps))).component('mimc').module([])
     h = airs.mimc128(steps)
