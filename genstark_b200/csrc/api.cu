@@ -57,6 +57,8 @@ void gs_ctx_destroy(gs_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->tw_lo); cudaFree(c->tw_hi); cudaFree(c->tw_small);
+    for (auto& kv : c->tw_tables) cudaFree(kv.second);
+    c->tw_tables.clear();
     if (c->scratch) cudaFree(c->scratch);
     if (c->counters) cudaFree(c->counters);
     if (c->mailbox) cudaFreeHost(c->mailbox);

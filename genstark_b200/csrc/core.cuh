@@ -24,6 +24,9 @@ struct Ctx {
     fp* tw_hi = nullptr;
     fp* tw_small = nullptr;     // w_1024^i
     u128 root_g = 0;
+    // full twiddle tables of the NTT passes, built on first use per shape (ntt_host.cuh)
+    std::map<unsigned long long, fp*> tw_tables;
+    size_t tw_table_bytes = 0;
     // scratch arena (grow on demand)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;

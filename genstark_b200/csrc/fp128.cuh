@@ -221,7 +221,8 @@ GS_D fp d_reduce256(const uint32_t (&r)[8]) {
     return out;
 }
 
-GS_D fp d_mul(const fp& a, const fp& b) {
+// 4x4 limb product, r = a * b (256 bits)
+GS_D void d_mul_wide(const fp& a, const fp& b, uint32_t (&r)[8]) {
     // even[k] = limb k, odd[k] = limb k+1
     uint32_t e0, e1, e2, e3, e4, e5, e6, e7;
     uint32_t o0, o1, o2, o3, o4, o5, o6;
@@ -259,7 +260,6 @@ GS_D fp d_mul(const fp& a, const fp& b) {
         "madc.lo.cc.u32 %2, %5, %6, %2;\n\t madc.hi.u32 %3, %5, %6, 0;"
         : "+r"(e4), "+r"(e5), "+r"(e6), "=r"(e7) : "r"(a1), "r"(a3), "r"(b3));
     // r = even + (odd << 32)
-    uint32_t r[8];
     r[0] = e0;
     asm("add.cc.u32 %0, %7, %14;\n\t"
         "addc.cc.u32 %1, %8, %15;\n\t"
@@ -271,6 +271,11 @@ GS_D fp d_mul(const fp& a, const fp& b) {
         : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
         : "r"(e1), "r"(e2), "r"(e3), "r"(e4), "r"(e5), "r"(e6), "r"(e7),
           "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(o4), "r"(o5), "r"(o6));
+}
+
+GS_D fp d_mul(const fp& a, const fp& b) {
+    uint32_t r[8];
+    d_mul_wide(a, b, r);
     return d_reduce256(r);
 }
 

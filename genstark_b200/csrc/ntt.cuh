@@ -49,6 +49,10 @@ struct NttPassParams {
     int log_ntot;                 // log2 of the full output length (incl. pruned digit)
     int has_scale;
     fp scale;                     // multiplied into every output of the final pass (n^-1 for inverse)
+    // optional full tables (ntt_host.cuh builds them once per context and shape; null = two-level lookup + 1 modmul)
+    const fp* tw_inter;           // [k][col] = w_nsub^(+-col*k), k < R, col < m      (column passes)
+    const fp* tw_coset;           // [j-1][pos] = w_ntot^(pos*j), j = 1..E-1, pos < T  (pruned LDE pass)
+    int log_t;                    // log2 T: row length of tw_coset
 };
 
 GS_DUAL_SOURCE(GS_FP_LDST_SRC,
@@ -170,8 +174,9 @@ __global__ void __launch_bounds__(256, MINB) ntt_pass_kernel(const NttPassParams
 #pragma unroll
             for (int a = 0; a < R1; ++a) {
                 const unsigned pos = ((unsigned)(a * R2 + r) << P.log_m) + col0 + c;
-                const unsigned e = (pos * (pre + (unsigned)P.coset_base)) << (P.log_g - P.coset_log_ntot);
-                x[a] = fp_mul(x[a], tw_lookup(P, e));
+                const unsigned j = pre + (unsigned)P.coset_base;
+                if (P.tw_coset) x[a] = fp_mul(x[a], ldg_fp(P.tw_coset + ((size_t)(j - 1) << P.log_t) + pos));
+                else x[a] = fp_mul(x[a], tw_lookup(P, (pos * j) << (P.log_g - P.coset_log_ntot)));
             }
         }
         dif_butterfly<LOG_R1>(x, s_tw, LOG_R);
@@ -189,8 +194,8 @@ __global__ void __launch_bounds__(256, MINB) ntt_pass_kernel(const NttPassParams
                 fp v = x[brev<LOG_R1>(k)];
                 if (!P.final_pass) {
                     if (k != 0) {
-                        const unsigned e = ((col0 + c) * (unsigned)k) << (P.log_g - P.log_nsub);
-                        v = fp_mul(v, tw_lookup(P, e));
+                        if (P.tw_inter) v = fp_mul(v, ldg_fp(P.tw_inter + ((size_t)k << P.log_m) + col0 + c));
+                        else v = fp_mul(v, tw_lookup(P, ((col0 + c) * (unsigned)k) << (P.log_g - P.log_nsub)));
                     }
                     st_fp(dst + dst_base + ((long long)k << P.log_m) + c, v);
                 } else {
@@ -217,8 +222,8 @@ __global__ void __launch_bounds__(256, MINB) ntt_pass_kernel(const NttPassParams
             const int k = k1 + R1 * k2;
             if (!P.final_pass) {
                 if (k != 0) {
-                    const unsigned e = ((col0 + c) * (unsigned)k) << (P.log_g - P.log_nsub);
-                    v = fp_mul(v, tw_lookup(P, e));
+                    if (P.tw_inter) v = fp_mul(v, ldg_fp(P.tw_inter + ((size_t)k << P.log_m) + col0 + c));
+                    else v = fp_mul(v, tw_lookup(P, ((col0 + c) * (unsigned)k) << (P.log_g - P.log_nsub)));
                 }
                 st_fp(dst + dst_base + ((long long)k << P.log_m) + c, v);
             } else {
@@ -227,6 +232,20 @@ __global__ void __launch_bounds__(256, MINB) ntt_pass_kernel(const NttPassParams
             }
         }
     }
+}
+
+// full twiddle tables (built once per context and shape from the two-level table)
+__global__ void tw_inter_table_kernel(NttPassParams P, int log_r, fp* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // k * m + col
+    if (i >= ((size_t)1 << P.log_nsub)) return;
+    const unsigned k = (unsigned)(i >> P.log_m), col = (unsigned)(i & (((size_t)1 << P.log_m) - 1));
+    st_fp(out + i, tw_lookup(P, (col * k) << (P.log_g - P.log_nsub)));
+}
+__global__ void tw_coset_table_kernel(NttPassParams P, int n_cosets_minus_1, fp* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;       // (j-1) * T + pos
+    if (i >= ((size_t)n_cosets_minus_1 << P.log_t)) return;
+    const unsigned j = (unsigned)(i >> P.log_t) + 1u, pos = (unsigned)(i & (((size_t)1 << P.log_t) - 1));
+    st_fp(out + i, tw_lookup(P, (pos * j) << (P.log_g - P.coset_log_ntot)));
 }
 
 }  // namespace gs

@@ -68,6 +68,41 @@ static inline int pass_log_r1(int log_r) {
     return t[log_r];
 }
 
+// Full twiddle tables.  The two-level root table costs one modular multiplication per looked-up power; with 180 GB of
+// HBM the powers a pass needs are simply stored: [k][col] for the inter-pass twiddles of a column pass (2^log_nsub
+// entries, shared by every prefix / coset, L2-resident up to 2^22) and [j][pos] for the coset factors of the pruned LDE
+// pass ((E-1)*T entries, streamed once per transform next to the coefficients).  GS_NTT_TABLES=0 keeps the lookups;
+// GS_NTT_TABLE_MB caps the memory spent (default 4096).  Never built under stream capture (first prove runs uncaptured).
+static inline bool ntt_tables_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GS_NTT_TABLES"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v != 0;
+}
+static inline size_t ntt_table_cap() {
+    static size_t v = 0;
+    if (!v) { const char* e = getenv("GS_NTT_TABLE_MB"); v = (size_t)(e ? atoll(e) : 4096) << 20; }
+    return v;
+}
+static inline const fp* ntt_table(Ctx* c, unsigned long long key, size_t entries, const NttPassParams& P, int kind, int arg) {
+    if (!ntt_tables_enabled()) return nullptr;
+    auto it = c->tw_tables.find(key);
+    if (it != c->tw_tables.end()) return it->second;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(c->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
+    const size_t bytes = entries * sizeof(fp);
+    if (c->tw_table_bytes + bytes > ntt_table_cap()) return nullptr;
+    fp* t = nullptr;
+    if (cudaMalloc(&t, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    const unsigned blocks = (unsigned)((entries + 255) / 256);
+    if (kind == 0) tw_inter_table_kernel<<<blocks, 256, 0, c->stream>>>(P, arg, t);
+    else tw_coset_table_kernel<<<blocks, 256, 0, c->stream>>>(P, arg, t);
+    if (cudaGetLastError() != cudaSuccess) { cudaFree(t); return nullptr; }
+    c->launches++;
+    c->tw_tables[key] = t;
+    c->tw_table_bytes += bytes;
+    return t;
+}
+
 // Transform `rows` vectors.
 //   log_t : log2 of the input length per row (the size of the DFTs actually computed)
 //   log_e : log2 of the pruned leading radix (0 = plain transform; >0 = evaluate on the domain of size
@@ -121,6 +156,12 @@ static inline int ntt_run(Ctx* c, const fp* src, long long src_stride, fp* dst, 
             P.log_m = log_m;
             P.log_nsub = lr + log_m;
             P.src_prefix_stride = (first && log_e_total > 0) ? 0 : (1ll << P.log_nsub);
+            P.log_t = log_t;
+            P.tw_inter = ntt_table(c, 0x1000000ull | ((unsigned long long)P.log_nsub << 16) | ((unsigned long long)lr << 8) | (inverse ? 1 : 0),
+                                   (size_t)1 << P.log_nsub, P, 0, lr);
+            if (P.coset_log_ntot > 0)
+                P.tw_coset = ntt_table(c, 0x2000000ull | ((unsigned long long)log_t << 16) | ((unsigned long long)log_e_total << 8),
+                                       (size_t)((1 << log_e_total) - 1) << log_t, P, 1, (1 << log_e_total) - 1);
             log_c = 12 - lr; if (log_c > log_m) log_c = log_m; if (log_c > 5) log_c = 5;
             grid = dim3(1u << (log_npre + log_m - log_c), rows);
         } else {
