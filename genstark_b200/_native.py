@@ -82,6 +82,20 @@ def lib() -> C.CDLL:
         'gs_stark_set_debug': (i32, [vp, i32]),
         'gs_stark_read_intermediate': (i32, [vp, i32, vp, C.c_size_t]),
         'gs_debug_modmul_probe': (i32, [vp, i32, i32, P(C.c_float)]),
+        'gs_field_prng': (i32, [cp, C.c_size_t, i32, C.c_char_p]),
+        'gs_poly_interpolate': (i32, [cp, cp, i32, C.c_char_p]),
+        'gs_poly_eval_at': (i32, [cp, i32, cp, C.c_char_p]),
+        'gs_poly_mul': (i32, [cp, i32, cp, i32, C.c_char_p]),
+        'gs_vec_combine': (i32, [vp, vp, vp, C.c_char_p]),
+        'gs_quartic_interpolate_batch': (i32, [vp, vp, vp, P(vp)]),
+        'gs_quartic_eval_batch': (i32, [vp, vp, vp, cp, P(vp)]),
+        'gs_mat_stack': (i32, [vp, P(vp), i32, P(vp)]),
+        'gs_mat_rows': (i32, [vp, vp, i64, i64, P(vp)]),
+        'gs_mat_transpose': (i32, [vp, vp, P(vp)]),
+        'gs_mat_reshape': (i32, [vp, i64, i64]),
+        'gs_mat_get': (i32, [vp, vp, i64, i64, C.c_char_p]),
+        'gs_hash_digest': (i32, [i32, cp, C.c_size_t, C.c_char_p]),
+        'gs_merkle_verify_batch': (i32, [i32, cp, P(C.c_uint32), i32, cp, C.c_size_t]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)

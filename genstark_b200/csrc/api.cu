@@ -670,4 +670,142 @@ int gs_stark_read_intermediate(gs_stark* s, int which, void* out, size_t out_byt
     return GS_OK;
 }
 
+// ---- rest of the FiniteField / Hash seam: the small-vector and reshaping methods ---------------------
+/* field.prng(seed) (count == 0: one element) / field.prng(seed, count)   (CompositionPolynomial.ts:58, LowDegreeProver.ts:132,194) */
+int gs_field_prng(const uint8_t* seed, size_t seed_len, int count, uint8_t* out16) {
+    if (!seed || !out16 || count < 0) return GS_E_ARG;
+    if (count == 0) { fp v = fp_from_u128(prng_one(seed, seed_len)); memcpy(out16, &v, 16); return GS_OK; }
+    const std::vector<u128> v = prng_many(seed, seed_len, count);
+    for (int i = 0; i < count; ++i) { fp f = fp_from_u128(v[i]); memcpy(out16 + 16 * (size_t)i, &f, 16); }
+    return GS_OK;
+}
+
+static u128 elem_in(const uint8_t* p) { fp f; memcpy(&f, p, 16); return fp_to_u128(f); }
+static std::vector<u128> elems_in(const uint8_t* p, int n) { std::vector<u128> v(n); for (int i = 0; i < n; ++i) v[i] = elem_in(p + 16 * (size_t)i); return v; }
+static void elems_out(const std::vector<u128>& v, uint8_t* p) { for (size_t i = 0; i < v.size(); ++i) { fp f = fp_from_u128(v[i]); memcpy(p + 16 * i, &f, 16); } }
+
+/* field.interpolate(xs, ys): Lagrange, coefficients low -> high (BoundaryConstraints.ts:42, LowDegreeProver.ts:243); host, n <= 4096 */
+int gs_poly_interpolate(const uint8_t* xs16, const uint8_t* ys16, int n, uint8_t* out16) {
+    if (!xs16 || !ys16 || !out16 || n < 1 || n > 4096) return GS_E_ARG;
+    elems_out(h_interpolate(elems_in(xs16, n), elems_in(ys16, n)), out16);
+    return GS_OK;
+}
+/* field.evalPolyAt(poly, x)   (BoundaryConstraints.ts:59-60, LowDegreeProver.ts:248) */
+int gs_poly_eval_at(const uint8_t* poly16, int n, const uint8_t x16[16], uint8_t out16[16]) {
+    if (!poly16 || !x16 || !out16 || n < 1) return GS_E_ARG;
+    fp f = fp_from_u128(h_eval_poly(elems_in(poly16, n), elem_in(x16)));
+    memcpy(out16, &f, 16);
+    return GS_OK;
+}
+/* field.mulPolys(a, b)   (BoundaryConstraints.ts:30); out: na + nb - 1 coefficients */
+int gs_poly_mul(const uint8_t* a16, int na, const uint8_t* b16, int nb, uint8_t* out16) {
+    if (!a16 || !b16 || !out16 || na < 1 || nb < 1 || (long long)na * nb > (1ll << 26)) return GS_E_ARG;
+    const std::vector<u128> a = elems_in(a16, na), b = elems_in(b16, nb);
+    std::vector<u128> o((size_t)na + nb - 1, 0);
+    for (int i = 0; i < na; ++i) for (int j = 0; j < nb; ++j) o[i + j] = h_add(o[i + j], h_mul(a[i], b[j]));
+    elems_out(o, out16);
+    return GS_OK;
+}
+
+/* field.combineVectors(a, b) = sum a[i]*b[i]   (CompositionPolynomial.ts:168,188; LinearCombination.ts:85) */
+int gs_vec_combine(gs_ctx* c, const gs_mat* a, const gs_mat* b, uint8_t out16[16]) {
+    if (!c || !a || !b || !out16) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    const long long n = a->rows * a->cols;
+    if (b->rows * b->cols != n) return c->fail(GS_E_ARG, "shape mismatch");
+    cudaSetDevice(c->device);
+    long long blocks = (n + 255) / 256; if (blocks > 1024) blocks = 1024;
+    int rc = c->ensure_scratch((size_t)blocks * sizeof(fp));
+    if (rc != GS_OK) return rc;
+    dot_partial_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(a->data, b->data, n, (fp*)c->scratch);
+    c->launches++;
+    GS_CUDA(c, cudaMemcpyAsync(c->mailbox, c->scratch, (size_t)blocks * sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    u128 acc = 0;
+    for (long long i = 0; i < blocks; ++i) acc = h_add(acc, elem_in((const uint8_t*)c->mailbox + 16 * i));
+    fp f = fp_from_u128(acc); memcpy(out16, &f, 16);
+    return GS_OK;
+}
+
+/* field.interpolateQuarticBatch(xSets, ySets): rows x 4 each -> rows x 4 coefficients   (LowDegreeProver.ts:137,191) */
+int gs_quartic_interpolate_batch(gs_ctx* c, const gs_mat* xs, const gs_mat* ys, gs_mat** polys) {
+    if (!c || !xs || !ys || !polys) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    if (xs->cols != 4 || ys->cols != 4 || xs->rows != ys->rows) return c->fail(GS_E_ARG, "two rows x 4 matrices expected");
+    cudaSetDevice(c->device);
+    int rc = gs_mat_alloc(c, xs->rows, 4, polys);
+    if (rc != GS_OK) return rc;
+    quartic_interpolate_kernel<<<(unsigned)((xs->rows + 127) / 128), 128, 0, c->stream>>>(xs->data, ys->data, xs->rows, (*polys)->data);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { gs_mat_free(*polys); *polys = nullptr; return c->cuda_fail(e, "quartic_interpolate_kernel"); }
+    return GS_OK;
+}
+/* field.evalQuarticBatch(polys, x): x = one element per row (xs, length rows) or one scalar (x16)   (LowDegreeProver.ts:140,195) */
+int gs_quartic_eval_batch(gs_ctx* c, const gs_mat* polys, const gs_mat* xs, const uint8_t* x16, gs_mat** out) {
+    if (!c || !polys || !out || (!xs && !x16)) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    if (polys->cols != 4 || (xs && xs->rows * xs->cols != polys->rows)) return c->fail(GS_E_ARG, "rows x 4 polynomials and one x per row expected");
+    cudaSetDevice(c->device);
+    int rc = gs_mat_alloc(c, 1, polys->rows, out);
+    if (rc != GS_OK) return rc;
+    fp x = fp_zero(); if (x16) memcpy(&x, x16, 16);
+    quartic_eval_kernel<<<(unsigned)((polys->rows + 255) / 256), 256, 0, c->stream>>>(polys->data, xs ? xs->data : nullptr, x, xs ? 1 : 0, polys->rows, (*out)->data);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { gs_mat_free(*out); *out = nullptr; return c->cuda_fail(e, "quartic_eval_kernel"); }
+    return GS_OK;
+}
+
+/* field.newMatrixFromVectors(vs) / vectorsToMatrix: stack equally long vectors (or matrices with equal column counts) as rows
+   (BoundaryConstraints.ts:84-85) */
+int gs_mat_stack(gs_ctx* c, const gs_mat* const* parts, int count, gs_mat** out) {
+    if (!c || !parts || !out || count < 1) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    long long rows = 0; const long long cols = parts[0] ? parts[0]->cols : 0;
+    for (int i = 0; i < count; ++i) { if (!parts[i] || parts[i]->cols != cols) return c->fail(GS_E_ARG, "parts must have equal column counts"); rows += parts[i]->rows; }
+    cudaSetDevice(c->device);
+    int rc = gs_mat_alloc(c, rows, cols, out);
+    if (rc != GS_OK) return rc;
+    long long r = 0;
+    for (int i = 0; i < count; ++i) {
+        GS_CUDA(c, cudaMemcpyAsync((*out)->data + r * cols, parts[i]->data, (size_t)parts[i]->rows * cols * sizeof(fp), cudaMemcpyDeviceToDevice, c->stream));
+        r += parts[i]->rows;
+    }
+    return GS_OK;
+}
+/* field.matrixRowsToVectors(m)[row0 .. row0+nrows): a copy of consecutive rows   (Stark.ts:114, BoundaryConstraints.ts:73) */
+int gs_mat_rows(gs_ctx* c, const gs_mat* m, int64_t row0, int64_t nrows, gs_mat** out) {
+    if (!c || !m || !out || row0 < 0 || nrows < 1 || row0 + nrows > m->rows) return c ? c->fail(GS_E_ARG, "row range out of bounds") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    int rc = gs_mat_alloc(c, nrows, m->cols, out);
+    if (rc != GS_OK) return rc;
+    GS_CUDA(c, cudaMemcpyAsync((*out)->data, m->data + row0 * m->cols, (size_t)nrows * m->cols * sizeof(fp), cudaMemcpyDeviceToDevice, c->stream));
+    return GS_OK;
+}
+/* field.transposeMatrix(m)   (LowDegreeProver.ts:181) */
+int gs_mat_transpose(gs_ctx* c, const gs_mat* m, gs_mat** out) {
+    if (!c || !m || !out) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    int rc = gs_mat_alloc(c, m->cols, m->rows, out);
+    if (rc != GS_OK) return rc;
+    dim3 grid((unsigned)((m->cols + 15) / 16), (unsigned)((m->rows + 15) / 16));
+    if (grid.y > 65535) { gs_mat_free(*out); *out = nullptr; return c->fail(GS_E_UNSUPPORTED, "more than 2^20 rows: transpose the other way round"); }
+    transpose_matrix_kernel<<<grid, 256, 0, c->stream>>>(m->data, m->rows, m->cols, (*out)->data);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { gs_mat_free(*out); *out = nullptr; return c->cuda_fail(e, "transpose_matrix_kernel"); }
+    return GS_OK;
+}
+/* field.joinMatrixRows(m) and its inverse: the same elements under another shape (row-major), no copy   (LowDegreeProver.ts:182) */
+int gs_mat_reshape(gs_mat* m, int64_t rows, int64_t cols) {
+    if (!m || rows < 1 || cols < 1 || rows * cols != m->rows * m->cols) return GS_E_ARG;
+    m->rows = rows; m->cols = cols;
+    return GS_OK;
+}
+/* Vector.getValue(i) / Matrix.getValue(row, col)   (Stark.ts:290,357; LowDegreeProver.ts:141-142) */
+int gs_mat_get(gs_ctx* c, const gs_mat* m, int64_t row, int64_t col, uint8_t out16[16]) {
+    if (!c || !m || !out16 || row < 0 || col < 0 || row >= m->rows || col >= m->cols) return c ? c->fail(GS_E_ARG, "index out of range") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    GS_CUDA(c, cudaMemcpyAsync(out16, m->data + row * m->cols + col, 16, cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return GS_OK;
+}
+
 }  // extern "C"

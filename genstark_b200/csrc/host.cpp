@@ -27,3 +27,37 @@ extern "C" int gs_stark_verify(const uint8_t* air_blob, size_t blob_len, int has
 
 /* which trace generator the last generate_trace of this thread used: "jit <hash>" or "interpreter (<reason>)" */
 extern "C" const char* gs_trace_backend(void) { return gs::trace_backend_status(); }
+
+/* hash.digest(buffer)   (lib/utils/index.ts:37) -- host */
+extern "C" int gs_hash_digest(int alg, const uint8_t* msg, size_t len, uint8_t out32[32]) {
+    if ((alg != 0 && alg != 1) || (!msg && len) || !out32) return GS_E_ARG;
+    using namespace gs;
+    HostHash H{alg};
+    const Digest d = H.digest(msg, len);
+    memcpy(out32, d.data(), 32);
+    return GS_OK;
+}
+/* MerkleTree.verifyBatch(root, indexes, proof, hash)   (Stark.ts:206; LowDegreeProver.ts:86,109,116) -- host.
+   proof blob = what gs_merkle_prove_batch writes: u32 n_values, u32 n_columns, u32 depth, values (32 B each),
+   then per column u32 length + nodes.  Returns 1 (valid), 0 (invalid) or a negative status. */
+extern "C" int gs_merkle_verify_batch(int alg, const uint8_t root32[32], const uint32_t* indexes, int count, const uint8_t* proof, size_t proof_len) {
+    if ((alg != 0 && alg != 1) || !root32 || !indexes || count < 1 || !proof || proof_len < 12) return GS_E_ARG;
+    using namespace gs;
+    uint32_t nv, nc, depth; memcpy(&nv, proof, 4); memcpy(&nc, proof + 4, 4); memcpy(&depth, proof + 8, 4);
+    if ((int)nv != count || depth > 32) return 0;
+    size_t off = 12;
+    if (proof_len < off + (size_t)nv * 32) return GS_E_ARG;
+    std::vector<Digest> values(nv);
+    for (uint32_t i = 0; i < nv; ++i) { memcpy(values[i].data(), proof + off, 32); off += 32; }
+    std::vector<std::vector<Digest>> nodes(nc);
+    for (uint32_t k = 0; k < nc; ++k) {
+        if (proof_len < off + 4) return GS_E_ARG;
+        uint32_t ln; memcpy(&ln, proof + off, 4); off += 4;
+        if (proof_len < off + (size_t)ln * 32) return GS_E_ARG;
+        nodes[k].resize(ln);
+        for (uint32_t j = 0; j < ln; ++j) { memcpy(nodes[k][j].data(), proof + off, 32); off += 32; }
+    }
+    Digest root; memcpy(root.data(), root32, 32);
+    HostHash H{alg};
+    return verify_batch(root, std::vector<uint32_t>(indexes, indexes + count), values, nodes, (int)depth, H) ? 1 : 0;
+}

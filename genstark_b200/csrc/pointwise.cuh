@@ -80,6 +80,87 @@ __global__ void transpose_vector_kernel(const fp* __restrict__ v, long long rows
     st_fp(out + t, ld_fp(v + (i + (long long)j * rows) * step));
 }
 
+// transposeMatrix(M): out[j][i] = M[i][j]   (LowDegreeProver.ts:181) -- tiled through shared memory, 16-byte elements
+__global__ void __launch_bounds__(256) transpose_matrix_kernel(const fp* __restrict__ in, long long rows, long long cols, fp* __restrict__ out) {
+    __shared__ uint4 tile[16][17];
+    const long long c0 = (long long)blockIdx.x * 16, r0 = (long long)blockIdx.y * 16;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    if (r0 + ty < rows && c0 + tx < cols) tile[ty][tx] = *reinterpret_cast<const uint4*>(in + (r0 + ty) * cols + c0 + tx);
+    __syncthreads();
+    if (c0 + ty < cols && r0 + tx < rows) *reinterpret_cast<uint4*>(out + (c0 + ty) * rows + r0 + tx) = tile[tx][ty];
+}
+
+// combineVectors(a, b) = sum_i a[i] * b[i]   (CompositionPolynomial.ts:168,188; LinearCombination.ts:85): per-block partial sums
+__global__ void __launch_bounds__(256) dot_partial_kernel(const fp* __restrict__ a, const fp* __restrict__ b, long long n, fp* __restrict__ partial) {
+    __shared__ fp red[256];
+    fp acc = fp_zero();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc = fp_add(acc, fp_mul(ld_fp(a + i), ld_fp(b + i)));
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) red[threadIdx.x] = fp_add(red[threadIdx.x], red[threadIdx.x + w]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_fp(partial + blockIdx.x, red[0]);
+}
+
+// interpolateQuarticBatch(xSets, ySets): per row the cubic through four points (LowDegreeProver.ts:137,191), Lagrange form with
+// the four denominators inverted together; a zero denominator (repeated x) inverts to 0 like everywhere else.
+// xs, ys, out: rows x 4, row-major.
+__global__ void __launch_bounds__(128) quartic_interpolate_kernel(const fp* __restrict__ xs, const fp* __restrict__ ys, long long rows, fp* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    fp x[4], y[4], den[4], pre[4], inv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { x[i] = ld_fp(xs + 4 * r + i); y[i] = ld_fp(ys + 4 * r + i); }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        fp d = fp_one();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j != i) d = fp_mul(d, fp_sub(x[i], x[j]));
+        den[i] = d;
+    }
+    fp acc = fp_one();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { pre[i] = acc; if (!fp_is_zero(den[i])) acc = fp_mul(acc, den[i]); }
+    fp ia = fp_inv(acc);
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+        if (fp_is_zero(den[i])) { inv[i] = fp_zero(); continue; }
+        inv[i] = fp_mul(ia, pre[i]);
+        ia = fp_mul(ia, den[i]);
+    }
+    // numerator of point i: prod_{j != i} (X - x_j) = X^3 - e1 X^2 + e2 X - e3 over the three other points
+    fp c0 = fp_zero(), c1 = fp_zero(), c2 = fp_zero(), c3 = fp_zero();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const fp a = x[(i + 1) & 3], b = x[(i + 2) & 3], c = x[(i + 3) & 3];
+        const fp ab = fp_mul(a, b);
+        const fp e1 = fp_add(fp_add(a, b), c);
+        const fp e2 = fp_add(ab, fp_mul(c, fp_add(a, b)));
+        const fp e3 = fp_mul(ab, c);
+        const fp f = fp_mul(y[i], inv[i]);
+        c3 = fp_add(c3, f);
+        c2 = fp_sub(c2, fp_mul(f, e1));
+        c1 = fp_add(c1, fp_mul(f, e2));
+        c0 = fp_sub(c0, fp_mul(f, e3));
+    }
+    st_fp(out + 4 * r + 0, c0); st_fp(out + 4 * r + 1, c1); st_fp(out + 4 * r + 2, c2); st_fp(out + 4 * r + 3, c3);
+}
+
+// evalQuarticBatch(polys, x): Horner per row; x is one value per row (xs_is_vector) or the same scalar for every row
+__global__ void __launch_bounds__(256) quartic_eval_kernel(const fp* __restrict__ polys, const fp* __restrict__ xs, fp x_scalar, int xs_is_vector,
+                                                           long long rows, fp* __restrict__ out) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const fp x = xs_is_vector ? ld_fp(xs + r) : x_scalar;
+    fp acc = ld_fp(polys + 4 * r + 3);
+#pragma unroll
+    for (int k = 2; k >= 0; --k) acc = fp_add(fp_mul(acc, x), ld_fp(polys + 4 * r + k));
+    st_fp(out + r, acc);
+}
+
 // dependent modmul chains: throughput probe used by bench.py to state the integer roofline
 __global__ void __launch_bounds__(256) modmul_probe_kernel(fp* out, int iters) {
     fp a, b, c2, d;

@@ -88,6 +88,28 @@ class Matrix:
             return vals
         return [vals[r * self.colCount:(r + 1) * self.colCount] for r in range(self.rowCount)]
 
+    def getValue(self, row: int, column: Optional[int] = None) -> int:
+        """Vector.getValue(i) / Matrix.getValue(row, column) (Stark.ts:290,357-358; LowDegreeProver.ts:141-142)"""
+        if column is None:
+            row, column = divmod(row, self.colCount) if self.rowCount > 1 else (0, row)
+        out = C.create_string_buffer(16)
+        self.ctx.check(self.ctx._lib.gs_mat_get(self.ctx.handle, self.handle, row, column, out))
+        return int.from_bytes(out.raw, 'little')
+
+    def copyValue(self, index: int, destination: bytearray, offset: int = 0) -> int:
+        """Vector.copyValue(index, destination, offset) -> bytes written (Stark.ts:290)"""
+        out = C.create_string_buffer(16)
+        r, c = divmod(index, self.colCount)
+        self.ctx.check(self.ctx._lib.gs_mat_get(self.ctx.handle, self.handle, r, c, out))
+        destination[offset:offset + 16] = out.raw
+        return 16
+
+    def rowsToBuffers(self, indexes: Optional[Sequence[int]] = None) -> List[bytes]:
+        """Matrix.rowsToBuffers(indexes): each selected row as colCount * 16 bytes (LowDegreeProver.ts:53,214-217)"""
+        raw, w = self.toBuffer(), self.colCount * 16
+        idx = range(self.rowCount) if indexes is None else indexes
+        return [raw[i * w:(i + 1) * w] for i in idx]
+
     def free(self):
         if self.handle:
             self.ctx._lib.gs_mat_free(self.handle)
@@ -101,6 +123,15 @@ class Matrix:
 
 
 Vector = Matrix
+
+
+def seed_bytes(seed) -> bytes:
+    """what the reference hashes for a seed: a Buffer as is; a bigint through ``Buffer.from(hex, 'hex')``, which drops a
+    trailing odd nibble (QueryIndexGenerator.ts:61-64 idiom)"""
+    if isinstance(seed, int):
+        h = format(seed, 'x')
+        return bytes.fromhex(h[: len(h) // 2 * 2])
+    return bytes(seed)
 
 
 def _enc(v: int) -> bytes:
@@ -216,6 +247,102 @@ class GpuField:
         self.ctx.check(self._lib.gs_fri_fold(self.ctx.handle, v.handle, domain_size.bit_length() - 1, depth, _enc(special_x % P128), C.byref(h)))
         return Matrix(self.ctx, h)
 
+    # randomness, small polynomials (host side of the library) ------------------------------------------
+    def prng(self, seed, length: Optional[int] = None):
+        """field.prng(seed) -> element; field.prng(seed, n) -> vector (CompositionPolynomial.ts:58; LowDegreeProver.ts:132)"""
+        sb = seed_bytes(seed)
+        n = 0 if length is None else int(length)
+        out = C.create_string_buffer(16 * max(n, 1))
+        rc = self._lib.gs_field_prng(sb, len(sb), n, out)
+        if rc != 0:
+            raise _native.NativeError(rc, 'prng')
+        vals = [int.from_bytes(out.raw[i:i + 16], 'little') for i in range(0, 16 * max(n, 1), 16)]
+        return vals[0] if length is None else self.newVectorFrom(vals)
+
+    @staticmethod
+    def _small(v) -> List[int]:
+        return v.toValues() if isinstance(v, Matrix) else [int(x) % P128 for x in v]
+
+    def interpolate(self, xs, ys) -> Matrix:
+        """Lagrange interpolation of a few points (BoundaryConstraints.ts:42; LowDegreeProver.ts:243)"""
+        x, y = self._small(xs), self._small(ys)
+        out = C.create_string_buffer(16 * len(x))
+        rc = self._lib.gs_poly_interpolate(b''.join(map(_enc, x)), b''.join(map(_enc, y)), len(x), out)
+        if rc != 0 or len(x) != len(y):
+            raise _native.NativeError(rc, 'interpolate: 1..4096 points, as many ys as xs')
+        return self._from_bytes(out.raw, 1, len(x))
+
+    def evalPolyAt(self, poly, x: int) -> int:
+        p = self._small(poly)
+        out = C.create_string_buffer(16)
+        rc = self._lib.gs_poly_eval_at(b''.join(map(_enc, p)), len(p), _enc(x % P128), out)
+        if rc != 0:
+            raise _native.NativeError(rc, 'evalPolyAt')
+        return int.from_bytes(out.raw, 'little')
+
+    def mulPolys(self, a, b) -> Matrix:
+        x, y = self._small(a), self._small(b)
+        out = C.create_string_buffer(16 * (len(x) + len(y) - 1))
+        rc = self._lib.gs_poly_mul(b''.join(map(_enc, x)), len(x), b''.join(map(_enc, y)), len(y), out)
+        if rc != 0:
+            raise _native.NativeError(rc, 'mulPolys')
+        return self._from_bytes(out.raw, 1, len(x) + len(y) - 1)
+
+    def combineVectors(self, a: Matrix, b: Matrix) -> int:
+        """sum a[i] * b[i] (CompositionPolynomial.ts:168,188; LinearCombination.ts:85)"""
+        out = C.create_string_buffer(16)
+        self.ctx.check(self._lib.gs_vec_combine(self.ctx.handle, a.handle, b.handle, out))
+        return int.from_bytes(out.raw, 'little')
+
+    def interpolateQuarticBatch(self, xSets: Matrix, ySets: Matrix) -> Matrix:
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_quartic_interpolate_batch(self.ctx.handle, xSets.handle, ySets.handle, C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    def evalQuarticBatch(self, polys: Matrix, x) -> Matrix:
+        h = C.c_void_p()
+        if isinstance(x, Matrix):
+            rc = self._lib.gs_quartic_eval_batch(self.ctx.handle, polys.handle, x.handle, None, C.byref(h))
+        else:
+            rc = self._lib.gs_quartic_eval_batch(self.ctx.handle, polys.handle, None, _enc(int(x) % P128), C.byref(h))
+        self.ctx.check(rc)
+        return Matrix(self.ctx, h)
+
+    # matrices <-> vectors ------------------------------------------------------------------------------
+    def newMatrixFromVectors(self, vectors: Sequence[Matrix]) -> Matrix:
+        arr = (C.c_void_p * len(vectors))(*[v.handle for v in vectors])
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_mat_stack(self.ctx.handle, arr, len(vectors), C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    vectorsToMatrix = newMatrixFromVectors
+
+    def matrixRowsToVectors(self, m: Matrix) -> List[Matrix]:
+        out = []
+        for r in range(m.rowCount):
+            h = C.c_void_p()
+            self.ctx.check(self._lib.gs_mat_rows(self.ctx.handle, m.handle, r, 1, C.byref(h)))
+            out.append(Matrix(self.ctx, h))
+        return out
+
+    def transposeMatrix(self, m: Matrix) -> Matrix:
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_mat_transpose(self.ctx.handle, m.handle, C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    def joinMatrixRows(self, m: Matrix) -> Matrix:
+        """row-major concatenation of the rows: a copy with shape 1 x (rows * cols) (LowDegreeProver.ts:182)"""
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_mat_rows(self.ctx.handle, m.handle, 0, m.rowCount, C.byref(h)))
+        if self._lib.gs_mat_reshape(h, 1, m.rowCount * m.colCount) != 0:
+            raise _native.NativeError(-1, 'reshape')
+        return Matrix(self.ctx, h)
+
+    def subMatrixElementsFromVectors(self, vectors, m: Matrix) -> Matrix:
+        """row r = vectors[r] - m[r] (BoundaryConstraints.ts:91); ``vectors`` may already be a matrix"""
+        v = vectors if isinstance(vectors, Matrix) else self.newMatrixFromVectors(vectors)
+        return self._binary(1, v, m)
+
     # polynomials over roots of unity (K1) ------------------------------------------------------------
     def interpolateRoots(self, domain, values: Matrix) -> Matrix:
         """lib/Stark.ts:106 -- ``domain`` is implied by the length (power series of getRootOfUnity)."""
@@ -266,6 +393,13 @@ class GpuHash:
         self.algorithm, self.alg, self.ctx = algorithm, self.ALGORITHMS.index(algorithm), ctx
         self._lib = ctx._lib
 
+    def digest(self, value: bytes) -> bytes:
+        """hash.digest(buffer) (lib/utils/index.ts:37) -- host"""
+        out = C.create_string_buffer(32)
+        if self._lib.gs_hash_digest(self.alg, bytes(value), len(value), out) != 0:
+            raise _native.NativeError(-1, 'digest')
+        return out.raw
+
     def mergeVectorRows(self, vectors: Sequence[Matrix]) -> Digests:
         arr = (C.c_void_p * len(vectors))(*[v.handle for v in vectors])
         h = C.c_void_p()
@@ -313,6 +447,26 @@ class MerkleTree:
             ln = int.from_bytes(raw[off:off + 4], 'little'); off += 4
             nodes.append([raw[off + 32 * j: off + 32 * j + 32] for j in range(ln)]); off += 32 * ln
         return values, nodes, depth
+
+    @staticmethod
+    def verifyBatch(root: bytes, indexes: Sequence[int], proof, hash: GpuHash) -> bool:
+        """MerkleTree.verifyBatch(root, indexes, proof, hash) (Stark.ts:206; LowDegreeProver.ts:86,109,116); ``proof`` is
+        (values, nodes, depth) as returned by proveBatch, or an object with those attributes"""
+        values, nodes, depth = proof if isinstance(proof, tuple) else (proof.values, proof.nodes, proof.depth)
+        blob = bytearray(len(values).to_bytes(4, 'little') + len(nodes).to_bytes(4, 'little') + int(depth).to_bytes(4, 'little'))
+        for v in values:
+            if len(v) != 32:
+                raise TypeError('leaf values must be 32-byte digests')
+            blob += v
+        for col in nodes:
+            blob += len(col).to_bytes(4, 'little')
+            for x in col:
+                blob += x
+        idx = (C.c_uint32 * len(indexes))(*indexes)
+        rc = hash._lib.gs_merkle_verify_batch(hash.alg, bytes(root), idx, len(indexes), bytes(blob), len(blob))
+        if rc < 0:
+            raise _native.NativeError(rc, 'malformed batch proof')
+        return rc == 1
 
     def __del__(self):
         try:

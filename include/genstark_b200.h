@@ -99,6 +99,33 @@ int gs_transpose_vector(gs_ctx* ctx, const gs_mat* v, int columns, int64_t step,
  * and rows = transposeVector(v, 4); v has length domain / 4^depth.   LowDegreeProver.ts:190-195 */
 int gs_fri_fold(gs_ctx* ctx, const gs_mat* v, int log2_domain, int depth, const uint8_t special_x16[16], gs_mat** column);
 
+/* ---- the rest of the FiniteField seam: small-vector, batch-cubic and reshaping methods ---------------------------
+ * field.prng(seed) (count = 0 -> one element) / field.prng(seed, count)   CompositionPolynomial.ts:58; LinearCombination.ts:58,82;
+ *                                                                         LowDegreeProver.ts:132,194   (host; seed = the bytes hashed) */
+int gs_field_prng(const uint8_t* seed, size_t seed_len, int count, uint8_t* out16);
+/* field.interpolate(xs, ys) -> n coefficients, low -> high (Lagrange)       BoundaryConstraints.ts:42; LowDegreeProver.ts:243   (host) */
+int gs_poly_interpolate(const uint8_t* xs16, const uint8_t* ys16, int n, uint8_t* out16);
+/* field.evalPolyAt(poly, x)                                               BoundaryConstraints.ts:59-60; LowDegreeProver.ts:248 (host) */
+int gs_poly_eval_at(const uint8_t* poly16, int n, const uint8_t x16[16], uint8_t out16[16]);
+/* field.mulPolys(a, b) -> na + nb - 1 coefficients                          BoundaryConstraints.ts:30                           (host) */
+int gs_poly_mul(const uint8_t* a16, int na, const uint8_t* b16, int nb, uint8_t* out16);
+/* field.combineVectors(a, b) = sum a[i] * b[i]                              CompositionPolynomial.ts:168,188; LinearCombination.ts:85 */
+int gs_vec_combine(gs_ctx* ctx, const gs_mat* a, const gs_mat* b, uint8_t out16[16]);
+/* field.interpolateQuarticBatch(xSets, ySets): rows x 4 each -> rows x 4     LowDegreeProver.ts:137,191 */
+int gs_quartic_interpolate_batch(gs_ctx* ctx, const gs_mat* xs, const gs_mat* ys, gs_mat** polys);
+/* field.evalQuarticBatch(polys, x): x one element per row (xs) or one scalar (xs = NULL, x16)   LowDegreeProver.ts:140,195 */
+int gs_quartic_eval_batch(gs_ctx* ctx, const gs_mat* polys, const gs_mat* xs, const uint8_t* x16, gs_mat** out);
+/* field.newMatrixFromVectors(vs): parts stacked as rows                     BoundaryConstraints.ts:84-85 */
+int gs_mat_stack(gs_ctx* ctx, const gs_mat* const* parts, int count, gs_mat** out);
+/* field.matrixRowsToVectors(m): a copy of rows [row0, row0 + nrows)          Stark.ts:114; BoundaryConstraints.ts:73; LinearCombination.ts:39 */
+int gs_mat_rows(gs_ctx* ctx, const gs_mat* m, int64_t row0, int64_t nrows, gs_mat** out);
+/* field.transposeMatrix(m)                                                LowDegreeProver.ts:181 */
+int gs_mat_transpose(gs_ctx* ctx, const gs_mat* m, gs_mat** out);
+/* field.joinMatrixRows(m): the same elements as one row (or any rows x cols with the same product), no copy   LowDegreeProver.ts:182 */
+int gs_mat_reshape(gs_mat* m, int64_t rows, int64_t cols);
+/* Vector.getValue(i) / Matrix.getValue(row, col)                           Stark.ts:290,357-358; LowDegreeProver.ts:141-142 */
+int gs_mat_get(gs_ctx* ctx, const gs_mat* m, int64_t row, int64_t col, uint8_t out16[16]);
+
 /* ---- Hash / MerkleTree (K5); alg 0 = sha256, 1 = blake2s256 --------------------------------------------
  * hash.mergeVectorRows(vectors): digest i = H(v0[i] || v1[i] || ...) over every row of every matrix   lib/Stark.ts:115
  * hash.digestValues(buffer, valueSize): one digest per row of a row-major matrix               LowDegreeProver.ts:45
@@ -115,6 +142,11 @@ int gs_merkle_root(gs_ctx* ctx, const gs_tree* tree, uint8_t out32[32]);
 int gs_merkle_prove_batch(gs_ctx* ctx, const gs_tree* tree, const uint32_t* indexes, int count, uint8_t* out,
                           size_t out_cap, size_t* out_len);
 void gs_tree_free(gs_tree* tree);
+/* hash.digest(buffer)                                                       lib/utils/index.ts:37   (host) */
+int gs_hash_digest(int alg, const uint8_t* msg, size_t len, uint8_t out32[32]);
+/* MerkleTree.verifyBatch(root, indexes, proof, hash): 1 valid, 0 invalid, < 0 malformed; proof = the blob of
+ * gs_merkle_prove_batch                                                     Stark.ts:206; LowDegreeProver.ts:86,109,116   (host) */
+int gs_merkle_verify_batch(int alg, const uint8_t root32[32], const uint32_t* indexes, int count, const uint8_t* proof, size_t proof_len);
 
 /* ---- fused prover: the body of Stark.prove in one crossing (lib/Stark.ts:81-163) -------------------
  * gs_stark_create  <->  new Stark(schema, component, options)            lib/Stark.ts:35-58

@@ -102,3 +102,84 @@ def test_big_tree_root_matches_host_hashlib():
     while len(level) > 1:
         level = [hashlib.blake2s(level[2 * i] + level[2 * i + 1], digest_size=32).digest() for i in range(len(level) // 2)]
     assert MerkleTree.create(d, h).root == level[0]
+
+
+def test_quartic_batch_interpolation_and_evaluation():
+    f = gpu_field()
+    rows = 3000
+    xs = [rand_elems(4, 1000 + i) for i in range(rows)]
+    ys = [rand_elems(4, 5000 + i) for i in range(rows)]
+    xs[7] = [5, 9, 5, 11]                       # repeated x: zero denominators invert to 0
+    xs[8] = [3, 3, 3, 3]
+    X, Y = f.newMatrixFrom(xs), f.newMatrixFrom(ys)
+    polys = f.interpolateQuarticBatch(X, Y)
+    assert (polys.rowCount, polys.colCount) == (rows, 4)
+    want = OF.interpolate_quartic_batch(xs, ys)
+    assert polys.toValues() == want
+    pts = rand_elems(rows, 77)
+    assert f.evalQuarticBatch(polys, f.newVectorFrom(pts)).toValues() == OF.eval_quartic_batch(want, pts)
+    assert f.evalQuarticBatch(polys, 123456789).toValues() == OF.eval_quartic_batch(want, 123456789)
+
+
+def test_unfused_fri_layer_equals_the_fused_fold():
+    """LowDegreeProver.ts:190-195 spelled with the reference's own sequence of calls vs gs_fri_fold"""
+    f = gpu_field()
+    n, depth = 2**14, 1
+    root = OF.get_root_of_unity(n)
+    domain = f.getPowerSeries(root, n)
+    L = n >> (2 * depth)
+    v = rand_elems(L, 31)
+    V = f.newVectorFrom(v)
+    x_sets = f.transposeVector(domain, 4, 4 ** depth)
+    y_sets = f.transposeVector(V, 4)
+    polys = f.interpolateQuarticBatch(x_sets, y_sets)
+    special = 0x1234567890abcdef1234567890abcdef % P128
+    column = f.evalQuarticBatch(polys, special)
+    assert column.toValues() == f.friFold(V, n, depth, special).toValues()
+
+
+def test_matrix_reshaping_methods_and_dot_product():
+    f = gpu_field()
+    rows = [rand_elems(300, 40 + i) for i in range(5)]
+    vs = [f.newVectorFrom(r) for r in rows]
+    M = f.newMatrixFromVectors(vs)
+    assert (M.rowCount, M.colCount) == (5, 300) and M.toValues() == rows
+    assert [v.toValues() for v in f.matrixRowsToVectors(M)] == rows
+    assert f.transposeMatrix(M).toValues() == OF.transpose_matrix(rows)
+    wide = [rand_elems(40, 90 + i) for i in range(33)]
+    assert f.transposeMatrix(f.newMatrixFrom(wide)).toValues() == OF.transpose_matrix(wide)
+    assert f.joinMatrixRows(M).toValues() == OF.join_matrix_rows(rows)
+    other = [rand_elems(300, 60 + i) for i in range(5)]
+    assert f.subMatrixElementsFromVectors(vs, f.newMatrixFrom(other)).toValues() == OF.sub_matrix_elements_from_vectors(rows, other)
+    den = [list(r) for r in other]
+    den[2][5] = 0
+    assert f.divMatrixElements(M, f.newMatrixFrom(den)).toValues() == OF.div_matrix_elements(rows, den)
+    a, b = rand_elems(100000, 1), rand_elems(100000, 2)
+    assert f.combineVectors(f.newVectorFrom(a), f.newVectorFrom(b)) == OF.combine_vectors(a, b)
+    assert f.combineVectors(f.newVectorFrom(a[:3]), f.newVectorFrom(b[:3])) == OF.combine_vectors(a[:3], b[:3])
+    assert M.getValue(3, 17) == rows[3][17] and vs[2].getValue(299) == rows[2][299]
+    buf = bytearray(40)
+    assert vs[1].copyValue(5, buf, 8) == 16 and int.from_bytes(buf[8:24], 'little') == rows[1][5]
+    assert M.rowsToBuffers([4, 0]) == [b''.join(x.to_bytes(16, 'little') for x in rows[4]), b''.join(x.to_bytes(16, 'little') for x in rows[0])]
+
+
+def test_prng_small_polys_digest_and_verify_batch_through_the_mirror():
+    f = gpu_field()
+    seed = bytes(range(32))
+    assert f.prng(seed) == OF.prng(seed) and f.prng(seed, 9).toValues() == OF.prng(seed, 9)
+    assert f.prng(42, 4).toValues() == OF.prng(42, 4)
+    xs, ys = rand_elems(6, 1), rand_elems(6, 2)
+    poly = f.interpolate(f.newVectorFrom(xs), f.newVectorFrom(ys))
+    assert poly.toValues() == OF.interpolate(xs, ys)
+    assert f.evalPolyAt(poly, xs[3]) == ys[3]
+    assert f.mulPolys(poly, [1, 2, 3]).toValues() == OF.mul_polys(OF.interpolate(xs, ys), [1, 2, 3])
+    h = GpuHash('blake2s256', f.ctx)
+    oh = OHash('blake2s256')
+    assert h.digest(b'abc') == oh.digest(b'abc')
+    v = rand_elems(4 * 256, 9)
+    d = h.digestValues(f.newMatrixFrom([v[4 * i:4 * i + 4] for i in range(256)]))
+    tree = MerkleTree.create(d, h)
+    idx = [9, 8, 200, 31]
+    proof = tree.proveBatch(idx)
+    assert MerkleTree.verifyBatch(tree.root, idx, proof, h)
+    assert not MerkleTree.verifyBatch(tree.root, [9, 8, 200, 30], proof, h)
