@@ -109,7 +109,9 @@ GS_D void dif_butterfly(fp (&x)[1 << S], const fp* tw, int log_r) {
     }
 }
 
-template <int LOG_R1, int LOG_R2, int MINB>
+// TAB: the pass reads its inter-pass (and coset) factors from the full tables; the other instantiation keeps the two-level
+// lookups and carries none of the table code (a run-time switch cost both paths registers: measured, profiles/)
+template <int LOG_R1, int LOG_R2, int MINB, bool TAB>
 __global__ void __launch_bounds__(256, MINB) ntt_pass_kernel(const NttPassParams P) {
     constexpr int R1 = 1 << LOG_R1, R2 = 1 << LOG_R2, LOG_R = LOG_R1 + LOG_R2, R = 1 << LOG_R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(256, MINB) ntt_pass_kernel(const NttPassParams
             for (int a = 0; a < R1; ++a) {
                 const unsigned pos = ((unsigned)(a * R2 + r) << P.log_m) + col0 + c;
                 const unsigned j = pre + (unsigned)P.coset_base;
-                if (P.tw_coset) x[a] = fp_mul(x[a], ldg_fp(P.tw_coset + ((size_t)(j - 1) << P.log_t) + pos));
+                if (TAB) x[a] = fp_mul(x[a], ldg_fp(P.tw_coset + ((size_t)(j - 1) << P.log_t) + pos));
                 else x[a] = fp_mul(x[a], tw_lookup(P, (pos * j) << (P.log_g - P.coset_log_ntot)));
             }
         }
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(256, MINB) ntt_pass_kernel(const NttPassParams
                 fp v = x[brev<LOG_R1>(k)];
                 if (!P.final_pass) {
                     if (k != 0) {
-                        if (P.tw_inter) v = fp_mul(v, ldg_fp(P.tw_inter + ((size_t)k << P.log_m) + col0 + c));
+                        if (TAB) v = fp_mul(v, ldg_fp(P.tw_inter + ((size_t)k << P.log_m) + col0 + c));
                         else v = fp_mul(v, tw_lookup(P, ((col0 + c) * (unsigned)k) << (P.log_g - P.log_nsub)));
                     }
                     st_fp(dst + dst_base + ((long long)k << P.log_m) + c, v);
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(256, MINB) ntt_pass_kernel(const NttPassParams
             const int k = k1 + R1 * k2;
             if (!P.final_pass) {
                 if (k != 0) {
-                    if (P.tw_inter) v = fp_mul(v, ldg_fp(P.tw_inter + ((size_t)k << P.log_m) + col0 + c));
+                    if (TAB) v = fp_mul(v, ldg_fp(P.tw_inter + ((size_t)k << P.log_m) + col0 + c));
                     else v = fp_mul(v, tw_lookup(P, ((col0 + c) * (unsigned)k) << (P.log_g - P.log_nsub)));
                 }
                 st_fp(dst + dst_base + ((long long)k << P.log_m) + c, v);

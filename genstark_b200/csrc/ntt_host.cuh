@@ -31,22 +31,25 @@ static inline int ntt_minb() {          // experiment knob: GS_NTT_MINB = 2 (def
     if (v < 0) { const char* e = getenv("GS_NTT_MINB"); v = e ? atoi(e) : 2; if (v < 2 || v > 4) v = 2; }
     return v;
 }
-template <int A, int B, int M>
+template <int A, int B, int M, bool TAB>
 static inline cudaError_t launch_pass_m(const NttPassParams& P, dim3 grid, int threads, size_t smem, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(ntt_pass_kernel<A, B, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(ntt_pass_kernel<A, B, M, TAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_set = true;
     }
-    ntt_pass_kernel<A, B, M><<<grid, threads, smem, s>>>(P);
+    ntt_pass_kernel<A, B, M, TAB><<<grid, threads, smem, s>>>(P);
     return cudaGetLastError();
 }
 template <int A, int B>
 static inline cudaError_t launch_pass_t(const NttPassParams& P, dim3 grid, int threads, size_t smem, cudaStream_t s) {
+    // table variant only when every factor the pass needs is stored (the final pass has none)
+    const bool tab = !P.final_pass && P.tw_inter != nullptr && (P.coset_log_ntot == 0 || P.tw_coset != nullptr);
+    if (tab) return launch_pass_m<A, B, 2, true>(P, grid, threads, smem, s);
     switch (ntt_minb()) {
-        case 3: return launch_pass_m<A, B, 3>(P, grid, threads, smem, s);
-        case 4: return launch_pass_m<A, B, 4>(P, grid, threads, smem, s);
-        default: return launch_pass_m<A, B, 2>(P, grid, threads, smem, s);
+        case 3: return launch_pass_m<A, B, 3, false>(P, grid, threads, smem, s);
+        case 4: return launch_pass_m<A, B, 4, false>(P, grid, threads, smem, s);
+        default: return launch_pass_m<A, B, 2, false>(P, grid, threads, smem, s);
     }
 }
 
@@ -157,9 +160,12 @@ static inline int ntt_run(Ctx* c, const fp* src, long long src_stride, fp* dst, 
             P.log_nsub = lr + log_m;
             P.src_prefix_stride = (first && log_e_total > 0) ? 0 : (1ll << P.log_nsub);
             P.log_t = log_t;
-            P.tw_inter = ntt_table(c, 0x1000000ull | ((unsigned long long)P.log_nsub << 16) | ((unsigned long long)lr << 8) | (inverse ? 1 : 0),
-                                   (size_t)1 << P.log_nsub, P, 0, lr);
-            if (P.coset_log_ntot > 0)
+            // inter-pass tables up to 2^21 entries (32 MiB) stay L2-resident; a 2^23-entry one streams from DRAM next to the data and
+            // measured slower than the lookups (forward 2^23: 0.69 vs 0.66 ms)
+            if (P.log_nsub <= 21)
+                P.tw_inter = ntt_table(c, 0x1000000ull | ((unsigned long long)P.log_nsub << 16) | ((unsigned long long)lr << 8) | (inverse ? 1 : 0),
+                                       (size_t)1 << P.log_nsub, P, 0, lr);
+            if (P.coset_log_ntot > 0 && P.tw_inter)
                 P.tw_coset = ntt_table(c, 0x2000000ull | ((unsigned long long)log_t << 16) | ((unsigned long long)log_e_total << 8),
                                        (size_t)((1 << log_e_total) - 1) << log_t, P, 1, (1 << log_e_total) - 1);
             log_c = 12 - lr; if (log_c > log_m) log_c = log_m; if (log_c > 5) log_c = 5;
