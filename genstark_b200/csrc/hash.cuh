@@ -79,51 +79,6 @@ GS_D void blake2s_compress(uint32_t (&h)[8], const uint32_t (&m)[16], uint32_t t
     h[4] ^= v4 ^ v12; h[5] ^= v5 ^ v13; h[6] ^= v6 ^ v14; h[7] ^= v7 ^ v15;
 }
 
-// One 64-byte node compression H(left || right) spread over FOUR lanes (lane j of an aligned group of four owns column j
-// of the 4x4 state: v[j], v[4+j], v[8+j], v[12+j]).  The column step is local; the diagonal step rotates rows 1..3 by
-// 1..3 lanes with width-4 shuffles and rotates them back.  A quarter of the ~1100 dependent instructions per lane:
-// used for the top levels of a tree, where a level is one compression deep and only latency counts.
-// m: the 16 message words in shared memory; returns digest words j (lo) and 4 + j (hi) on lane j.
-#define B2S_G_PLAIN(a, b, c, d, x, y)                                   \
-    a = a + b + (x); d = __byte_perm(d ^ a, 0, 0x1032);                  \
-    c = c + d; b = rotr32(b ^ c, 12);                                    \
-    a = a + b + (y); d = __byte_perm(d ^ a, 0, 0x0321);                  \
-    c = c + d; b = rotr32(b ^ c, 7);
-GS_D void blake2s_node_coop4(const uint32_t* m, int j, uint32_t& out_lo, uint32_t& out_hi) {
-    const unsigned full = 0xFFFFFFFFu;
-    const uint32_t iv_lo = j == 0 ? B2S_IV0 : j == 1 ? B2S_IV1 : j == 2 ? B2S_IV2 : B2S_IV3;
-    const uint32_t iv_hi = j == 0 ? B2S_IV4 : j == 1 ? B2S_IV5 : j == 2 ? B2S_IV6 : B2S_IV7;
-    const uint32_t h_lo = j == 0 ? (B2S_IV0 ^ 0x01010020u) : iv_lo, h_hi = iv_hi;
-    uint32_t a = h_lo, b = h_hi, c = iv_lo;
-    uint32_t d = j == 0 ? (B2S_IV4 ^ 64u) : j == 2 ? ~B2S_IV6 : iv_hi;      // t0 = 64 bytes, final block
-    // sigma rows as 16 nibbles, entry k in bits 4k..4k+3
-#define B2S_SIG(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15)                                          \
-    ((unsigned long long)(s0) | ((unsigned long long)(s1) << 4) | ((unsigned long long)(s2) << 8) | ((unsigned long long)(s3) << 12) |     \
-     ((unsigned long long)(s4) << 16) | ((unsigned long long)(s5) << 20) | ((unsigned long long)(s6) << 24) | ((unsigned long long)(s7) << 28) | \
-     ((unsigned long long)(s8) << 32) | ((unsigned long long)(s9) << 36) | ((unsigned long long)(s10) << 40) | ((unsigned long long)(s11) << 44) | \
-     ((unsigned long long)(s12) << 48) | ((unsigned long long)(s13) << 52) | ((unsigned long long)(s14) << 56) | ((unsigned long long)(s15) << 60))
-    const unsigned long long sigma[10] = {
-        B2S_SIG(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15), B2S_SIG(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3),
-        B2S_SIG(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4), B2S_SIG(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8),
-        B2S_SIG(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13), B2S_SIG(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9),
-        B2S_SIG(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11), B2S_SIG(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10),
-        B2S_SIG(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5), B2S_SIG(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0)};
-#undef B2S_SIG
-    const int sh = 8 * j;                                   // nibble 2j of the low / high half of a sigma row
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned lo = (unsigned)sigma[r] >> sh, hi = (unsigned)(sigma[r] >> 32) >> sh;
-        const uint32_t x0 = m[lo & 15u], y0 = m[(lo >> 4) & 15u], x1 = m[hi & 15u], y1 = m[(hi >> 4) & 15u];
-        B2S_G_PLAIN(a, b, c, d, x0, y0)
-        // diagonal step: lane j works on (v[j], v[4 + (j+1)%4], v[8 + (j+2)%4], v[12 + (j+3)%4])
-        b = __shfl_sync(full, b, (j + 1) & 3, 4); c = __shfl_sync(full, c, (j + 2) & 3, 4); d = __shfl_sync(full, d, (j + 3) & 3, 4);
-        B2S_G_PLAIN(a, b, c, d, x1, y1)
-        b = __shfl_sync(full, b, (j + 3) & 3, 4); c = __shfl_sync(full, c, (j + 2) & 3, 4); d = __shfl_sync(full, d, (j + 1) & 3, 4);
-    }
-    out_lo = h_lo ^ a ^ c;
-    out_hi = h_hi ^ b ^ d;
-}
-
 GS_D void blake2s_init(uint32_t (&h)[8]) {
     h[0] = B2S_IV0 ^ 0x01010020u; h[1] = B2S_IV1; h[2] = B2S_IV2; h[3] = B2S_IV3;
     h[4] = B2S_IV4; h[5] = B2S_IV5; h[6] = B2S_IV6; h[7] = B2S_IV7;
@@ -300,6 +255,9 @@ __global__ void __launch_bounds__(1024) merkle_subtree_kernel(uint32_t* __restri
     }
 }
 
+// (Tried and dropped, round 1: hashing one node on four lanes -- column / diagonal steps with width-4 shuffles -- for the
+// narrow levels.  merkle_build stayed at 0.708 ms: a level is bound by the ~240-deep dependency chain of one compression,
+// which four lanes do not shorten, not by the ~1100 instructions a single lane issues.)
 // Top of a tree in ONE launch: the level with `level_nodes` nodes (heap indices level_nodes .. 2*level_nodes) is cut into
 // 512-node subtrees, one per block, reduced in shared memory (every intermediate node is written out); the block that
 // finishes last then reduces the subtree roots to the root.  Replaces a launch per level where a level is a handful of
@@ -319,24 +277,6 @@ __global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ 
         __syncthreads();
         for (int l = log_n - 1; l >= 0; --l) {
             const int cnt = 1 << l;
-            if (ALG == HASH_BLAKE2S && 4 * cnt <= (int)blockDim.x) {
-                // narrow levels: four lanes per node (latency, not throughput, is what is left here)
-                const int node = threadIdx.x >> 2, lane4 = threadIdx.x & 3;
-                uint32_t dlo = 0, dhi = 0;
-                if ((int)((threadIdx.x & ~31u) >> 2) < cnt) {           // warp-uniform: this warp holds at least one live node
-                    const int nd = node < cnt ? node : cnt - 1;
-                    blake2s_node_coop4(reinterpret_cast<const uint32_t*>(s) + 16 * nd, lane4, dlo, dhi);
-                }
-                __syncthreads();
-                if (node < cnt) {
-                    uint32_t* sw = reinterpret_cast<uint32_t*>(s);
-                    sw[8 * node + lane4] = dlo; sw[8 * node + 4 + lane4] = dhi;
-                    uint32_t* g = nodes + 8 * (((long long)top << l) + node);
-                    g[lane4] = dlo; g[4 + lane4] = dhi;
-                }
-                __syncthreads();
-                continue;
-            }
             uint32_t d[8];
             const int j = threadIdx.x;
             if (j < cnt) {
