@@ -377,13 +377,23 @@ def run_ours(args, rank, local_rank, world):
         issue_roofline = None            # per-rank work counts differ per commit on the sharded path: N=1 only
     elif L.gs_debug_modmul_probe(ctx.handle, sm_count * 8, 2000, C.byref(probe_ms)) == 0 and probe_ms.value > 0:
         modmul_peak = sm_count * 8 * 256 * 4 * 2000.0 / (probe_ms.value * 1e-3)
-        log_n = LOG_STEPS + (EXT.bit_length() - 1)
-        # K1 modular multiplications per element per pass ~ 5 (butterflies + local and inter-pass twiddles), 3 passes, last has no inter-pass twiddle
-        ntt_modmuls = (1 << log_n) * 13 + (1 << LOG_STEPS) * 13
-        issue_roofline['modmul_probe'] = {'unit': 'modmul/s', 'peak': modmul_peak, 'probe_ms': probe_ms.value}
-        if grouped.get('ntt'):
-            a = ntt_modmuls / (grouped['ntt'] * 1e-3)
-            issue_roofline['ntt'] = {'unit': 'modmul/s (multiplications only; +23 add/sub per element)', 'achieved': a, 'peak': modmul_peak, 'frac': a / modmul_peak}
+        issue_roofline['modmul_probe'] = {'unit': 'modmul/s', 'peak': modmul_peak, 'probe_ms': probe_ms.value,
+                                          'how': 'gs_debug_modmul_probe: 8 CTAs x 256 threads per SM, 4 independent chains each'}
+        # K1 against the rate of its own instruction mix: a butterfly = modular add + modular sub + modular multiplication
+        # (gs_debug_butterfly_probe).  Butterflies of one prove: iNTT of T points + E coset transforms of T points, (n/2) log2 n each
+        # (the register-resident radix-8/16 stages skip the multiplications by 1, so this counts a few more multiplications than issued).
+        bf_ms = C.c_float()
+        if L.gs_debug_butterfly_probe(ctx.handle, sm_count * 8, 2000, C.byref(bf_ms)) == 0 and bf_ms.value > 0 and grouped.get('ntt'):
+            bf_peak = sm_count * 8 * 256 * 2 * 2000.0 / (bf_ms.value * 1e-3)
+            rows = air.trace_register_count + sum(1 for s_ in air.static_registers if s_.kind == 'input')
+            n_bf = rows * (1 + EXT) * (steps // 2) * LOG_STEPS
+            a = n_bf / (grouped['ntt'] * 1e-3)
+            issue_roofline['ntt'] = {'unit': 'butterflies/s', 'achieved': a, 'peak': bf_peak, 'frac': a / bf_peak, 'probe_ms': bf_ms.value,
+                                     'butterflies_per_prove': n_bf}
+        if ntt.get('lde_2^20_to_2^23') and bf_ms.value > 0:
+            bf_peak = sm_count * 8 * 256 * 2 * 2000.0 / (bf_ms.value * 1e-3)
+            a = (8 * (1 << 19) * 20) / (ntt['lde_2^20_to_2^23']['ms'] * 1e-3)
+            issue_roofline['lde_2^20_to_2^23'] = {'unit': 'butterflies/s', 'achieved': a, 'peak': bf_peak, 'frac': a / bf_peak}
 
     cpu = None
     if world == 1:

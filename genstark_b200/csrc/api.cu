@@ -427,16 +427,18 @@ int gs_merkle_prove_batch(gs_ctx* c, const gs_tree* t, const uint32_t* indexes, 
 }
 void gs_tree_free(gs_tree* t) { if (!t) return; cudaSetDevice(t->ctx->device); cudaFree(t->nodes); delete t; }
 
-int gs_debug_modmul_probe(gs_ctx* c, int blocks, int iters, float* ms_out) {
+static int run_probe(gs_ctx* c, int kind, int blocks, int iters, float* ms_out) {
     if (!c || !ms_out) return GS_E_ARG;
     cudaSetDevice(c->device);
     int rc = c->ensure_scratch(64);
     if (rc != GS_OK) return rc;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    modmul_probe_kernel<<<blocks, 256, 0, c->stream>>>((fp*)c->scratch, iters);    // warm-up
-    cudaEventRecord(e0, c->stream);
-    modmul_probe_kernel<<<blocks, 256, 0, c->stream>>>((fp*)c->scratch, iters);
+    for (int pass = 0; pass < 2; ++pass) {          // pass 0 = warm-up
+        if (pass == 1) cudaEventRecord(e0, c->stream);
+        if (kind == 0) modmul_probe_kernel<<<blocks, 256, 0, c->stream>>>((fp*)c->scratch, iters);
+        else butterfly_probe_kernel<<<blocks, 256, 0, c->stream>>>((fp*)c->scratch, iters);
+    }
     cudaEventRecord(e1, c->stream);
     GS_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(ms_out, e0, e1);
@@ -444,6 +446,10 @@ int gs_debug_modmul_probe(gs_ctx* c, int blocks, int iters, float* ms_out) {
     c->launches += 2;
     return GS_OK;
 }
+/* blocks x 256 threads x 4 independent chains x iters modular multiplications */
+int gs_debug_modmul_probe(gs_ctx* c, int blocks, int iters, float* ms_out) { return run_probe(c, 0, blocks, iters, ms_out); }
+/* blocks x 256 threads x 2 butterflies (u + v, (u - v) * w) x iters */
+int gs_debug_butterfly_probe(gs_ctx* c, int blocks, int iters, float* ms_out) { return run_probe(c, 1, blocks, iters, ms_out); }
 
 // ---- fused prover ------------------------------------------------------------------------------
 int gs_stark_create(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,

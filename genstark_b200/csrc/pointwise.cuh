@@ -174,4 +174,22 @@ __global__ void __launch_bounds__(256) modmul_probe_kernel(fp* out, int iters) {
     if (r.v[0] == 0xFFFFFFFFu && r.v[3] == 0x12345u) st_fp(out, r);   // keep the chains alive
 }
 
+// the NTT's instruction mix: (u, v) -> (u + v, (u - v) * w); 2 butterflies per thread per iteration (scripts/pipe_probe.cu)
+__global__ void __launch_bounds__(256) butterfly_probe_kernel(fp* out, int iters) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    fp x[4], w = fp_from_u64(0x94D049BB133111EBull * (t + 5));
+    for (int i = 0; i < 4; ++i) x[i] = fp_from_u64(0x9E3779B97F4A7C15ull * (t + 1 + i));
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const fp u = x[2 * k], v = x[2 * k + 1];
+            x[2 * k] = fp_add(u, v);
+            x[2 * k + 1] = fp_mul(fp_sub(u, v), w);
+        }
+        const fp tmp = x[1]; x[1] = x[2]; x[2] = tmp;
+    }
+    fp r = fp_add(fp_add(x[0], x[1]), fp_add(x[2], x[3]));
+    if (r.v[0] == 0xFFFFFFFFu && r.v[3] == 0x12345u) st_fp(out, r);
+}
+
 }  // namespace gs

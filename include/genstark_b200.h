@@ -206,6 +206,8 @@ int gs_timer_end(gs_ctx* ctx, float* ms);
 int gs_ntt_into(gs_ctx* ctx, const gs_mat* src, gs_mat* dst, gs_mat* work, int inverse);
 /* runs blocks x 256 threads x (4*iters) dependent modular multiplications; returns kernel ms */
 int gs_debug_modmul_probe(gs_ctx* ctx, int blocks, int iters, float* ms_out);
+/* same for the NTT's instruction mix: blocks x 256 threads x 2 butterflies (u + v, (u - v) * w) x iters */
+int gs_debug_butterfly_probe(gs_ctx* ctx, int blocks, int iters, float* ms_out);
 
 #ifdef __cplusplus
 }
