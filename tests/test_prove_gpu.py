@@ -69,7 +69,7 @@ def test_north_star_shape_proof_verifies_under_oracle_verifier():
     assert gpu.securityLevel == ora.security_level
 
 
-@pytest.mark.parametrize('log_steps,e', [(16, 8), (18, 16), (20, 8)])
+@pytest.mark.parametrize('log_steps,e', [(16, 8), (18, 16), (20, 8), (20, 16)])      # (20, 8) = north star, (20, 16) = config 4 on one GPU
 def test_large_proofs_match_c_oracle_port(log_steps, e):
     """BASELINE sizes: the GPU proof is byte-identical to the plain-C oracle port (itself pinned to the Python
     restatement by tests/test_cport.py), which runs the reference's unfused data flow on the host cores."""
