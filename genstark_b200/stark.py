@@ -193,33 +193,7 @@ class Stark:
 
     def parse(self, buf: bytes) -> dict:                            # Serializer.ts:83-144
         ev_leaf, ld_leaf = self._leaf_sizes()
-        es, ds = self.elementSize, self.digestSize
-        ev_root = bytes(buf[:ds])
-        ev_proof, off = _read_merkle_proof(buf, ds, ev_leaf, ds)
-        lc_root = bytes(buf[off:off + ds]); off += ds
-        lc_proof, off = _read_merkle_proof(buf, off, ld_leaf, ds)
-        count = buf[off]; off += 1
-        comps = []
-        for _ in range(count):
-            column_root = bytes(buf[off:off + ds]); off += ds
-            column_proof, off = _read_merkle_proof(buf, off, ld_leaf, ds)
-            poly_proof, off = _read_merkle_proof(buf, off, ld_leaf, ds)
-            comps.append({'columnRoot': column_root, 'columnProof': column_proof, 'polyProof': poly_proof})
-        rl = buf[off] or MAX_ARRAY_LENGTH; off += 1
-        remainder = []
-        for _ in range(rl):
-            remainder.append(int.from_bytes(buf[off:off + es], 'little')); off += es
-        n_inputs = buf[off]; off += 1
-        shapes = []
-        for _ in range(n_inputs):
-            rank = buf[off]; off += 1
-            shape = []
-            for _ in range(rank):
-                shape.append(struct.unpack_from('<I', buf, off)[0]); off += 4
-            shapes.append(shape)
-        return {'evRoot': ev_root, 'evProof': ev_proof,
-                'ldProof': {'lcRoot': lc_root, 'lcProof': lc_proof, 'components': comps, 'remainder': remainder},
-                'iShapes': shapes}
+        return parse_proof(buf, ev_leaf, ld_leaf, self.elementSize, self.digestSize)
 
     def sizeOf(self, proof: dict) -> int:                           # sizeof.ts:12-53
         es, ds = self.elementSize, self.digestSize
@@ -231,6 +205,37 @@ class Stark:
         size += len(ld['remainder']) * es + 1
         size += 1 + sum(1 + 4 * len(s) for s in proof['iShapes'])
         return size
+
+
+def parse_proof(buf: bytes, ev_leaf: int, ld_leaf: int, es: int, ds: int) -> dict:
+    """Serializer.parseProof (lib/Serializer.ts:83-144): only the leaf sizes, the element size and the digest size enter the
+    wire format -- not the trace length -- so a proof can be read before the instance for its input shapes exists"""
+    ev_root = bytes(buf[:ds])
+    ev_proof, off = _read_merkle_proof(buf, ds, ev_leaf, ds)
+    lc_root = bytes(buf[off:off + ds]); off += ds
+    lc_proof, off = _read_merkle_proof(buf, off, ld_leaf, ds)
+    count = buf[off]; off += 1
+    comps = []
+    for _ in range(count):
+        column_root = bytes(buf[off:off + ds]); off += ds
+        column_proof, off = _read_merkle_proof(buf, off, ld_leaf, ds)
+        poly_proof, off = _read_merkle_proof(buf, off, ld_leaf, ds)
+        comps.append({'columnRoot': column_root, 'columnProof': column_proof, 'polyProof': poly_proof})
+    rl = buf[off] or MAX_ARRAY_LENGTH; off += 1
+    remainder = []
+    for _ in range(rl):
+        remainder.append(int.from_bytes(buf[off:off + es], 'little')); off += es
+    n_inputs = buf[off]; off += 1
+    shapes = []
+    for _ in range(n_inputs):
+        rank = buf[off]; off += 1
+        shape = []
+        for _ in range(rank):
+            shape.append(struct.unpack_from('<I', buf, off)[0]); off += 4
+        shapes.append(shape)
+    return {'evRoot': ev_root, 'evProof': ev_proof,
+            'ldProof': {'lcRoot': lc_root, 'lcProof': lc_proof, 'components': comps, 'remainder': remainder},
+            'iShapes': shapes}
 
 
 def _size_of_merkle_proof(p: BatchMerkleProof) -> int:              # sizeof.ts:55-99
@@ -380,8 +385,8 @@ class ScriptStark:
         if isinstance(proof, (bytes, bytearray)):
             # iShapes close the wire format (Serializer.ts:66-76): walk back from the end is ambiguous, so parse with
             # the shape-independent reader (leaf sizes do not depend on the trace length)
-            proof = _parse_with(self.component.trace_register_count, self.component.secret_input_count,
-                                max(8, (self.component.modulus.bit_length() + 7) // 8), 32, proof)
+            es = max(8, (self.component.modulus.bit_length() + 7) // 8)
+            proof = parse_proof(proof, (self.component.trace_register_count + self.component.secret_input_count) * es, 4 * es, es, 32)
         return [list(s) for s in proof['iShapes']]
 
     def verify(self, assertions, proof, publicInputs=None) -> bool:
@@ -395,20 +400,6 @@ class ScriptStark:
 
     def sizeOf(self, proof: dict) -> int:
         return self._stark_for_shapes(proof['iShapes']).sizeOf(proof)
-
-
-def _parse_with(registers: int, secrets: int, element_size: int, digest_size: int, buf: bytes) -> dict:
-    """Serializer.parse without an instance: only the register counts and sizes enter the wire format"""
-    class _Shim(Stark):
-        def __init__(self):                       # noqa: D401 - no device instance behind it
-            self.elementSize, self.digestSize = element_size, digest_size
-
-        def _leaf_sizes(self):
-            return (registers + secrets) * element_size, element_size * 4
-
-        def __del__(self):
-            pass
-    return Stark.parse(_Shim(), buf)
 
 
 def instantiate(source, component: str = 'default', options: Optional[dict] = None, logger=None, context: Optional[Context] = None):

@@ -202,3 +202,20 @@ def test_lib128_merkle_root_component_matches_plain_merkle_tree():
     st = OracleStark(m, dict(hashAlgorithm='blake2s256', extensionFactor=16, exeQueryCount=12, friQueryCount=6))
     proof = st.parse(st.serialize(st.prove(a, inputs, [])))
     assert st.verify(a, proof, [[bits]])
+
+
+def test_proof_parser_needs_only_sizes_not_an_instance():
+    """ScriptStark reads iShapes out of serialized proofs before it knows the trace length (stark.py: parse_proof)"""
+    from genstark_b200.stark import parse_proof
+    from oracle import cport
+    comp = assembly.compile(SPONGE_SOURCE).component('sponge')
+    inputs = sponge_inputs(2, 4)
+    m = comp.module_for(inputs)
+    want = sponge_control(inputs, 2, 4)
+    T = m.trace_length
+    a = [dict(step=T - 1, register=0, value=want[0][T - 1])]
+    opts = dict(hashAlgorithm='sha256', extensionFactor=8, exeQueryCount=12, friQueryCount=6)
+    buf = cport.prove(m, opts, a, inputs, [])
+    proof = parse_proof(buf, (4 + 2) * 16, 64, 16, 32)
+    assert proof['iShapes'] == [[2], [2], [2, 4]] and proof['evRoot'] == buf[:32]
+    assert len(proof['ldProof']['remainder']) in (64, 128, 256)
