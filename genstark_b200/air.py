@@ -253,6 +253,9 @@ class AirModule:
     input_shapes: Callable = lambda inputs: []
     # public inputs (verify side) -> T-length traces of the public input registers, in register order
     expand_public_inputs: Callable = lambda public_inputs: []
+    # optional fast path of expand_inputs: inputs -> the same columns as one bytes object (16-byte little-endian elements,
+    # register after register); used on the prove path, where a Python list of T integers per register costs more than the proof
+    expand_inputs_blob: Optional[Callable] = None
 
     def __post_init__(self):
         if self.constraint_degrees is None:
@@ -288,6 +291,24 @@ class AirModule:
         m = copy.copy(self)
         m.extension_factor = int(extension_factor)
         return m
+
+
+def gather_column_blob(values: Sequence[int], index, modulus: int) -> bytes:
+    """column[t] = values[index[t]] as 16-byte little-endian elements; ``index`` is a numpy integer array"""
+    import numpy as np
+    table = np.frombuffer(b''.join((int(v) % modulus).to_bytes(16, 'little') for v in values), dtype=np.uint8).reshape(-1, 16)
+    return table[np.asarray(index)].tobytes()
+
+
+def input_blob(air: 'AirModule', inputs) -> Optional[bytes]:
+    """T-length columns of the input registers as the C ABI takes them (gs_stark_prove: input_traces)"""
+    if air.expand_inputs_blob is not None:
+        return air.expand_inputs_blob(inputs or []) or None
+    traces = air.expand_inputs(inputs or [])
+    if not traces:
+        return None
+    p = air.modulus
+    return b''.join((int(v) % p).to_bytes(16, 'little') for t in traces for v in t)
 
 
 AIR_BLOB_MAGIC = 0x52494147      # 'GAIR'

@@ -9,7 +9,7 @@ from __future__ import annotations
 import hashlib
 from typing import List, Sequence
 
-from .air import (AirModule, ProgramBuilder, StaticRegister, P128, P32, prng_sha256)
+from .air import (AirModule, ProgramBuilder, StaticRegister, P128, P32, gather_column_blob, prng_sha256)
 
 MIMC_SEED = bytes.fromhex('4d694d43')       # examples/mimc/mimc128.ts:15,36
 
@@ -307,6 +307,17 @@ def poseidon_merkle_proof(depth: int = 8, proofs: int = 1, extension_factor: int
             regs[4][s] = int(bits[pr][lv]) % p
         return regs
 
+    def expand_blob(inputs):
+        """same columns as expand(), gathered with numpy"""
+        import numpy as np
+        leaf0, leaf1, node0, node1, bits = inputs
+        nxt = (np.arange(steps, dtype=np.int64) + 1) % steps
+        pr, lv = nxt // period, (nxt % period) // cyc
+        flat = lambda m: [x for row in m for x in row]
+        return b''.join([gather_column_blob(leaf0, pr, p), gather_column_blob(leaf1, pr, p),
+                         gather_column_blob(flat(node0), pr * depth + lv, p), gather_column_blob(flat(node1), pr * depth + lv, p),
+                         gather_column_blob(flat(bits), pr * depth + lv, p)])
+
     def expand_public(public_inputs):
         (bits,) = public_inputs
         out = [0] * steps
@@ -323,7 +334,7 @@ def poseidon_merkle_proof(depth: int = 8, proofs: int = 1, extension_factor: int
     return AirModule(
         name='poseidon_mp', modulus=p, trace_register_count=12, trace_length=steps,
         transition=t.build(), evaluation=e.build(), static_registers=statics, extension_factor=extension_factor,
-        init=init, expand_inputs=expand, expand_public_inputs=expand_public,
+        init=init, expand_inputs=expand, expand_public_inputs=expand_public, expand_inputs_blob=expand_blob,
         input_shapes=lambda inputs: [[proofs], [proofs], [proofs, depth], [proofs, depth], [proofs, depth]])
 
 

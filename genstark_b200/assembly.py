@@ -41,7 +41,7 @@ import os
 import re
 from typing import Dict, List, Optional, Sequence
 
-from .air import AirModule, Program, ProgramBuilder, StaticRegister, prng_sha256, _Node
+from .air import AirModule, Program, ProgramBuilder, StaticRegister, gather_column_blob, prng_sha256, _Node
 
 
 class AssemblyError(Exception):
@@ -606,6 +606,24 @@ class AirComponent:
             if len(inputs or []) != len(regs): raise AssemblyError(f'{len(regs)} inputs expected')
             return traces_of(inputs, range(len(regs)))
 
+        index_cache = {}
+
+        def expand_blob(inputs):
+            """the columns of expand() as bytes, gathered with numpy (prove path)"""
+            import numpy as np
+            if len(inputs or []) != len(regs): raise AssemblyError(f'{len(regs)} inputs expected')
+            out = []
+            for k, vals in enumerate(inputs):
+                if _shape_of(vals, ranks[k]) != shapes[k]:
+                    raise AssemblyError(f'input {k} does not have the shape {shapes[k]} this instance was built for')
+                flat = [int(v) % p for v in _flatten(vals, ranks[k])]
+                if binary[k] and any(v not in (0, 1) for v in flat):
+                    raise AssemblyError(f'input {k} is declared binary')
+                if k not in index_cache:
+                    index_cache[k] = ((np.arange(T, dtype=np.int64) - shifts[k]) % T) // span[k]
+                out.append(gather_column_blob(flat, index_cache[k], p))
+            return b''.join(out)
+
         def expand_public(public_inputs):
             if len(public_inputs or []) != len(public): raise AssemblyError(f'{len(public)} public inputs expected')
             return traces_of(public_inputs, public)
@@ -632,7 +650,8 @@ class AirComponent:
         m = AirModule(name=ex.name, modulus=p, trace_register_count=ex.registers, trace_length=T,
                       transition=transition, evaluation=evaluation, static_registers=statics,
                       extension_factor=extension_factor, init=init, expand_inputs=expand,
-                      expand_public_inputs=expand_public, input_shapes=lambda inputs: [list(s) for s in shapes])
+                      expand_public_inputs=expand_public, input_shapes=lambda inputs: [list(s) for s in shapes],
+                      expand_inputs_blob=expand_blob if regs else None)
         self._modules[key] = m
         return m
 

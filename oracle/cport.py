@@ -58,8 +58,8 @@ def prove(air, options, assertions, inputs=None, seed=None, threads=None, stages
     a_blob = b''.join(struct.pack('<II', int(a['register']), int(a['step'])) + (int(a['value']) % p).to_bytes(16, 'little')
                       for a in assertions)
     init = b''.join((int(v) % p).to_bytes(16, 'little') for v in air.init(inputs or [], seed or []))
-    traces = air.expand_inputs(inputs or [])
-    in_blob = b''.join((int(v) % p).to_bytes(16, 'little') for t in traces for v in t) if traces else None
+    from genstark_b200.air import input_blob
+    in_blob = input_blob(air, inputs)
     shapes = air.input_shapes(inputs or [])
     s_blob = bytes([len(shapes)]) + b''.join(bytes([len(s)]) + b''.join(struct.pack('<I', x) for x in s) for s in shapes)
     out_p, out_n = C.POINTER(C.c_uint8)(), C.c_size_t()

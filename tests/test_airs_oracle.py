@@ -38,3 +38,18 @@ def test_oracle_roundtrip_and_c_port(case):
     bad = [dict(a[0], value=a[0]['value'] + 1)] + a[1:]
     with pytest.raises(Exception):
         ora.verify(bad, ora.parse(buf), inputs[4:] if air.name == 'poseidon_mp' else None)
+
+
+def test_numpy_input_expansion_equals_the_list_based_one():
+    """AirModule.expand_inputs_blob (prove path) produces byte for byte the columns of expand_inputs"""
+    from genstark_b200 import assembly
+    from genstark_b200.air import input_blob
+    from asm_sources import SPONGE_SOURCE, sponge_inputs
+    todo = [cases.poseidon(2, 1, e=16), cases.poseidon(4, 8), cases.rescue(4)]
+    inputs = sponge_inputs(4, 8)
+    todo.append((assembly.compile(SPONGE_SOURCE).component('sponge').module_for(inputs), None, None, inputs, []))
+    for air, _, _, inputs, _ in todo:
+        p = air.modulus
+        slow = b''.join((int(v) % p).to_bytes(16, 'little') for t in air.expand_inputs(inputs) for v in t)
+        assert input_blob(air, inputs) == slow
+        assert len(slow) == 16 * air.trace_length * sum(1 for s in air.static_registers if s.kind == 'input')
