@@ -29,7 +29,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # host-only code goes through the host compiler directly (better code for the sequential trace loop)
     host_obj = os.path.join(HERE, 'host.o')
     cxx = os.environ.get('CXX', 'g++')
-    hcmd = [cxx, '-O3', '-std=c++17', '-fPIC', '-c', os.path.join(CSRC, 'host.cpp'), '-o', host_obj]
+    hcmd = [cxx, '-O3', '-std=c++17', '-fPIC', '-pthread', '-c', os.path.join(CSRC, 'host.cpp'), '-o', host_obj]
     cmd = [nvcc, *NVCC_FLAGS, '-o', LIB] + [os.path.join(CSRC, s) for s in SOURCES] + [host_obj]
     if verbose:
         cmd.insert(1, '-Xptxas'); cmd.insert(2, '-v')

@@ -17,6 +17,8 @@
 #include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
+#include <vector>
 #include "hostair.h"
 #include "hostcrypto.h"
 #include "hostfield_fast.h"
@@ -28,7 +30,8 @@ struct JitArgs {
     const w128* const* stat;        // per static register: table of values (cycle values or a T-length input column)
     const u64_t* stat_mask;         // index = step & mask
     w128* trace;                    // R x T canonical residues
-    long long T, s0, s1;            // writes rows s0..s1-1; applies the transition after each of them except step T-1
+    long long T, s0, s1;            // visits rows s0..s1-1; applies the transition after each of them except step T-1
+    long long w0;                   // rows below w0 are visited but not written (warm-up step of a parallel chunk)
 };
 typedef void (*JitTraceFn)(const JitArgs*);
 
@@ -72,16 +75,18 @@ static inline std::string jit_emit_source(const HostProgram& pr, int R, int n_st
     }
     std::ostringstream o;
     o << "#include <x86intrin.h>\n" << GS_HOSTFIELD_SRC << "\n" << GS_HOSTFIELD_FAST_SRC << "\n";
-    o << "struct JitArgs { w128* state; const w128* const* stat; const u64_t* stat_mask; w128* trace; long long T, s0, s1; };\n";
+    o << "struct JitArgs { w128* state; const w128* const* stat; const u64_t* stat_mask; w128* trace; long long T, s0, s1, w0; };\n";
     o << "static const w128 k_zero = {0, 0};\n";
     for (size_t i = 0; i < pr.consts.size(); ++i)
         o << "static const w128 k" << i << " = {" << jit_hex_u64((u64_t)pr.consts[i]) << ", " << jit_hex_u64((u64_t)(pr.consts[i] >> 64)) << "};\n";
     o << "extern \"C\" void gs_trace_block(const JitArgs* a) {\n";
-    o << "  const long long T = a->T; w128* const tr = a->trace;\n";
+    o << "  const long long T = a->T, w0 = a->w0; w128* const tr = a->trace;\n";
     for (int r = 0; r < R; ++r) o << "  w128 s" << r << " = a->state[" << r << "];\n";
     for (int k = 0; k < n_static; ++k) o << "  const w128* const st" << k << " = a->stat[" << k << "]; const u64_t m" << k << " = a->stat_mask[" << k << "];\n";
     o << "  for (long long s = a->s0; s < a->s1; ++s) {\n";
-    for (int r = 0; r < R; ++r) o << "    tr[" << r << " * T + s] = w_from(w_canon(s" << r << "));\n";
+    o << "    if (__builtin_expect(s >= w0, 1)) {\n";
+    for (int r = 0; r < R; ++r) o << "      tr[" << r << " * T + s] = w_from(w_canon(s" << r << "));\n";
+    o << "    }\n";
     o << "    if (s + 1 == T) break;\n";
     std::vector<std::string> name(n);            // expression naming each definition's value
     std::vector<std::string> nxt(R);
@@ -214,7 +219,56 @@ void generate_trace(const AirHost* S, const u128* init_state, const fp* input_tr
             if (sr.kind == 0) { stat[k] = reinterpret_cast<const w128*>(sr.values.data()); mask[k] = sr.values.size() - 1; }
             else { stat[k] = reinterpret_cast<const w128*>(input_traces + (size_t)(ii++) * T); mask[k] = ~0ull; }
         }
-        JitArgs a{state.data(), stat.data(), mask.data(), reinterpret_cast<w128*>(tr), T, 0, 0};
+        JitArgs a{state.data(), stat.data(), mask.data(), reinterpret_cast<w128*>(tr), T, 0, 0, 0};
+        // Segments in parallel.  A step whose transition does not read the current state (the last step of a `for each`
+        // segment: every output is mask * f(inputs) + (1 - mask) * g(state) with mask = 1) cuts the chain: the rows behind it
+        // follow from the static registers alone.  Such steps sit at the end of power-of-two cycles, so step b - 1 is tried for
+        // every chunk boundary b (and a few steps after it); "does not read the state" is tested on the compiled function
+        // itself with two random states -- equal outputs mean a constant polynomial in the state except with probability
+        // ~2^-120.  No such step (MiMC: one chain) => the sequential loop below.  GS_TRACE_THREADS=1 turns this off.
+        int threads = (int)std::thread::hardware_concurrency(); if (threads > 16) threads = 16;
+        if (const char* e = getenv("GS_TRACE_THREADS")) threads = atoi(e);
+        std::vector<long long> cut;                     // cut[k]: first row of chunk k
+        if (threads >= 2 && T >= 4096 && R <= 64) {
+            int P = 1; while (2 * P <= threads && T / (2 * P) >= 1024) P *= 2;
+            const long long chunk = T / P;
+            auto state_free = [&](long long s) {        // transition at step s ignores the current state?
+                w128 sa[64], sb[64];
+                u64_t seed = 0x9E3779B97F4A7C15ull ^ (u64_t)s;
+                auto next = [&]() { seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17; return seed; };
+                for (int r = 0; r < R; ++r) { sa[r] = w128{next(), next() >> 1}; sb[r] = w128{next(), next() >> 1}; }
+                JitArgs t = a; t.s0 = s; t.s1 = s + 1; t.w0 = T;
+                t.state = sa; jit->fn(&t);
+                t.state = sb; jit->fn(&t);
+                for (int r = 0; r < R; ++r) if (sa[r].lo != sb[r].lo || sa[r].hi != sb[r].hi) return false;
+                return true;
+            };
+            cut.push_back(0);
+            for (int k = 1; k < P && !cut.empty(); ++k) {
+                long long found = -1;
+                for (long long s = k * chunk - 1; s < k * chunk - 1 + 64 && s + 1 < T; ++s) if (state_free(s)) { found = s + 1; break; }
+                if (found < 0 || found <= cut.back()) cut.clear(); else cut.push_back(found);
+            }
+        }
+        if (cut.size() >= 2) {
+            const int P = (int)cut.size();
+            std::vector<std::thread> pool;
+            std::vector<std::vector<w128>> st(P, std::vector<w128>(R, w128{0, 0}));
+            st[0] = state;
+            for (int k = 0; k < P; ++k) {
+                JitArgs ak = a;
+                ak.state = st[k].data();
+                ak.s0 = k == 0 ? 0 : cut[k] - 1;        // chunk k > 0 starts one step early: that step ignores the state
+                ak.w0 = cut[k];
+                ak.s1 = k + 1 < P ? cut[k + 1] : T;
+                if (k + 1 < P) pool.emplace_back([fn = jit->fn, ak]() { fn(&ak); });
+                else jit->fn(&ak);                         // the caller's thread takes the last chunk
+            }
+            for (auto& th : pool) th.join();
+            g_trace_backend = jit->status + " x" + std::to_string(P) + " threads";
+            if (on_chunk) for (long long s0 = 0; s0 < T; s0 += 0x10000) (*on_chunk)(s0, s0 + 0x10000 < T ? s0 + 0x10000 : T);
+            return;
+        }
         for (long long s0 = 0; s0 < T; s0 += 0x10000) {
             a.s0 = s0; a.s1 = s0 + 0x10000 < T ? s0 + 0x10000 : T;
             jit->fn(&a);

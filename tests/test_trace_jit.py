@@ -67,3 +67,33 @@ def test_jit_falls_back_to_the_interpreter_without_a_compiler(tmp_path, monkeypa
         want.append(x)
         x = (x * x + 0xB200_0001) % air.modulus
     assert got[0] == want
+
+
+@pytest.mark.parametrize('name', ['rescue', 'poseidon'])
+def test_segment_parallel_generation_equals_the_sequential_one(name, monkeypatch):
+    """AIRs whose segments restart from the inputs (`for each` loops) are generated chunk-parallel (hostjit.h); one chain
+    (MiMC) is not.  Same trace either way."""
+    import cases
+    big = {'rescue': lambda: cases.rescue(256), 'poseidon': lambda: cases.poseidon(4, 32)}[name]
+    air, opts, a, inputs, seed = big()
+    assert air.trace_length >= 4096
+    monkeypatch.setenv('GS_TRACE_THREADS', '1')
+    seq = gstark.generate_execution_trace(air, inputs, seed)
+    backend = gstark.trace_backend()
+    if not backend.startswith('jit'):
+        pytest.skip(f'no host compiler for the trace JIT: {backend}')
+    assert 'threads' not in backend
+    for x in a:
+        assert seq[x['register']][x['step']] == x['value']
+    for n in ('2', '4', '16'):
+        monkeypatch.setenv('GS_TRACE_THREADS', n)
+        par = gstark.generate_execution_trace(air, inputs, seed)
+        assert 'threads' in gstark.trace_backend(), gstark.trace_backend()
+        assert par == seq
+    # one dependent chain: no state-free step, so no chunks
+    monkeypatch.setenv('GS_TRACE_THREADS', '8')
+    m_air, _, _, m_in, m_seed = cases.mimc(8192, 8)
+    tr = gstark.generate_execution_trace(m_air, m_in, m_seed)
+    assert 'threads' not in gstark.trace_backend()
+    from genstark_b200 import airs
+    assert tr[0] == airs.run_mimc(8192, airs.mimc_round_constants(), 3)
