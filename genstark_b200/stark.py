@@ -354,18 +354,23 @@ class ScriptStark:
             self._proto = self._proto or st
         return st
 
-    def _any(self) -> Stark:
-        if self._proto is None:
-            raise StarkError('no proof has been generated or parsed yet: the trace length follows from the inputs')
-        return self._proto
+    def _unit_module(self) -> AirModule:
+        """the component with one value per input level: register counts, degrees and the extension factor do not depend
+        on the input shapes, only the trace length does"""
+        shapes = [[1] * r for r in self.component._rank]
+        return self.component.module(shapes, self.options.get('extensionFactor'))
 
     @property
     def air(self):
-        return self._any().air
+        return self._proto.air if self._proto is not None else self._unit_module()
 
     @property
-    def securityLevel(self) -> int:
-        return self._any().securityLevel
+    def securityLevel(self) -> int:                                # Stark.ts:62-77 (no device instance needed)
+        air = self.air
+        e = air.extension_factor
+        exe = self.options.get('exeQueryCount') or DEFAULT_EXE_QUERY_COUNT
+        fri = self.options.get('friQueryCount') or DEFAULT_FRI_QUERY_COUNT
+        return math.floor(min(_pow_log2(e / air.max_constraint_degree, int(exe)), math.log2(e) * int(fri), 32 * 4))
 
     def prove_bytes(self, assertions, inputs=None, seed=None) -> bytes:
         return self._stark_for_shapes(self.component.input_shapes(inputs or [])).prove_bytes(assertions, inputs, seed)

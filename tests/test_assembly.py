@@ -219,3 +219,12 @@ def test_proof_parser_needs_only_sizes_not_an_instance():
     proof = parse_proof(buf, (4 + 2) * 16, 64, 16, 32)
     assert proof['iShapes'] == [[2], [2], [2, 4]] and proof['evRoot'] == buf[:32]
     assert len(proof['ldProof']['remainder']) in (64, 128, 256)
+
+
+def test_script_stark_answers_shape_independent_questions_without_a_device():
+    from genstark_b200.stark import ScriptStark
+    comp = assembly.compile(SPONGE_SOURCE).component('sponge')
+    st = ScriptStark(comp, dict(hashAlgorithm='blake2s256', extensionFactor=16, exeQueryCount=48, friQueryCount=24))
+    assert st.air.trace_register_count == 4 and st.air.max_constraint_degree == 4 and st.air.extension_factor == 16
+    # Stark.ts:62-77: min(log2((E / d)^exe), log2(E) * fri, 128) = min(96, 96, 128)
+    assert st.securityLevel == 96
