@@ -209,6 +209,11 @@ static inline std::string stark_verify(const AirHost& A, int hash_alg, int exe_q
     std::vector<u128> remainder(rem_len);
     for (auto& v : remainder) { uint8_t b[16]; rd.bytes(b, 16); v = read_elem(b); }
     if (!rd.ok) return "Verification of low degree failed: malformed proof";
+    // input shapes close the proof (Serializer.ts:121-131): the instance was built for them already, but a proof cut short
+    // inside this section is still a malformed proof
+    const int n_shapes = rd.u8();
+    for (int i = 0; i < n_shapes && rd.ok; ++i) { const int rank = rd.u8(); for (int j = 0; j < rank && rd.ok; ++j) { uint8_t b[4]; rd.bytes(b, 4); } }
+    if (!rd.ok) return "Verification failed: malformed proof (input shapes)";
     // ---- context: composition / linear-combination parameters (CompositionPolynomial ctor :29-61)
     const u128 w = h_root_of_unity(log_n);
     int max_deg = 1; for (int d : A.degrees) if (d > max_deg) max_deg = d;

@@ -298,6 +298,19 @@ def verify_proof(air: AirModule, options: dict, assertions: Sequence[dict], proo
         raise TypeError(f'Hash algorithm {alg} is not supported')
     a_blob = b''.join(struct.pack('<II', int(a['register']), int(a['step'])) + (int(a['value']) % p).to_bytes(16, 'little')
                       for a in assertions)
+    # the proof carries the input shapes it was generated for (Serializer.ts:66-76); the reference builds its verification
+    # context from them (Stark.ts:177), here the instance already has a trace length, so they have to agree
+    es = max(8, (p.bit_length() + 7) // 8)
+    try:
+        claimed = parse_proof(bytes(proof_bytes), (air.trace_register_count + air.secret_input_count) * es, 4 * es, es, 32)['iShapes']
+    except (IndexError, struct.error):
+        raise StarkError('Verification failed: malformed proof')
+    try:
+        expected = [list(x) for x in air.input_shapes(None)]
+    except Exception:                       # an AIR whose shapes depend on the inputs: nothing to compare with
+        expected = None
+    if expected is not None and [list(x) for x in claimed] != expected:
+        raise StarkError(f'Verification failed: the proof was generated for input shapes {claimed}, this instance is built for {expected}')
     pub = air.expand_public_inputs(publicInputs or [])
     pub_blob = b''.join((int(v) % p).to_bytes(16, 'little') for t in pub for v in t) if pub else None
     blob = pack_air(air)

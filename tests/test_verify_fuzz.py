@@ -1,0 +1,69 @@
+"""The native verifier (gs_stark_verify, host C++) on damaged proofs: every mutation is rejected with a StarkError -- never
+accepted, never a crash.  A verifier reads attacker-controlled bytes; lengths and counts inside the wire format
+(lib/Serializer.ts:83-144) must not be trusted.  (Bytes after the end of the proof are ignored, as in the reference's parser, which never
+checks the final offset: lib/Serializer.ts:126-143.)"""
+import random
+
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import cases
+from genstark_b200.stark import StarkError, verify_proof
+from oracle.stark import Stark as OracleStark
+
+_cache = {}
+
+
+def _case(name):
+    if name not in _cache:
+        air, opts, a, inputs, seed = {'mimc': lambda: cases.mimc(256, 8), 'poseidon': lambda: cases.poseidon(2, 1, e=16)}[name]()
+        ora = OracleStark(air, opts)
+        buf = ora.serialize(ora.prove(a, inputs, seed))
+        pub = inputs[4:] if name == 'poseidon' else None
+        assert verify_proof(air, opts, a, buf, pub)
+        _cache[name] = (air, opts, a, buf, pub)
+    return _cache[name]
+
+
+@pytest.mark.parametrize('name', ['mimc', 'poseidon'])
+@settings(max_examples=300, deadline=None)
+@given(data=st.data())
+def test_mutated_proofs_are_rejected_without_crashing(name, data):
+    air, opts, a, buf, pub = _case(name)
+    kind = data.draw(st.sampled_from(['flip', 'truncate', 'byte', 'splice', 'zero_run']))
+    t = bytearray(buf)
+    if kind == 'flip':
+        pos = data.draw(st.integers(0, len(t) - 1)); t[pos] ^= 1 << data.draw(st.integers(0, 7))
+    elif kind == 'truncate':
+        t = t[:data.draw(st.integers(0, len(t) - 1))]
+    elif kind == 'byte':
+        pos = data.draw(st.integers(0, len(t) - 1)); old = t[pos]; t[pos] = data.draw(st.integers(0, 255).filter(lambda v: v != old))
+    elif kind == 'splice':
+        i = data.draw(st.integers(0, len(t) - 2)); j = data.draw(st.integers(i + 1, min(len(t), i + 200)))
+        k = data.draw(st.integers(0, len(t) - (j - i)))
+        if bytes(t[k:k + j - i]) == bytes(t[i:j]):
+            return
+        t[k:k + j - i] = t[i:j]
+    else:
+        i = data.draw(st.integers(0, len(t) - 1)); n = data.draw(st.integers(1, 40))
+        if not any(t[i:i + n]):
+            return
+        t[i:i + n] = bytes(len(t[i:i + n]))
+    if bytes(t) == buf:
+        return
+    with pytest.raises(StarkError):
+        verify_proof(air, opts, a, bytes(t), pub)
+
+
+def test_length_bytes_pointing_past_the_buffer():
+    """counts of 255 / 0 (= 256) in every count position near the start of each section"""
+    air, opts, a, buf, pub = _case('mimc')
+    r = random.Random(1)
+    for pos in [32, 33, 34] + [r.randrange(32, len(buf)) for _ in range(200)]:
+        for v in (0, 255, 254, 128):
+            t = bytearray(buf)
+            if t[pos] == v:
+                continue
+            t[pos] = v
+            with pytest.raises(StarkError):
+                verify_proof(air, opts, a, bytes(t), pub)
