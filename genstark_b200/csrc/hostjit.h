@@ -261,8 +261,10 @@ void generate_trace(const AirHost* S, const u128* init_state, const fp* input_tr
                 ak.s0 = k == 0 ? 0 : cut[k] - 1;        // chunk k > 0 starts one step early: that step ignores the state
                 ak.w0 = cut[k];
                 ak.s1 = k + 1 < P ? cut[k + 1] : T;
-                if (k + 1 < P) pool.emplace_back([fn = jit->fn, ak]() { fn(&ak); });
-                else jit->fn(&ak);                         // the caller's thread takes the last chunk
+                if (k + 1 < P) {
+                    try { pool.emplace_back([fn = jit->fn, ak]() { fn(&ak); }); }
+                    catch (...) { jit->fn(&ak); }           // no thread to be had: the chunk runs here (chunks are independent)
+                } else jit->fn(&ak);                       // the caller's thread takes the last chunk
             }
             for (auto& th : pool) th.join();
             g_trace_backend = jit->status + " x" + std::to_string(P) + " threads";
