@@ -39,6 +39,7 @@ struct Ctx {
     int rank = 0, world = 1;
     NcclComm comm = nullptr;
     unsigned long long launches = 0;   // kernels launched through this context (bench.py gpu_launches)
+    uint32_t prove_epoch = 0;          // one per prove ATTEMPT on this context (the mailbox handshake of prover.cuh)
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     // per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
     bool profiling = false;

@@ -18,6 +18,7 @@
 #include "core.cuh"
 #include "compose.cuh"
 #include "hostcrypto.h"
+#include "jitcache.h"
 
 namespace gs {
 
@@ -127,28 +128,21 @@ static inline std::string compose_emit_source(const AirHost& A) {
     return o.str();
 }
 
-static inline std::string devjit_cache_dir() {
-    if (const char* e = getenv("GS_JIT_CACHE")) return e;
-    std::string base;
-    if (const char* x = getenv("XDG_CACHE_HOME")) base = x;
-    else if (const char* h = getenv("HOME")) base = std::string(h) + "/.cache";
-    else base = "/tmp";
-    return base + "/genstark_b200";
-}
-
 // source -> cubin for sm_100a (disk cache keyed by the source hash); "" + *why on failure.  Needs no device.
 static inline std::string compose_compile_cubin(const std::string& src, std::string* key_out, std::string* why) {
     uint8_t dg[32]; sha256_bytes((const uint8_t*)src.data(), src.size(), dg);
     char hex[33]; for (int i = 0; i < 16; ++i) snprintf(hex + 2 * i, 3, "%02x", dg[i]);
     *key_out = hex;
-    const std::string dir = devjit_cache_dir();
-    { std::string curd; for (size_t i = 0; i <= dir.size(); ++i) { if (i == dir.size() || dir[i] == '/') { if (!curd.empty()) mkdir(curd.c_str(), 0700); } if (i < dir.size()) curd += dir[i]; } }
-    const std::string path = dir + "/compose_" + hex + "_sm100a.cubin";
-    if (FILE* f = fopen(path.c_str(), "rb")) {
-        std::string bin; char buf[65536]; size_t n;
-        while ((n = fread(buf, 1, sizeof buf, f)) > 0) bin.append(buf, n);
-        fclose(f);
-        if (!bin.empty()) return bin;
+    std::string dir_why;
+    const std::string dir = jit_cache_dir(&dir_why);          // "" => compile every time, nothing is cached
+    const std::string path = dir.empty() ? std::string() : dir + "/compose_" + hex + "_sm100a.cubin";
+    if (!path.empty() && jit_file_trusted(path)) {
+        if (FILE* f = fopen(path.c_str(), "rb")) {
+            std::string bin; char buf[65536]; size_t n;
+            while ((n = fread(buf, 1, sizeof buf, f)) > 0) bin.append(buf, n);
+            fclose(f);
+            if (!bin.empty()) return bin;
+        }
     }
     NvrtcApi& N = nvrtc_api();
     if (!N.load()) { *why = N.error; return ""; }
@@ -168,6 +162,7 @@ static inline std::string compose_compile_cubin(const std::string& src, std::str
     if (!sz || N.GetCUBIN(prog, &bin[0]) != 0) { *why = "nvrtcGetCUBIN failed"; N.DestroyProgram(&prog); return ""; }
     N.DestroyProgram(&prog);
     const std::string tmp = path + "." + std::to_string((long)getpid()) + ".tmp";
+    if (path.empty()) return bin;
     if (FILE* f = fopen(tmp.c_str(), "wb")) { fwrite(bin.data(), 1, bin.size(), f); fclose(f); if (rename(tmp.c_str(), path.c_str()) != 0) unlink(tmp.c_str()); }
     return bin;
 }

@@ -22,6 +22,7 @@
 #include "hostair.h"
 #include "hostcrypto.h"
 #include "hostfield_fast.h"
+#include "jitcache.h"
 
 namespace gs {
 
@@ -133,25 +134,6 @@ static inline std::string jit_emit_source(const HostProgram& pr, int R, int n_st
     return o.str();
 }
 
-static inline std::string jit_cache_dir() {
-    if (const char* e = getenv("GS_JIT_CACHE")) return e;
-    std::string base;
-    if (const char* x = getenv("XDG_CACHE_HOME")) base = x;
-    else if (const char* h = getenv("HOME")) base = std::string(h) + "/.cache";
-    else base = "/tmp";
-    return base + "/genstark_b200";
-}
-
-static inline bool jit_mkdirs(const std::string& dir) {
-    std::string cur;
-    for (size_t i = 0; i <= dir.size(); ++i) {
-        if (i == dir.size() || dir[i] == '/') { if (!cur.empty()) mkdir(cur.c_str(), 0700); }
-        if (i < dir.size()) cur += dir[i];
-    }
-    struct stat st;
-    return stat(dir.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
-}
-
 // compile (or reuse) the block function of a transition program; never throws, never fails the prove
 std::shared_ptr<TraceJit> jit_get(const HostProgram& pr, int R, int n_static);
 #ifdef GS_HOSTAIR_IMPL
@@ -162,28 +144,37 @@ std::shared_ptr<TraceJit> jit_get(const HostProgram& pr, int R, int n_static) {
     if (const char* e = getenv("GS_TRACE_JIT")) if (e[0] == '0') return interp("GS_TRACE_JIT=0");
     const std::string src = jit_emit_source(pr, R, n_static);
     if (src.empty()) return interp("program not supported by the code generator");
-    uint8_t dg[32]; sha256_bytes((const uint8_t*)src.data(), src.size(), dg);
+    const char* cxx = getenv("GS_JIT_CXX"); if (!cxx) cxx = getenv("CXX"); if (!cxx) cxx = "g++";
+    // -march=native: the code runs on the machine that compiles it (mulx / adx shorten the carry chains); compiler, flags
+    // and CPU model are part of the key, so a cache on a shared home never serves another machine's object
+    const std::vector<std::string> flags = {"-O3", "-march=native", "-std=c++17", "-fPIC", "-shared"};
+    std::string keyed = src + "\n//cxx " + cxx;
+    for (const std::string& f : flags) keyed += " " + f;
+    keyed += "\n//cpu " + jit_cpu_tag();
+    uint8_t dg[32]; sha256_bytes((const uint8_t*)keyed.data(), keyed.size(), dg);
     char hex[33]; for (int i = 0; i < 16; ++i) snprintf(hex + 2 * i, 3, "%02x", dg[i]);
     const std::string key(hex);
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     auto done = [&](std::shared_ptr<TraceJit> j) { cache[key] = j; return j; };
-    const std::string dir = jit_cache_dir();
-    if (!jit_mkdirs(dir)) return done(interp("cannot create " + dir));
+    std::string why;
+    const std::string dir = jit_cache_dir(&why);
+    if (dir.empty()) return done(interp(why));
     const std::string so = dir + "/trace_" + key + ".so";
     struct stat st;
-    if (stat(so.c_str(), &st) != 0) {
+    if (lstat(so.c_str(), &st) == 0 && !jit_file_trusted(so)) return done(interp(so + " exists but is not a private regular file of this user"));
+    if (!jit_file_trusted(so)) {
         const std::string tag = dir + "/trace_" + key + "." + std::to_string((long)getpid());
         const std::string cpp = tag + ".cpp", tmp = tag + ".so.tmp", log = tag + ".log";
         FILE* f = fopen(cpp.c_str(), "w");
         if (!f) return done(interp("cannot write " + cpp));
         fwrite(src.data(), 1, src.size(), f); fclose(f);
-        const char* cxx = getenv("GS_JIT_CXX"); if (!cxx) cxx = getenv("CXX"); if (!cxx) cxx = "g++";
-        // -march=native: the code runs on the machine that compiles it (mulx / adx shorten the carry chains)
-        const std::string cmd = std::string(cxx) + " -O3 -march=native -std=c++17 -fPIC -shared -o '" + tmp + "' '" + cpp + "' > '" + log + "' 2>&1";
-        const int rc = system(cmd.c_str());
-        if (rc != 0 || rename(tmp.c_str(), so.c_str()) != 0) { unlink(tmp.c_str()); return done(interp("host compiler failed: " + cmd)); }
+        std::vector<std::string> argv = {cxx};
+        argv.insert(argv.end(), flags.begin(), flags.end());
+        argv.insert(argv.end(), {"-o", tmp, cpp});
+        const int rc = jit_spawn(argv, log);
+        if (rc != 0 || rename(tmp.c_str(), so.c_str()) != 0) { unlink(tmp.c_str()); return done(interp(std::string("host compiler failed: ") + cxx + " (log: " + log + ")")); }
         unlink(cpp.c_str()); unlink(log.c_str());
     }
     auto j = std::make_shared<TraceJit>();

@@ -556,11 +556,19 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     // 5b-7 ---- compose + the whole FRI layer chain (second captured region)
     std::vector<FriLayer> layers;
     uint8_t* mb = (uint8_t*)c->mailbox;
-    const size_t MB_FLAG = 16, MB_ROOT = 128, MB_REM = 4096;
+    // mailbox layout: [0, 32) evaluation root, then the compose fail flag; [1024, 1792) FRI layer roots; [2048, 2144) one
+    // epoch flag per layer; [4096, 8192) remainder; [8192, ...) gathered query data
+    const size_t MB_ROOT = 1024, MB_FLAG = 2048, MB_REM = 4096;
     int n_layers = 0;
     // epoch flag: the chain copies it to the mailbox right behind each layer root; the host polls for it
-    // (events recorded inside a captured graph cannot be synchronised from the host)
-    const uint32_t epoch = (uint32_t)(S->proves_done + 1);
+    // (events recorded inside a captured graph cannot be synchronised from the host).  The mailbox belongs to the
+    // context, which several Stark instances share, and a prove can fail half way: the epoch counts every ATTEMPT on
+    // the context (never a value an earlier prove left behind) and the flag / root slots are cleared first -- the
+    // stream is idle here (synchronised for the evaluation root above).
+    if (++c->prove_epoch == 0) ++c->prove_epoch;
+    const uint32_t epoch = c->prove_epoch;
+    memset(mb + MB_ROOT, 0, 32 * 24);
+    memset(mb + MB_FLAG, 0, 4 * 24);
     GS_CUDA(c, cudaMemcpyAsync(S->d_epoch.p, &epoch, 4, cudaMemcpyHostToDevice, c->stream));
     GS_CUDA(c, cudaMemsetAsync(S->d_epoch.as<uint8_t>() + 32, 0, 16, c->stream));
     auto fri_region = [&]() -> int {

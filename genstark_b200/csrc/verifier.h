@@ -83,6 +83,7 @@ struct ProofReader {
 // MerkleTree.verifyBatch with the leaf values already hashed (rehashMerkleProofValues, utils/index.ts:34-45)
 static inline bool verify_batch(const Digest& root, const std::vector<uint32_t>& indexes, const std::vector<Digest>& values,
                                 const std::vector<std::vector<Digest>>& nodes, int depth, const HostHash& H) {
+    if (depth < 0 || depth > 32) return false;
     const uint64_t offset = 1ull << depth;
     std::map<uint32_t, int> index_map;
     for (size_t i = 0; i < indexes.size(); ++i) { if (indexes[i] >= offset) return false; index_map[indexes[i]] = (int)i; }
@@ -194,6 +195,15 @@ static inline std::string stark_verify(const AirHost& A, int hash_alg, int exe_q
     const HostHash H{hash_alg};
     const int R = A.R, K = A.K, log_t = A.log_t, log_e = A.log_e, log_n = log_t + log_e;
     const uint64_t T = 1ull << log_t, N = 1ull << log_n, E = 1ull << log_e;
+    // the same checks the prover makes on its assertions (prover.cuh): a register outside the bank would index past
+    // the leaf, a repeated (register, step) pair makes the interpolation divide by zero
+    for (size_t i = 0; i < asserts.size(); ++i) {
+        if (asserts[i].reg >= (uint32_t)R) return "Invalid assertion: register " + std::to_string(asserts[i].reg) + " is outside of register bank";
+        if (asserts[i].step >= T) return "Invalid assertion: step " + std::to_string(asserts[i].step) + " is outside of execution trace";
+        for (size_t j = 0; j < i; ++j)
+            if (asserts[j].reg == asserts[i].reg && asserts[j].step == asserts[i].step)
+                return "Invalid assertion: repeated assertion for register " + std::to_string(asserts[i].reg) + " at step " + std::to_string(asserts[i].step);
+    }
     const size_t ev_leaf = (size_t)(R + A.n_secret) * 16, ld_leaf = 64;
     // ---- parse (Serializer.ts:83-144)
     ProofReader rd{proof, proof_len};
@@ -202,6 +212,12 @@ static inline std::string stark_verify(const AirHost& A, int hash_alg, int exe_q
     Digest lc_root; rd.bytes(lc_root.data(), 32);
     ParsedBatch lc_proof; if (!rd.batch(lc_proof, ld_leaf)) return "Verification of low degree failed: malformed proof";
     const int n_comp = rd.u8();
+    // the layer count follows from N (LowDegreeProver.ts:179: fold while the column is longer than 256); a proof that
+    // claims another count would drive column_length below 4 further down
+    {
+        int want = 0; for (uint64_t l = N; l > 256; l >>= 2) ++want;
+        if (n_comp != want) return "Verification of low degree failed: malformed proof (" + std::to_string(n_comp) + " components, " + std::to_string(want) + " expected)";
+    }
     struct Comp { Digest root; ParsedBatch column, poly; };
     std::vector<Comp> comps(n_comp);
     for (auto& c : comps) { rd.bytes(c.root.data(), 32); if (!rd.batch(c.column, ld_leaf) || !rd.batch(c.poly, ld_leaf)) return "Verification of low degree failed: malformed proof"; }
@@ -340,7 +356,7 @@ static inline std::string stark_verify(const AirHost& A, int hash_alg, int exe_q
         const std::vector<uint32_t> lc_pos = aug4(positions, column_length);
         std::vector<u128> checks;
         if (lc_proof.values.size() != lc_pos.size() || !column_values(lc_proof, positions, lc_pos, column_length, checks)) return "Verification of low degree failed: Verification of linear combination Merkle proof failed";
-        if (!verify_batch(lc_root, lc_pos, hashed_values(lc_proof), lc_proof.nodes, lc_proof.depth, H)) return "Verification of low degree failed: Verification of linear combination Merkle proof failed";
+        if ((1ull << (lc_proof.depth & 63)) != (column_length >> 2) || !verify_batch(lc_root, lc_pos, hashed_values(lc_proof), lc_proof.nodes, lc_proof.depth, H)) return "Verification of low degree failed: Verification of linear combination Merkle proof failed";
         for (size_t i = 0; i < lc_values.size(); ++i) if (lc_values[i] != checks[i]) return "Verification of low degree failed: Verification of linear combination correctness failed";
     }
     Digest p_root = lc_root;
@@ -355,8 +371,9 @@ static inline std::string stark_verify(const AirHost& A, int hash_alg, int exe_q
         const std::vector<uint32_t> augp = aug4(pos, column_length);
         std::vector<u128> colv;
         if (cp.column.values.size() != augp.size() || !column_values(cp.column, pos, augp, column_length, colv)) return "Verification of low degree failed: Verification of column Merkle proof failed at depth " + std::to_string(depth);
-        if (!verify_batch(cp.root, augp, hashed_values(cp.column), cp.column.nodes, cp.column.depth, H)) return "Verification of low degree failed: Verification of column Merkle proof failed at depth " + std::to_string(depth);
-        if (cp.poly.values.size() != pos.size() || !verify_batch(p_root, pos, hashed_values(cp.poly), cp.poly.nodes, cp.poly.depth, H)) return "Verification of low degree failed: Verification of polynomial Merkle proof failed at depth " + std::to_string(depth);
+        if (column_length < 8) return "Verification of low degree failed: malformed proof (column too short)";
+        if ((1ull << (cp.column.depth & 63)) != (column_length >> 2) || !verify_batch(cp.root, augp, hashed_values(cp.column), cp.column.nodes, cp.column.depth, H)) return "Verification of low degree failed: Verification of column Merkle proof failed at depth " + std::to_string(depth);
+        if (cp.poly.values.size() != pos.size() || (1ull << (cp.poly.depth & 63)) != column_length || !verify_batch(p_root, pos, hashed_values(cp.poly), cp.poly.nodes, cp.poly.depth, H)) return "Verification of low degree failed: Verification of polynomial Merkle proof failed at depth " + std::to_string(depth);
         const u128 special_x = prng_one(p_root.data(), 32);
         for (size_t i = 0; i < pos.size(); ++i) {
             const u128 xe = h_pow(rou, pos[i]);

@@ -97,3 +97,20 @@ def test_segment_parallel_generation_equals_the_sequential_one(name, monkeypatch
     assert 'threads' not in gstark.trace_backend()
     from genstark_b200 import airs
     assert tr[0] == airs.run_mimc(8192, airs.mimc_round_constants(), 3)
+
+
+def test_jit_cache_refuses_a_directory_others_can_write_to(tmp_path, monkeypatch):
+    """what is loaded from the cache is executed: a world-writable directory is not used (hostjit.h / jitcache.h); the
+    object is compiled into a private mkdtemp directory instead and nothing in the shared one is touched or loaded"""
+    air = _quadratic_air(64, 0xB200_0002)
+    shared = tmp_path / 'shared'
+    shared.mkdir()
+    os.chmod(shared, 0o777)
+    monkeypatch.setenv('GS_JIT_CACHE', str(shared))
+    monkeypatch.setenv('GS_TRACE_JIT', '1')
+    got = gstark.generate_execution_trace(air, [], [5])
+    backend = gstark.trace_backend()
+    if not backend.startswith('jit'):
+        pytest.skip(f'no host compiler for the trace JIT: {backend}')
+    assert got == _oracle_trace(air, [], [5])
+    assert list(shared.iterdir()) == []
