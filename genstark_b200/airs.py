@@ -338,17 +338,30 @@ def poseidon_merkle_proof(depth: int = 8, proofs: int = 1, extension_factor: int
         input_shapes=lambda inputs: [[proofs], [proofs], [proofs, depth], [proofs, depth], [proofs, depth]])
 
 
+_TREE_CACHE: dict = {}
+
+
+def _poseidon_tree(leaves, p):
+    """all levels of the Poseidon Merkle tree over `leaves` (one tree serves every branch of a workload)"""
+    key = (hash(leaves), p)
+    if key not in _TREE_CACHE:
+        level = [list(x) for x in leaves]
+        tree = [level]
+        while len(level) > 1:
+            level = [poseidon_hash(level[2 * i] + level[2 * i + 1], p) for i in range(len(level) // 2)]
+            tree.append(level)
+        _TREE_CACHE.clear()
+        _TREE_CACHE[key] = tree
+    return _TREE_CACHE[key]
+
+
 def poseidon_merkle_inputs(index: int, leaves: Sequence[Sequence[int]], p: int = P128):
     """A depth-log2(len(leaves)) Merkle branch over Poseidon (examples/poseidon/utils.ts MerkleTree) for one proof:
     returns (leaf, nodes[depth], bits[depth], root).  node[0] is the sibling leaf; bits are the index shifted by
     one level as in merkleProof.ts:110-114."""
     n = len(leaves)
     depth = n.bit_length() - 1
-    level = [list(x) for x in leaves]
-    tree = [level]
-    while len(level) > 1:
-        level = [poseidon_hash(level[2 * i] + level[2 * i + 1], p) for i in range(len(level) // 2)]
-        tree.append(level)
+    tree = _poseidon_tree(tuple(tuple(x) for x in leaves), p)
     nodes, idx = [], index
     for d in range(depth):
         nodes.append(tree[d][idx ^ 1]); idx >>= 1
