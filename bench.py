@@ -1,20 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- MiMC-128 prove() on B200 (BASELINE.json metric), one JSON line on rank 0.
+"""bench.py -- Stark.prove() on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-A "step" is one Stark.prove() of the north-star workload (MiMC over p128, 2^20 steps, extension factor 8,
-blake2s256, 48 trace / 24 FRI queries: examples/mimc/mimc128.ts:22-28 with the E of BASELINE.json's target).
+A "step" is one Stark.prove() of the selected workload.  `--config` picks it (default `ns`, the configuration
+BASELINE.json's metric is quoted on: MiMC over p128, 2^20 steps, extension factor 8, blake2s256, 48 trace / 24 FRI
+queries -- examples/mimc/mimc128.ts:22-28 with the E of the north-star target); `2`, `3`, `4`, `5` are BASELINE.json's
+configs[1..4] (genstark_b200/workloads.py).
   value        ms per prove with the execution trace already resident in HBM (CUDA events on the prover stream)
   e2e.value    ms per prove through the public API from host inputs to host-resident proof bytes
-               (host trace generation + H2D of the trace + every D2H inside the timed region)
+               (host trace generation + H2D of the trace + every D2H inside the timed region) -- BASELINE.md section 4's
+               definition of prove() time, and the headline
+  parity_*     SHA-256 of every rank's proof bytes against the C oracle's proof for the same workload (computed once,
+               outside every timed region)
   roofline     dominant kernel class of the step: algorithmic bytes / CUDA-event time vs measured HBM peak
-  cpu_baseline the oracle port of the same path on the host cores (bounded sample), N=1 rank 0 only
-`--impl reference` times that CPU port alone (the reference itself needs node + npm packages that this
-image does not have: SURVEY.md §8c).
+  ntt          K1 alone (second half of BASELINE.json's metric): rows in {1,4,12}, 2^13..2^24 points, forward / inverse /
+               LDE, median of 20 runs; at N > 1 every rank's share of the coset-sharded LDE
+  cpu_baseline the oracle port of the same path on the host cores (one prove), N=1 rank 0 only
+`--impl reference` times that CPU port alone (the reference itself needs node + npm packages that this image does not
+have: SURVEY.md section 8c); its `value` leaves out the trace-generation stage like ours, its `e2e` is the whole prove().
+One proof is sharded over the N ranks by cosets, so "scaling" is "strong" at every N.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -25,14 +34,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LOG_STEPS = int(os.environ.get('GS_BENCH_LOG_STEPS', '20'))
-EXT = int(os.environ.get('GS_BENCH_EXT', '8'))
-OPTS = dict(hashAlgorithm='blake2s256', extensionFactor=EXT, exeQueryCount=48, friQueryCount=24)
-METRIC = 'mimc128_prove_ms'
-
-
-def workload_name(log_steps=LOG_STEPS, ext=EXT):
-    return f'MiMC-128 prove(), 2^{log_steps} steps, extensionFactor {ext}, blake2s256, 48/24 queries (north-star target)'
+METRICS = {'ns': 'mimc128_prove_ms', '2': 'mimc128_prove_ms', '4': 'mimc128_prove_ms', '3': 'rescue4x128_prove_ms',
+           '5': 'poseidon_merkle_prove_ms', 'test': 'mimc128_prove_ms'}
+DTYPE = 'u128 (integer mod p = 2^128 - 9*2^32 + 1, 4x u32 limbs)'
 
 
 def measured_peaks():
@@ -96,108 +100,153 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm), 'window': window}
 
 
-def mimc_case(log_steps):
-    from genstark_b200 import airs
-    steps = 1 << log_steps
-    air = airs.mimc128(steps)
-    return air, steps
+def load_workload(name):
+    """(air, options, assertions, inputs, seed, description) -- built outside every timed region"""
+    from genstark_b200 import workloads
+    return workloads.config(name)
 
 
-def mimc_assertions(steps, seed=3):
-    """control values via the native library's scalar ops would be slow in Python for 2^20 steps; use the
-    closed loop in Python ints (examples/mimc/utils.ts:7-14) -- outside every timed region."""
-    from genstark_b200 import airs
-    from genstark_b200.air import P128
-    k = airs.mimc_round_constants()
-    x = seed % P128
-    for i in range(steps - 1):
-        x = (x * x % P128 * x + k[i & 63]) % P128
-    return [dict(step=0, register=0, value=seed), dict(step=steps - 1, register=0, value=x)]
+def host_threads():
+    # physical cores: hyper-threads do not help the oracle's memory-bound loops (measured: 128 threads slower than 64)
+    ncpu = os.cpu_count() or 1
+    return ncpu // 2 if ncpu > 16 else ncpu
 
 
 # ------------------------------------------------------------------------------------------ CPU port
-def cpu_port_prove_ms(log_steps, ext, threads=None):
-    """time the oracle's prove() on the host.  Prefers the compiled C port (oracle/_build), else the
-    Python restatement (single thread)."""
-    try:
-        from oracle import cport
-        if cport.available():
-            return cport.time_mimc_prove(log_steps, ext, threads)
-    except Exception as e:        # pragma: no cover
-        print(f'[bench] C port unavailable: {e}', file=sys.stderr)
-    from genstark_b200 import airs
-    from oracle.stark import Stark as OracleStark
-    steps = 1 << log_steps
-    air = airs.mimc128(steps)
-    st = OracleStark(air, dict(OPTS, extensionFactor=ext))
-    a = mimc_assertions(steps)
+def oracle_prove(workload, threads=None):
+    """one prove() of the workload by the C oracle port: (proof bytes, total ms, stage list, threads)"""
+    from oracle import cport
+    air, opts, a, inputs, seed, _ = workload
+    L = cport.lib()
+    L.oracle_set_threads(int(threads or host_threads()))
+    n = L.oracle_threads()
+    stages = []
     t = time.perf_counter()
-    st.prove(a, [], [3])
-    return (time.perf_counter() - t) * 1e3, 1, 'python'
+    proof = cport.prove(air, opts, a, inputs, seed, stages=stages)
+    return proof, (time.perf_counter() - t) * 1e3, stages, n
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    # bounded sample: the Python port cannot run 2^20 steps in minutes; the C port can
-    try:
-        from oracle import cport
-        have_c = cport.available()
-    except Exception:
-        have_c = False
-    log_steps = LOG_STEPS if have_c else 12
-    times = []
-    cores = 1
-    kind = 'python'
+    workload = load_workload(args.config)
+    desc = workload[5]
+    tot, res, n = [], [], 1
     for i in range(args.warmup + args.steps):
-        ms, cores, kind = cpu_port_prove_ms(log_steps, EXT, None)
+        proof, ms, stages, n = oracle_prove(workload)
         if i >= args.warmup:
-            times.append(ms)
-    ms = sum(times) / len(times)
-    scale = 1.0
-    sample = f'prove() of MiMC-128 2^{log_steps} steps E={EXT} ({kind} oracle port)'
-    if log_steps != LOG_STEPS:
-        # N log N extrapolation to the named workload, stated as such
-        n0, n1 = (1 << log_steps) * EXT, (1 << LOG_STEPS) * EXT
-        scale = (n1 * (LOG_STEPS + 3)) / (n0 * (log_steps + 3))
-        sample += f'; value extrapolated x{scale:.0f} by N log N to 2^{LOG_STEPS} steps'
-    v = ms * scale
-    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'ms', 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': v, 'higher_is_better': False, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'u128 (integer mod p)', 'data': 'synthetic',
-            'config': {'workload': workload_name(), 'parallelism': 'cpu'},
-            'cpu_baseline': {'value': v, 'unit': 'ms', 'cores': cores, 'kind': 'port', 'sample': sample},
-            'e2e': {'value': v, 'unit': 'ms', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            tot.append(ms)
+            res.append(ms - dict(stages).get('trace', 0.0))
+    e2e = sum(tot) / len(tot)
+    v = sum(res) / len(res)
+    sample = f'{args.steps} whole prove() of the workload by the C oracle port (oracle/c/stark_oracle.c, OpenMP, {n} threads)'
+    line = {'impl': 'reference', 'metric': METRICS[args.config], 'value': v, 'unit': 'ms', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': v, 'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': DTYPE, 'data': 'synthetic',
+            'config': {'workload': desc, 'value_excludes': 'execution-trace generation (as on the GPU arm, whose `value` starts from a resident trace)'},
+            'cpu_baseline': {'value': v, 'unit': 'ms', 'cores': n, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': e2e, 'unit': 'ms', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'stages_ms': [[k, round(t, 3)] for k, t in stages],
+            'proof_sha256': hashlib.sha256(proof).hexdigest(),
             'note': 'the reference (genSTARK + galois/merkle/air-assembly WASM) cannot run here: no node in the image'}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+def fri_layers(n):
+    out = []
+    while True:
+        out.append(n)
+        if n <= 256:
+            return out
+        n >>= 2
+
+
 def algorithmic_bytes(cls, log_t, log_e, r, s, n_boundary):
-    """SURVEY.md §8d / App. A.9 per-unit figures x units of ONE prove, per kernel class."""
+    """SURVEY.md section 8d / App. A.9 per-unit figures x units of ONE prove, per kernel class."""
     T, N = 1 << log_t, 1 << (log_t + log_e)
     B, D = 16, 32
-    fri = []
-    L = N
-    while True:
-        fri.append(L)
-        if L <= 256:
-            break
-        L >>= 2
+    fri = fri_layers(N)
     if cls.startswith('ntt'):
         # iNTT(T) + LDE(T -> N) for R (+S) rows: 32 B/point of the transform actually computed
         return (r + s) * (2 * B * T + B * (T + N))
     if cls == 'hash_columns':
         return N * ((r + s) * B + D) + sum((l // 4) * (4 * B + D) for l in fri)
     if cls == 'merkle_build':
-        return 2 * N * D + sum(2 * (l // 4) * D for l in fri)      # read 2 digests / write 1 per node ~ 2n*32... counted as 64 B/leaf
+        return 2 * N * D + sum(2 * (l // 4) * D for l in fri)      # 64 B per tree node: read two digests, write one
     if cls == 'compose':
         return N * B * (r + s + n_boundary + 1)
     if cls in ('batch_inverse', 'zb_eval'):
         return n_boundary * N * 2 * B
     if cls == 'fri_fold':
         return sum(B * l + B * l // 4 for l in fri[:-1])
+    if cls == 'fri_tail':
+        return sum(B * l + (l // 4) * 3 * D for l in fri if l <= (1 << 17))
     return 0
+
+
+def ntt_table(ctx, L, hbm, rank, world, full=True):
+    """K1 alone: rows x points of uniform residues (device-side SplitMix64, seed 0xB200), median of 20 runs
+    after 3 warm-ups, CUDA events on the library's stream, data resident in HBM.  Rows: [kind, rows, log2 t, log2 n, ms,
+    G elements/s, fraction of the HBM roof at 16(t+n) algorithmic bytes per row]."""
+    rows_out = []
+
+    def alloc(r, n):
+        h = C.c_void_p()
+        ctx.check(L.gs_mat_alloc(ctx.handle, r, n, C.byref(h)))
+        return h
+
+    def timed(fn, reps=20, warm=3):
+        ms, samples = C.c_float(), []
+        for i in range(warm + reps):
+            L.gs_timer_begin(ctx.handle)
+            ctx.check(fn())
+            L.gs_timer_end(ctx.handle, C.byref(ms))
+            if i >= warm:
+                samples.append(ms.value)
+        samples.sort()
+        return samples[len(samples) // 2]
+
+    sizes = list(range(13, 25)) if full else [20, 23]
+    for r in (1, 4, 12):
+        for log_n in sizes:
+            n = 1 << log_n
+            kinds = [('fwd', log_n, 0), ('inv', log_n, 1), ('lde8', log_n - 3, 0)]
+            if r == 1:
+                kinds += [('lde16', log_n - 4, 0), ('lde32', log_n - 5, 0)]
+            dst, work = alloc(r, n), alloc(r, n)
+            for kind, log_t, inv in kinds:
+                src = alloc(r, 1 << log_t)
+                ctx.check(L.gs_mat_fill_random(ctx.handle, src, 0xB200))
+                med = timed(lambda: L.gs_ntt_into(ctx.handle, src, dst, work, inv))
+                alg = 16 * ((1 << log_t) + n) * r
+                rows_out.append([kind, r, log_t, log_n, round(med, 5), round(r * n / (med * 1e-3) / 1e9, 3),
+                                 round(alg / (med * 1e-3) / 1e9 / hbm, 4)])
+                L.gs_mat_free(src)
+            L.gs_mat_free(dst); L.gs_mat_free(work)
+    return rows_out
+
+
+def sharded_lde(ctx, L, rank, world, log_t, log_e):
+    """every rank's share of the coset-sharded LDE of the benched shape (2^log_e / world cosets per rank): ms on this rank"""
+    per = (1 << log_e) // world
+    n_loc = (1 << log_t) * per
+    src, dst, work = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    ctx.check(L.gs_mat_alloc(ctx.handle, 1, 1 << log_t, C.byref(src)))
+    ctx.check(L.gs_mat_alloc(ctx.handle, 1, n_loc, C.byref(dst)))
+    ctx.check(L.gs_mat_alloc(ctx.handle, 1, n_loc, C.byref(work)))
+    ctx.check(L.gs_mat_fill_random(ctx.handle, src, 0xB200))
+    ms, samples = C.c_float(), []
+    for i in range(23):
+        L.gs_timer_begin(ctx.handle)
+        ctx.check(L.gs_lde_cosets_into(ctx.handle, src, dst, work, rank * per, log_e))
+        L.gs_timer_end(ctx.handle, C.byref(ms))
+        if i >= 3:
+            samples.append(ms.value)
+    for h in (src, dst, work):
+        L.gs_mat_free(h)
+    samples.sort()
+    return samples[len(samples) // 2]
 
 
 def run_ours(args, rank, local_rank, world):
@@ -214,30 +263,45 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    from genstark_b200.field import Context, GpuField
+    from genstark_b200.field import Context
     from genstark_b200.stark import Stark
     from genstark_b200 import _native
     L = _native.lib()
 
-    air, steps = mimc_case(LOG_STEPS)
+    workload = load_workload(args.config)
+    air, opts, assertions, inputs, seed, desc = workload
+    air = air.with_options(opts.get('extensionFactor'))
+    steps, ext = air.trace_length, air.extension_factor
+    log_t, log_e = steps.bit_length() - 1, ext.bit_length() - 1
     ctx = Context(local_rank)
     if world > 1:
-        # one proof sharded over the ranks by cosets (strong scaling): NCCL all-gather of digests at every Merkle commit
-        if EXT % world:
-            raise SystemExit(f'extension factor {EXT} has fewer cosets than ranks ({world})')
+        # one proof sharded over the ranks by cosets (strong scaling): NCCL exchange of digests at every Merkle commit
+        if ext % world:
+            raise SystemExit(f'extension factor {ext} has fewer cosets than ranks ({world})')
         uid = [Context.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(rank, world, uid[0])
-    st = Stark(air, dict(OPTS), context=ctx)
-    assertions = mimc_assertions(steps)
-    seed = [3]
+    st = Stark(air, dict(opts), context=ctx)
+
+    # ---- parity: the C oracle's proof of the same workload (rank 0, outside every timed region)
+    want_sha, cpu, oracle_note = None, None, None
+    if rank == 0:
+        try:
+            want, ms_cpu, stages, cores = oracle_prove(workload)
+            want_sha = hashlib.sha256(want).hexdigest()
+            if world == 1:
+                cpu = {'value': ms_cpu, 'unit': 'ms', 'cores': cores, 'kind': 'port',
+                       'sample': f'one whole prove() of the workload (trace generation included) by the C oracle port, {cores} OpenMP threads',
+                       'stages_ms': [[k, round(t, 3)] for k, t in stages]}
+        except Exception as e:        # pragma: no cover
+            oracle_note = f'C oracle unavailable: {e!r}'
 
     sampler = ClockSampler(local_rank)
     sampler.start()
 
     # warm-up (also allocates every buffer)
     for _ in range(max(args.warmup, 3)):
-        proof = st.prove_bytes(assertions, [], seed)
+        proof = st.prove_bytes(assertions, inputs, seed)
     proof_len = len(proof)
     from genstark_b200.stark import trace_backend as _tb
     trace_backend = _tb()
@@ -247,22 +311,23 @@ def run_ours(args, rank, local_rank, world):
     launches0 = ctx.launch_count
     t0 = time.perf_counter()
     t_region0 = t0
-    e2e_dev = []
+    e2e_dev, hashes = [], set()
     for _ in range(args.steps):
-        st.prove_bytes(assertions, [], seed)
+        pb = st.prove_bytes(assertions, inputs, seed)
         e2e_dev.append(st.last_timing())
+        hashes.add(pb)            # a set of bytes objects: comparing is outside the cost of a prove, hashing comes after the region
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     launches_per_step = (ctx.launch_count - launches0) // args.steps
     stage_times = st.stage_times()
 
     # ---- resident leg: trace already in HBM; CUDA events on the prover stream around the whole device part
-    st.prove_bytes(assertions, [], seed, _reuse_resident_trace=True)
+    hashes.add(st.prove_bytes(assertions, inputs, seed, _reuse_resident_trace=True))
     barrier()
     dev_ms = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        st.prove_bytes(assertions, [], seed, _reuse_resident_trace=True)
+        hashes.add(st.prove_bytes(assertions, inputs, seed, _reuse_resident_trace=True))
         dev_ms.append(st.last_timing()[0])
     barrier()
     wall_resident = (time.perf_counter() - t0) * 1e3 / args.steps
@@ -271,7 +336,7 @@ def run_ours(args, rank, local_rank, world):
     L.gs_ctx_profile(ctx.handle, 1)
     prof_dev = []
     for _ in range(args.steps):
-        st.prove_bytes(assertions, [], seed, _reuse_resident_trace=True)
+        hashes.add(st.prove_bytes(assertions, inputs, seed, _reuse_resident_trace=True))
         prof_dev.append(st.last_timing()[0])
     barrier()
     prof = json.loads(L.gs_ctx_profile_report(ctx.handle).decode())
@@ -281,38 +346,34 @@ def run_ours(args, rank, local_rank, world):
     clocks = sampler.summary(t_region0, t_region1)
 
     ms_step = sum(dev_ms) / len(dev_ms)
+    my_sha = sorted(hashlib.sha256(h).hexdigest() for h in hashes)        # every proof of every leg: one value expected
+    all_sha = [my_sha]
     if dist is not None:
         t = torch.tensor([ms_step, e2e_ms], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, e2e_ms = float(t[0]), float(t[1])
+        all_sha = [None] * world
+        dist.all_gather_object(all_sha, my_sha)
+
+    peaks, peak_kind = measured_peaks()
+    hbm = float(peaks.get('hbm_gbs', 6650.0))
 
     # ---- K1 alone: NTT throughput (second half of BASELINE.json's metric)
     ntt = {}
+    if world > 1:
+        lde_ms = sharded_lde(ctx, L, rank, world, log_t, log_e)
+        t = torch.tensor([lde_ms], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_out = steps * ext
+        ntt['sharded_lde'] = {'shape': f'2^{log_t} -> 2^{log_t + log_e}, {ext // world} of {ext} cosets per rank', 'ms_max_over_ranks': round(float(t[0]), 5),
+                              'elements_per_s': n_out / (float(t[0]) * 1e-3), 'this_rank_ms': round(lde_ms, 5)}
     if rank == 0:
-        f = GpuField(ctx)
-        import random
-        r = random.Random(0xB200)
-        for name, log_t, log_n, inv in (('ntt_fwd_2^23', 23, 23, 0), ('lde_2^20_to_2^23', 20, 23, 0), ('intt_2^20', 20, 20, 1)):
-            t_, n_ = 1 << log_t, 1 << log_n
-            # uniform 127-bit residues (canonical: top bit of every element cleared)
-            ba = bytearray(r.randbytes(16 * t_))
-            ba[15::16] = bytes(x & 0x7F for x in ba[15::16])
-            src = f._from_bytes(bytes(ba), 1, t_)
-            dst, work = C.c_void_p(), C.c_void_p()
-            ctx.check(L.gs_mat_alloc(ctx.handle, 1, n_, C.byref(dst)))
-            ctx.check(L.gs_mat_alloc(ctx.handle, 1, n_, C.byref(work)))
-            ms = C.c_float()
-            best = []
-            for i in range(8):
-                L.gs_timer_begin(ctx.handle)
-                ctx.check(L.gs_ntt_into(ctx.handle, src.handle, dst, work, inv))
-                L.gs_timer_end(ctx.handle, C.byref(ms))
-                if i >= 3:
-                    best.append(ms.value)
-            med = sorted(best)[len(best) // 2]
-            alg_bytes = 16 * (t_ + n_)
-            ntt[name] = {'ms': round(med, 4), 'elements_per_s': n_ / (med * 1e-3), 'algorithmic_GBps': alg_bytes / (med * 1e-3) / 1e9}
-            L.gs_mat_free(dst); L.gs_mat_free(work); src.free()
+        table = ntt_table(ctx, L, hbm, rank, world, full=(not args.quick_ntt))
+        ntt['columns'] = ['kind', 'rows', 'log2_t', 'log2_n', 'ms_median_of_20', 'G_elements_per_s', 'hbm_frac_at_16(t+n)_bytes_per_row']
+        ntt['table'] = table
+        for row in table:           # the three figures earlier rounds quoted
+            if row[1] == 1 and (row[0], row[3]) in (('fwd', 23), ('lde8', 23), ('inv', 20)):
+                ntt[f'{row[0]}_2^{row[3]}'] = {'ms': row[4], 'elements_per_s': row[5] * 1e9}
 
     if rank != 0:
         if dist is not None:
@@ -320,30 +381,38 @@ def run_ours(args, rank, local_rank, world):
             dist.destroy_process_group()
         return
 
-    peaks, peak_kind = measured_peaks()
-    hbm = float(peaks.get('hbm_gbs', 6650.0))
+    parity_ok = None
+    if want_sha is not None:
+        parity_ok = all(s == [want_sha] for s in all_sha)
+
     # dominant kernel class of the resident step
     per_step = {k: v['ms'] / args.steps for k, v in prof.items()}
-    # group the K1 passes
     grouped = {}
     for k, v in per_step.items():
         key = 'ntt' if k.startswith('ntt') else k
         grouped[key] = grouped.get(key, 0.0) + v
-    dom = max(grouped, key=grouped.get)
-    log_t, log_e = LOG_STEPS, EXT.bit_length() - 1
+    compute = {k: v for k, v in grouped.items() if not k.startswith('nccl')}
+    dom = max(compute, key=compute.get)
+    n_reg, n_sec = air.trace_register_count, air.secret_input_count
+    n_boundary = len({int(a['register']) for a in assertions})
     # sharded runs: kernel times are rank 0's, which holds 1/world of the evaluation domain
-    alg = algorithmic_bytes(dom, log_t, log_e, air.trace_register_count, air.secret_input_count, 1) // world
+    alg = algorithmic_bytes(dom, log_t, log_e, n_reg, n_sec, n_boundary) // world
     achieved = alg / (grouped[dom] * 1e-3) / 1e9
-    traffic = None
+    # DRAM traffic of that kernel class: ncu counters of this code on this workload (profiles/ncu_summary.json records the
+    # commit and the workload of the capture); single GPU only -- no counters were taken on the sharded path
+    traffic, traffic_src = None, None
     summ = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
-    if os.path.exists(summ):
+    if world == 1 and os.path.exists(summ):
         try:
-            traffic = json.load(open(summ)).get(dom, {}).get('dram_bytes_per_step')
-            traffic = traffic // world if traffic else traffic
+            sj = json.load(open(summ))
+            ent = sj.get('configs', {}).get(args.config, {})
+            if dom in ent.get('classes', {}):
+                traffic = ent['classes'][dom].get('dram_bytes_per_step')
+                traffic_src = f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum over the launches of one prove; capture at commit {ent.get('commit')}"
         except Exception:
             traffic = None
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
-                'traffic': traffic, 'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs)',
+                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs)',
                 'kernel_ms_per_step': grouped[dom], 'algorithmic_bytes_per_step': alg,
                 'share_of_step': grouped[dom] / (sum(prof_dev) / len(prof_dev)),
                 'note': '128-bit modular arithmetic on 32-bit integer pipes: every kernel here is issue-bound, not HBM-bound'}
@@ -354,76 +423,56 @@ def run_ours(args, rank, local_rank, world):
     #  * modmul kernels: gs_debug_modmul_probe measures the chip's dependent-free modular-multiplication rate
     sm_hz = (clocks.get('sm_mhz') or 1965.0) * 1e6
     sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
-    comp_peak = sm_count * 4 * 32 * sm_hz / (2 * 648.0)
-    n_eval = steps * EXT
-    fri_rows, l_ = 0, n_eval
-    while True:
-        fri_rows += l_ // 4
-        if l_ <= 256:
-            break
-        l_ >>= 2
-    comp_hash_cols = n_eval + fri_rows
-    comp_merkle = (n_eval - 1) + fri_rows
-    issue_roofline = {
-        'hash_columns': {'unit': 'blake2s compressions/s', 'achieved': comp_hash_cols / (grouped.get('hash_columns', 0) * 1e-3) if grouped.get('hash_columns') else None,
-                         'peak': comp_peak, 'peak_how': 'ALU pipe: SMs*4*32 lanes*f / (2 cycles * 648 ALU instructions per compression)'},
-        'merkle_build': {'unit': 'blake2s compressions/s', 'achieved': comp_merkle / (grouped.get('merkle_build', 0) * 1e-3) if grouped.get('merkle_build') else None,
-                         'peak': comp_peak, 'peak_how': 'same ALU-pipe bound; the top levels of every tree are latency-bound'},
-    }
-    for v in issue_roofline.values():
-        v['frac'] = (v['achieved'] / v['peak']) if v['achieved'] else None
-    probe_ms = C.c_float()
-    if world > 1:
-        issue_roofline = None            # per-rank work counts differ per commit on the sharded path: N=1 only
-    elif L.gs_debug_modmul_probe(ctx.handle, sm_count * 8, 2000, C.byref(probe_ms)) == 0 and probe_ms.value > 0:
-        modmul_peak = sm_count * 8 * 256 * 4 * 2000.0 / (probe_ms.value * 1e-3)
-        issue_roofline['modmul_probe'] = {'unit': 'modmul/s', 'peak': modmul_peak, 'probe_ms': probe_ms.value,
-                                          'how': 'gs_debug_modmul_probe: 8 CTAs x 256 threads per SM, 4 independent chains each'}
-        # K1 against the rate of its own instruction mix: a butterfly = modular add + modular sub + modular multiplication
-        # (gs_debug_butterfly_probe).  Butterflies of one prove: iNTT of T points + E coset transforms of T points, (n/2) log2 n each
-        # (the register-resident radix-8/16 stages skip the multiplications by 1, so this counts a few more multiplications than issued).
-        bf_ms = C.c_float()
-        if L.gs_debug_butterfly_probe(ctx.handle, sm_count * 8, 2000, C.byref(bf_ms)) == 0 and bf_ms.value > 0 and grouped.get('ntt'):
-            bf_peak = sm_count * 8 * 256 * 2 * 2000.0 / (bf_ms.value * 1e-3)
-            rows = air.trace_register_count + sum(1 for s_ in air.static_registers if s_.kind == 'input')
-            n_bf = rows * (1 + EXT) * (steps // 2) * LOG_STEPS
-            a = n_bf / (grouped['ntt'] * 1e-3)
-            issue_roofline['ntt'] = {'unit': 'butterflies/s', 'achieved': a, 'peak': bf_peak, 'frac': a / bf_peak, 'probe_ms': bf_ms.value,
-                                     'butterflies_per_prove': n_bf}
-        if ntt.get('lde_2^20_to_2^23') and bf_ms.value > 0:
-            bf_peak = sm_count * 8 * 256 * 2 * 2000.0 / (bf_ms.value * 1e-3)
-            a = (8 * (1 << 19) * 20) / (ntt['lde_2^20_to_2^23']['ms'] * 1e-3)
-            issue_roofline['lde_2^20_to_2^23'] = {'unit': 'butterflies/s', 'achieved': a, 'peak': bf_peak, 'frac': a / bf_peak}
-
-    cpu = None
+    issue_roofline = None
     if world == 1:
-        try:
-            from oracle import cport
-            have_c = cport.available()
-        except Exception:
-            have_c = False
-        ls = LOG_STEPS if have_c else 12
-        ms_cpu, cores, kind = cpu_port_prove_ms(ls, EXT, None)
-        sample = f'one prove() of MiMC-128 2^{ls} steps E={EXT} by the {kind} oracle port'
-        if ls != LOG_STEPS:
-            n0, n1 = (1 << ls) * EXT, (1 << LOG_STEPS) * EXT
-            sc = (n1 * (LOG_STEPS + 3)) / (n0 * (ls + 3))
-            ms_cpu *= sc
-            sample += f', extrapolated x{sc:.0f} (N log N) to 2^{LOG_STEPS} steps'
-        cpu = {'value': ms_cpu, 'unit': 'ms', 'cores': cores, 'kind': 'port', 'sample': sample}
+        comp_peak = sm_count * 4 * 32 * sm_hz / (2 * 648.0)
+        n_eval = steps * ext
+        fri_rows = sum(l // 4 for l in fri_layers(n_eval))
+        leaf_blocks = -(-((n_reg + n_sec) * 16) // 64)              # 64-byte blake2s blocks per leaf
+        comp_hash_cols = n_eval * leaf_blocks + fri_rows
+        comp_merkle = (n_eval - 1) + fri_rows
+        hash_ms = grouped.get('hash_columns', 0) + grouped.get('fri_tail', 0)
+        issue_roofline = {
+            'hash_columns': {'unit': 'blake2s compressions/s', 'achieved': comp_hash_cols / (hash_ms * 1e-3) if hash_ms else None,
+                             'peak': comp_peak, 'peak_how': 'ALU pipe: SMs*4*32 lanes*f / (2 cycles * 648 ALU instructions per compression)'},
+            'merkle_build': {'unit': 'blake2s compressions/s', 'achieved': comp_merkle / (grouped.get('merkle_build', 0) * 1e-3) if grouped.get('merkle_build') else None,
+                             'peak': comp_peak, 'peak_how': 'same ALU-pipe bound; the top levels of every tree are latency-bound'},
+        }
+        for v in issue_roofline.values():
+            v['frac'] = (v['achieved'] / v['peak']) if v['achieved'] else None
+        probe_ms = C.c_float()
+        if L.gs_debug_modmul_probe(ctx.handle, sm_count * 8, 2000, C.byref(probe_ms)) == 0 and probe_ms.value > 0:
+            modmul_peak = sm_count * 8 * 256 * 4 * 2000.0 / (probe_ms.value * 1e-3)
+            issue_roofline['modmul_probe'] = {'unit': 'modmul/s', 'peak': modmul_peak, 'probe_ms': probe_ms.value,
+                                              'how': 'gs_debug_modmul_probe: 8 CTAs x 256 threads per SM, 4 independent chains each'}
+            # K1 against the rate of its own instruction mix: a butterfly = modular add + modular sub + modular multiplication
+            # (gs_debug_butterfly_probe).  Butterflies of one prove: iNTT of T points + E coset transforms of T points, (n/2) log2 n each
+            bf_ms = C.c_float()
+            if L.gs_debug_butterfly_probe(ctx.handle, sm_count * 8, 2000, C.byref(bf_ms)) == 0 and bf_ms.value > 0 and grouped.get('ntt'):
+                bf_peak = sm_count * 8 * 256 * 2 * 2000.0 / (bf_ms.value * 1e-3)
+                rows = n_reg + sum(1 for s_ in air.static_registers if s_.kind == 'input')
+                n_bf = rows * (1 + ext) * (steps // 2) * log_t
+                a = n_bf / (grouped['ntt'] * 1e-3)
+                issue_roofline['ntt'] = {'unit': 'butterflies/s', 'achieved': a, 'peak': bf_peak, 'frac': a / bf_peak, 'probe_ms': bf_ms.value,
+                                         'butterflies_per_prove': n_bf}
 
-    trace_bytes = air.trace_register_count * steps * 16
-    value, e2e_val = ms_step, e2e_ms
+    trace_bytes = n_reg * steps * 16
     line = {
-        'metric': METRIC, 'value': value, 'unit': 'ms', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-        'ms_per_step': ms_step, 'higher_is_better': False, 'scaling': 'weak' if world == 1 else 'strong', 'vs_baseline': None,
-        'dtype': 'u128 (integer mod p = 2^128 - 9*2^32 + 1, 4x u32 limbs)', 'data': 'synthetic',
-        'config': {'workload': workload_name(), 'parallelism': 'single GPU' if world == 1 else f'one proof sharded over {world} GPUs by cosets ({EXT // world} of {EXT} cosets per rank); NCCL all-gather of digests at each Merkle commit, one all-reduce of queried rows; trace generation replicated on every host process',
-                   'l2': 'working set (>= 128 MiB per vector, ~1.4 GiB per prove) exceeds the 126 MB L2; no explicit flush',
+        'metric': METRICS[args.config], 'value': ms_step, 'unit': 'ms', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms_step, 'higher_is_better': False, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': DTYPE, 'data': 'synthetic',
+        'config': {'workload': desc,
+                   'value_excludes': 'execution-trace generation (the trace is resident in HBM when the timed region starts; e2e includes it)',
+                   'parallelism': 'single GPU' if world == 1 else f'one proof sharded over {world} GPUs by cosets ({ext // world} of {ext} cosets per rank); digest exchange at each Merkle commit, one all-reduce of queried rows; trace generation replicated on every host process',
+                   'l2': 'working set per prove exceeds the 126 MB L2 for the 2^20-step shapes; no explicit flush',
                    'proof_bytes': proof_len},
-        'e2e': {'value': e2e_val, 'unit': 'ms', 'h2d_bytes_per_step': trace_bytes + 4096, 'd2h_bytes_per_step': proof_len + 32 * 12,
+        'e2e': {'value': e2e_ms, 'unit': 'ms', 'h2d_bytes_per_step': trace_bytes + 4096, 'd2h_bytes_per_step': proof_len + 32 * 12,
                 'device_ms_inside': sum(d for d, _ in e2e_dev) / len(e2e_dev), 'host_ms_inside': sum(h for _, h in e2e_dev) / len(e2e_dev),
                 'stages_ms': stage_times},
+        'parity_sha256': want_sha, 'parity_ok': parity_ok,
+        'parity': {'oracle_sha256': want_sha, 'rank_sha256': all_sha, 'proofs_checked_per_rank': 3 * args.steps + 1,
+                   'how': 'SHA-256 of the proof bytes every rank returned in every timed leg vs the C oracle port (oracle/c) proving the same workload on the host',
+                   'note': oracle_note},
         'gpu_launches': int(launches_per_step),
         'roofline': roofline,
         'issue_roofline': issue_roofline,
@@ -451,6 +500,8 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default=os.environ.get('GS_BENCH_CONFIG', 'ns'), choices=sorted(METRICS))
+    ap.add_argument('--quick-ntt', action='store_true', help='NTT table at two sizes only (development runs)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

@@ -640,6 +640,46 @@ int gs_ntt_into(gs_ctx* c, const gs_mat* src, gs_mat* dst, gs_mat* work, int inv
                    log_n - log_t, inverse != 0);
 }
 
+int gs_lde_cosets_into(gs_ctx* c, const gs_mat* src, gs_mat* dst, gs_mat* work, int coset_base, int log_e_total) {
+    if (!c || !src || !dst || !work) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    const int log_t = ilog2_exact(src->cols), log_n = ilog2_exact(dst->cols);
+    if (log_t < 2 || log_n < log_t || dst->rows != src->rows || work->rows != dst->rows || work->cols != dst->cols)
+        return c->fail(GS_E_ARG, "shape mismatch");
+    const int log_e = log_n - log_t;
+    if (log_e_total < log_e || log_e_total < 1 || coset_base < 0 || coset_base + (1 << log_e) > (1 << log_e_total))
+        return c->fail(GS_E_ARG, "coset range outside the evaluation domain");
+    cudaSetDevice(c->device);
+    return ntt_run(c, src->data, src->cols, dst->data, dst->cols, work->data, dst->cols, (int)src->rows, log_t, log_e, false,
+                   coset_base, log_e_total);
+}
+
+namespace gs {
+__global__ void fill_random_kernel(fp* __restrict__ out, size_t n, unsigned long long seed) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long w[2];
+    for (int k = 0; k < 2; ++k) {                 // SplitMix64 at counter seed + 2i + k
+        unsigned long long z = seed + (2ull * i + k + 1ull) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        w[k] = z ^ (z >> 31);
+    }
+    fp v; v.v[0] = (uint32_t)w[0]; v.v[1] = (uint32_t)(w[0] >> 32); v.v[2] = (uint32_t)w[1]; v.v[3] = (uint32_t)(w[1] >> 32);
+    st_fp(out + i, fp_add(v, fp_zero()));         // the modular addition canonicalises (v < 2^128 < 2p)
+}
+}  // namespace gs
+
+int gs_mat_fill_random(gs_ctx* c, gs_mat* m, uint64_t seed) {
+    if (!c || !m) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    const size_t n = (size_t)m->rows * (size_t)m->cols;
+    if (!n) return GS_OK;
+    fill_random_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(m->data, n, seed);
+    GS_CUDA(c, cudaGetLastError());
+    c->launches++;
+    return GS_OK;
+}
+
 const char* gs_stark_compose_backend(gs_stark* s) {
     static thread_local std::string out;
     out = (s && s->compose_jit) ? s->compose_jit->status : std::string("interpreter");

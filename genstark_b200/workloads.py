@@ -69,6 +69,7 @@ CONFIGS = {
     '2': ('mimc', (1 << 13, 8), 'MiMC-128 prove(), 2^13 steps, extensionFactor 8, blake2s256, 48/24 queries (BASELINE config 2)'),
     '3': ('rescue', (128, 16), 'Rescue 4x128 hash chain prove(), 128 instances = 2^12 steps, 4 registers, extensionFactor 16, blake2s256, 68/24 queries (BASELINE config 3)'),
     '4': ('mimc', (1 << 20, 16), 'MiMC-128 prove(), 2^20 steps, extensionFactor 16, blake2s256, 48/24 queries (BASELINE config 4)'),
+    'test': ('mimc', (1 << 10, 8), 'MiMC-128 prove(), 2^10 steps, extensionFactor 8, blake2s256, 48/24 queries (the shape tests/test_bench_contract.py runs)'),
     '5': ('poseidon', (8, 128, 32), 'Poseidon Merkle-proof prove(), 128 branches of depth 8 = 2^16 steps, 12 registers, extensionFactor 32, blake2s256, 44/20 queries (BASELINE config 5)'),
 }
 

@@ -204,6 +204,12 @@ int gs_timer_end(gs_ctx* ctx, float* ms);
 /* transform src (rows x t) into dst (rows x n >= t) with caller-provided work (rows x n): n == t -> NTT or
  * (inverse) iNTT; n > t -> LDE.  No allocation: used to time K1 alone. */
 int gs_ntt_into(gs_ctx* ctx, const gs_mat* src, gs_mat* dst, gs_mat* work, int inverse);
+/* a rank's share of a coset-sharded LDE: src (rows x t) -> dst (rows x t*cosets), the `cosets` cosets starting at
+ * coset_base of the evaluation domain of size t * 2^log_e_total, local position q*cosets + (j - coset_base) (section 8e) */
+int gs_lde_cosets_into(gs_ctx* ctx, const gs_mat* src, gs_mat* dst, gs_mat* work, int coset_base, int log_e_total);
+/* fills m with uniform canonical residues from a counter-based generator (SplitMix64 of seed + 2*index, two draws
+ * -> 128 bits, reduced mod p): the synthetic NTT inputs of SURVEY.md section 8d, generated on the device */
+int gs_mat_fill_random(gs_ctx* ctx, gs_mat* m, uint64_t seed);
 /* runs blocks x 256 threads x (4*iters) dependent modular multiplications; returns kernel ms */
 int gs_debug_modmul_probe(gs_ctx* ctx, int blocks, int iters, float* ms_out);
 /* same for the NTT's instruction mix: blocks x 256 threads x 2 butterflies (u + v, (u - v) * w) x iters */

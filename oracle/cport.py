@@ -73,22 +73,3 @@ def prove(air, options, assertions, inputs=None, seed=None, threads=None, stages
     if stages is not None:
         stages.extend(zip(STAGES, list(st)[:len(STAGES)]))
     return data
-
-
-def time_mimc_prove(log_steps: int, ext: int, threads=None):
-    """(ms, threads used, 'c') for one prove of the bench workload."""
-    import bench
-    from genstark_b200 import airs
-    steps = 1 << log_steps
-    air = airs.mimc128(steps)
-    a = bench.mimc_assertions(steps)
-    L = lib()
-    if not threads:
-        # physical cores: hyper-threads do not help these memory-bound loops (measured: 128 threads slower than 64)
-        ncpu = os.cpu_count() or 1
-        threads = ncpu // 2 if ncpu > 16 else ncpu
-    L.oracle_set_threads(int(threads))
-    n = L.oracle_threads()
-    t = time.perf_counter()
-    prove(air, dict(bench.OPTS, extensionFactor=ext), a, [], [3])
-    return (time.perf_counter() - t) * 1e3, n, 'c'

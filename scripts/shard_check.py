@@ -1,5 +1,10 @@
-"""Coset-sharded proving on W GPUs of one box: W processes (one per GPU), NCCL all-gather at every Merkle commit.
-Checks that every rank returns the proof the oracle computes.  Usage: python scripts/shard_check.py W [log_steps] [E]"""
+"""Coset-sharded proving on W GPUs of one box: W processes (one per GPU), NCCL exchange at every Merkle commit.
+Checks that every rank returns the proof bytes the C oracle computes for the same workload.
+
+Usage: python scripts/shard_check.py W [config ...]
+  config = a key of genstark_b200.workloads.CONFIGS ('ns', '2', '3', '4', '5') or 'small' (MiMC 2^13 / E=8 and a
+  depth-2 Poseidon branch, the quick shapes).  Default: small."""
+import hashlib
 import multiprocessing as mp
 import os
 import sys
@@ -7,12 +12,19 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
 
-def worker(rank, world, id_path, case_name, args, out_q):
+def build_case(name):
+    from genstark_b200 import workloads
+    if name == 'small-mimc':
+        return workloads.mimc(1 << 13, 8)
+    if name == 'small-poseidon':
+        return workloads.poseidon(2, 1, 16)
+    return workloads.config(name)[:5]
+
+
+def worker(rank, world, id_path, case_name, out_q):
     try:
-        import cases
         from genstark_b200.field import Context
         from genstark_b200.stark import Stark
         ctx = Context(rank)
@@ -26,7 +38,7 @@ def worker(rank, world, id_path, case_name, args, out_q):
                 time.sleep(0.01)
             uid = open(id_path, 'rb').read()
         ctx.comm_init(rank, world, uid)
-        air, opts, a, inputs, seed = getattr(cases, case_name)(*args)
+        air, opts, a, inputs, seed = build_case(case_name)
         st = Stark(air, opts, context=ctx)
         proofs = [st.prove_bytes(a, inputs, seed) for _ in range(3)]
         t = time.perf_counter()
@@ -39,16 +51,16 @@ def worker(rank, world, id_path, case_name, args, out_q):
         out_q.put((rank, None, False, repr(e) + traceback.format_exc(), 0))
 
 
-def run(world, case_name, args, want=None):
+def run(world, case_name, want=None):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     id_path = f'/tmp/gs_nccl_id_{os.getpid()}_{case_name}_{world}'
     if os.path.exists(id_path):
         os.remove(id_path)
-    procs = [ctx.Process(target=worker, args=(r, world, id_path, case_name, args, q)) for r in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, id_path, case_name, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in range(world)]
+    res = [q.get(timeout=900) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
     res.sort(key=lambda x: x[0])
@@ -57,24 +69,29 @@ def run(world, case_name, args, want=None):
         if proof is None:
             print(f'rank {rank} FAILED: {ms}'); ok = False; continue
         same = (proof == res[0][1]) and (want is None or proof == want)
-        print(f'rank {rank}: {len(proof)} bytes, stable={stable}, same_as_expected={same}, e2e {ms:.2f} ms, device {dev:.2f} ms')
+        print(f'[{case_name} W={world}] rank {rank}: {len(proof)} bytes, sha256 {hashlib.sha256(proof).hexdigest()[:16]}, stable={stable}, '
+              f'equals_oracle={same}, e2e {ms:.2f} ms, device {dev:.2f} ms', flush=True)
         ok &= stable and same
     return ok, res[0][1]
 
 
-if __name__ == '__main__':
-    world = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-    log_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 13
-    e = int(sys.argv[3]) if len(sys.argv) > 3 else 8
-    import cases
+def main(argv):
+    world = int(argv[1]) if len(argv) > 1 else 2
+    names = argv[2:] or ['small']
+    cases = []
+    for n in names:
+        cases += ['small-mimc', 'small-poseidon'] if n == 'small' else [n]
     from oracle import cport
-    air, opts, a, inputs, seed = cases.mimc(1 << log_steps, e)
-    want = cport.prove(air, opts, a, inputs, seed)
-    ok, _ = run(world, 'mimc', (1 << log_steps, e), want)
-    if ok and log_steps <= 13:
-        air, opts, a, inputs, seed = cases.poseidon(2, 1, 16)
+    ok = True
+    for name in cases:
+        air, opts, a, inputs, seed = build_case(name)
+        t = time.perf_counter()
         want = cport.prove(air, opts, a, inputs, seed)
-        ok2, _ = run(world, 'poseidon', (2, 1, 16), want)
-        ok &= ok2
+        print(f'[{name}] C oracle proof: {len(want)} bytes, sha256 {hashlib.sha256(want).hexdigest()[:16]} ({time.perf_counter() - t:.1f} s)', flush=True)
+        ok &= run(world, name, want)[0]
     print('SHARD_CHECK', 'OK' if ok else 'FAILED')
-    sys.exit(0 if ok else 1)
+    return 0 if ok else 1
+
+
+if __name__ == '__main__':
+    sys.exit(main(sys.argv))

@@ -1,9 +1,9 @@
 """AirAssembly front-end (genstark_b200/assembly.py): source text -> AirModule.
 
-CPU tests.  The MiMC and sponge modules below are written for these tests; the lib128 checks read the
-library from the reference checkout when it is present (this container) and are skipped elsewhere --
-they reproduce examples/assembly/lib128.ts:51-118: the trace the component generates ends in the value
-an independent plain implementation computes."""
+CPU tests.  The MiMC and sponge modules below are written for these tests; the lib128 checks read the reference's
+own library file, kept verbatim as a fixture (tests/golden/lib128.aa = /root/reference/assembly/lib128.aa, so the tests
+also run on the GPU box where the reference checkout does not exist) -- they reproduce examples/assembly/lib128.ts:51-118:
+the trace the component generates ends in the value an independent plain implementation computes."""
 import os
 
 import pytest
@@ -14,8 +14,15 @@ from genstark_b200.stark import generate_execution_trace
 
 from asm_sources import MIMC_SOURCE, SPONGE_SOURCE, sponge_control, sponge_inputs
 
-LIB128 = '/root/reference/assembly/lib128.aa'
-needs_lib128 = pytest.mark.skipif(not os.path.exists(LIB128), reason='reference checkout not present')
+LIB128 = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'lib128.aa')
+needs_lib128 = pytest.mark.skipif(not os.path.exists(LIB128), reason='tests/golden/lib128.aa missing')
+
+
+def test_lib128_fixture_is_the_reference_file():
+    ref = '/root/reference/assembly/lib128.aa'
+    if not os.path.exists(ref):
+        pytest.skip('reference checkout not present (GPU box)')
+    assert open(ref, 'rb').read() == open(LIB128, 'rb').read()
 
 
 def test_sexpr_parser_handles_comments_and_nesting():

@@ -71,7 +71,9 @@ def test_unsupported_field_is_refused_loudly():
         instantiate(src, 'mimc', dict(extensionFactor=8))
 
 
-@pytest.mark.skipif(not os.path.exists('/root/reference/assembly/lib128.aa'), reason='reference checkout not present')
+LIB128 = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'lib128.aa')     # the reference's assembly/lib128.aa, verbatim
+
+
 def test_lib128_merkle_root_from_the_library_file():
     import random
     from test_assembly import _poseidon, _poseidon_params
@@ -91,10 +93,10 @@ def test_lib128_merkle_root_from_the_library_file():
     leaf = tree[0][index]
     inputs = [[leaf[0]], [leaf[1]], [[n[0] for n in nodes]], [[n[1] for n in nodes]], [bits]]
     opts = dict(hashAlgorithm='blake2s256', extensionFactor=32, exeQueryCount=44, friQueryCount=20)
-    st = instantiate('/root/reference/assembly/lib128.aa', 'ComputeMerkleRoot', opts)
+    st = instantiate(LIB128, 'ComputeMerkleRoot', opts)
     root = tree[-1][0]
     a = [dict(step=64 * depth - 1, register=0, value=root[0]), dict(step=64 * depth - 1, register=1, value=root[1])]
     got = st.prove_bytes(a, inputs)
     assert st.verify(a, got, [[bits]])
-    module = assembly.compile('/root/reference/assembly/lib128.aa').component('ComputeMerkleRoot').module_for(inputs)
+    module = assembly.compile(LIB128).component('ComputeMerkleRoot').module_for(inputs)
     assert got == cport.prove(module, opts, a, inputs, [])

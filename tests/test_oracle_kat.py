@@ -58,9 +58,8 @@ def test_poseidon_mds_kat():
     ys = [h(f'HadesMDSy{i}') for i in range(n)]
     mds00 = f.inv(f.sub(xs[0], ys[0]))
     import re
-    src = open('/root/reference/assembly/lib128.aa').read() if __import__('os').path.exists('/root/reference/assembly/lib128.aa') else None
-    if src is None:
-        pytest.skip('reference tree not present (GPU box)')
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'lib128.aa')).read()   # = assembly/lib128.aa
     first = int(re.search(r'\(const \$mds matrix\s*\(\s*(\d+)', src).group(1))
     assert first == mds00
 

@@ -74,11 +74,8 @@ def test_large_proofs_match_c_oracle_port(log_steps, e):
     """BASELINE sizes: the GPU proof is byte-identical to the plain-C oracle port (itself pinned to the Python
     restatement by tests/test_cport.py), which runs the reference's unfused data flow on the host cores."""
     from oracle import cport
-    import bench
-    steps = 1 << log_steps
-    air = airs.mimc128(steps)
-    opts = dict(OPTS, extensionFactor=e)
-    a = bench.mimc_assertions(steps)
+    from genstark_b200 import workloads
+    air, opts, a, _, _ = workloads.mimc(1 << log_steps, e)
     gpu = Stark(air, opts)
     got = gpu.prove_bytes(a, [], [3])
     want = cport.prove(air, opts, a, [], [3])
