@@ -25,6 +25,10 @@ def lib() -> C.CDLL:
     path = _build.LIB
     if not os.path.exists(path):
         path = _build.build()
+    # development: A/B another build of the same library (scripts/ build variants next to it); never a different implementation
+    alt = os.environ.get('GS_NATIVE_LIB')
+    if alt:
+        path = alt if os.path.isabs(alt) else os.path.join(os.path.dirname(_build.LIB), alt)
     L = C.CDLL(path)
     vp, i32, i64, u64, cp = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_char_p
     P = C.POINTER

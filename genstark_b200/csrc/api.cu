@@ -58,6 +58,7 @@ void gs_ctx_destroy(gs_ctx* c) {
     cudaStreamSynchronize(c->stream);
     cudaFree(c->tw_lo); cudaFree(c->tw_hi); cudaFree(c->tw_small);
     for (auto& kv : c->tw_tables) cudaFree(kv.second);
+    if (c->ntt2_xs) cudaFree(c->ntt2_xs);
     c->tw_tables.clear();
     if (c->scratch) cudaFree(c->scratch);
     if (c->counters) cudaFree(c->counters);

@@ -27,6 +27,7 @@ struct Ctx {
     // full twiddle tables of the NTT passes, built on first use per shape (ntt_host.cuh)
     std::map<unsigned long long, fp*> tw_tables;
     size_t tw_table_bytes = 0;
+    fp* ntt2_xs = nullptr;          // CTA-private running-product tiles of the two-pass LDE (ntt2.cuh), 2 * SMs * 64 KiB
     // scratch arena (grow on demand)
     void* scratch = nullptr;
     size_t scratch_bytes = 0;

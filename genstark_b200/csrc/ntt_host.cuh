@@ -3,6 +3,7 @@
 #include "core.cuh"
 #include <cstdlib>
 #include "ntt.cuh"
+#include "ntt2.cuh"
 
 namespace gs {
 
@@ -106,6 +107,102 @@ static inline const fp* ntt_table(Ctx* c, unsigned long long key, size_t entries
     return t;
 }
 
+// ------------------------------------------------------------------------------------------------ two-pass form (ntt2.cuh)
+static inline int ntt2_mode() {          // GS_NTT2 = 1 (default) | 0: keep the three-pass kernels of ntt.cuh for every size
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GS_NTT2"); v = e ? atoi(e) : 1; }
+    return v;
+}
+static inline const fp* ntt2_table(Ctx* c, unsigned long long key, const Ntt2Params& P, int kind, fp scale, int has_scale) {
+    auto it = c->tw_tables.find(key);
+    if (it != c->tw_tables.end()) return it->second;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(c->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
+    const size_t entries = (size_t)1 << P.log_t, bytes = entries * sizeof(fp);
+    fp* t = nullptr;
+    if (cudaMalloc(&t, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    const unsigned blocks = (unsigned)((entries + 255) / 256);
+    if (kind == 0) tw2_inter_table_kernel<<<blocks, 256, 0, c->stream>>>(P, scale, has_scale, t);
+    else tw2_step_table_kernel<<<blocks, 256, 0, c->stream>>>(P, t);
+    if (cudaGetLastError() != cudaSuccess) { cudaFree(t); return nullptr; }
+    c->launches++;
+    c->tw_tables[key] = t;
+    c->tw_table_bytes += bytes;
+    return t;
+}
+template <int LOG_R, bool LDE>
+static inline cudaError_t ntt2_launch_pass1(const Ntt2Params& P, unsigned grid, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(ntt2_pass1_kernel<LOG_R, LDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT2_SMEM); attr_set = true; }
+    ntt2_pass1_kernel<LOG_R, LDE><<<grid, 256, NTT2_SMEM, s>>>(P);
+    return cudaGetLastError();
+}
+template <int LOG_R>
+static inline cudaError_t ntt2_launch_pass2(const Ntt2Params& P, unsigned grid, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(ntt2_pass2_kernel<LOG_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT2_SMEM); attr_set = true; }
+    ntt2_pass2_kernel<LOG_R><<<grid, 256, NTT2_SMEM, s>>>(P);
+    return cudaGetLastError();
+}
+
+// returns GS_OK when the transform was launched, 1 when this shape is left to ntt_run's three-pass plan
+static inline int ntt2_try(Ctx* c, const fp* src, long long src_stride, fp* dst, long long dst_stride, fp* work, long long work_stride,
+                           int rows, int log_t, int log_e, bool inverse, int coset_base, int log_e_total) {
+    if (!ntt2_mode() || log_t < 16 || log_t > 20 || work == nullptr) return 1;
+    const bool lde = log_e_total > 0;
+    const int lr1 = (log_t + 1) / 2, lr2 = log_t / 2;
+    Ntt2Params P;
+    memset(&P, 0, sizeof P);
+    P.tw_small = c->tw_small; P.tw_lo = c->tw_lo; P.tw_hi = c->tw_hi; P.log_g = c->log_g; P.log_lo = c->log_lo;
+    P.inverse = inverse ? 1 : 0;
+    P.log_t = log_t; P.log_m = lr2; P.log_ntot = log_t + (lde ? log_e_total : 0);
+    P.n_cosets = 1 << log_e; P.log_cosets = log_e; P.coset_base = coset_base;
+    P.log_r1 = lr1;
+    // tables (built on the first, uncaptured use of a shape)
+    fp scale = fp_one();
+    if (inverse) scale = fp_from_u128(h_inv((u128)1 << log_t));
+    P.tw_inter = ntt2_table(c, 0x3000000ull | ((unsigned long long)log_t << 8) | (inverse ? 1 : 0), P, 0, scale, inverse ? 1 : 0);
+    if (!P.tw_inter) return 1;
+    if (lde) {
+        P.tw_step = ntt2_table(c, 0x4000000ull | ((unsigned long long)log_t << 8) | (unsigned long long)log_e_total, P, 1, scale, 0);
+        if (!P.tw_step) return 1;
+    }
+    const unsigned max_grid = 2u * (unsigned)c->sm_count;
+    if (lde && !c->ntt2_xs) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(c->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return 1; }
+        if (cudaMalloc(&c->ntt2_xs, (size_t)max_grid * 4096 * sizeof(fp)) != cudaSuccess) { cudaGetLastError(); c->ntt2_xs = nullptr; return 1; }
+    }
+    // ---- pass 1: src -> work[row][jl][k_1][n_2]
+    P.src = src; P.src_row_stride = src_stride;
+    P.dst = work; P.dst_row_stride = work_stride;
+    P.xs = c->ntt2_xs;
+    const int log_c1 = 12 - lr1;
+    P.units = (unsigned)rows << (lr2 - log_c1 + log_e);
+    unsigned grid = P.units < max_grid ? P.units : max_grid;
+    cudaError_t e;
+    {
+        ProfScope ps(c, lde ? "ntt_column_coset" : "ntt_column");
+        if (lde) e = lr1 == 10 ? ntt2_launch_pass1<10, true>(P, grid, c->stream) : lr1 == 9 ? ntt2_launch_pass1<9, true>(P, grid, c->stream) : ntt2_launch_pass1<8, true>(P, grid, c->stream);
+        else e = lr1 == 10 ? ntt2_launch_pass1<10, false>(P, grid, c->stream) : lr1 == 9 ? ntt2_launch_pass1<9, false>(P, grid, c->stream) : ntt2_launch_pass1<8, false>(P, grid, c->stream);
+        if (e != cudaSuccess) return c->cuda_fail(e, "ntt2_pass1_kernel");
+        c->launches++;
+    }
+    // ---- pass 2: work -> dst, natural order
+    P.src = work; P.src_row_stride = work_stride;
+    P.dst = dst; P.dst_row_stride = dst_stride;
+    const int log_c2 = 12 - lr2;
+    P.units = (unsigned)rows << (lr1 + log_e - log_c2);
+    grid = P.units < max_grid ? P.units : max_grid;
+    {
+        ProfScope ps(c, lde ? "ntt_final_lde" : (inverse ? "ntt_final_inv" : "ntt_final_fwd"));
+        e = lr2 == 10 ? ntt2_launch_pass2<10>(P, grid, c->stream) : lr2 == 9 ? ntt2_launch_pass2<9>(P, grid, c->stream) : ntt2_launch_pass2<8>(P, grid, c->stream);
+        if (e != cudaSuccess) return c->cuda_fail(e, "ntt2_pass2_kernel");
+        c->launches++;
+    }
+    return GS_OK;
+}
+
 // Transform `rows` vectors.
 //   log_t : log2 of the input length per row (the size of the DFTs actually computed)
 //   log_e : log2 of the pruned leading radix (0 = plain transform; >0 = evaluate on the domain of size
@@ -127,6 +224,10 @@ static inline int ntt_run(Ctx* c, const fp* src, long long src_stride, fp* dst, 
     }
     if (log_e_total > 0 && log_t < 2) return c->fail(GS_E_UNSUPPORTED, "LDE needs at least 4 coefficients");
     if (log_e_total > 0 && inverse) return c->fail(GS_E_UNSUPPORTED, "inverse coset transform");
+    {
+        const int rc2 = ntt2_try(c, src, src_stride, dst, dst_stride, work, work_stride, rows, log_t, log_e, inverse, coset_base, log_e_total);
+        if (rc2 != 1) return rc2;
+    }
     NttPlan plan = ntt_plan(log_t, log_e_total > 0);
     if (plan.n_pass > 1 && work == nullptr) return c->fail(GS_E_ARG, "work buffer required");
     int log_m = log_t;

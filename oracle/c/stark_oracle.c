@@ -724,6 +724,21 @@ int oracle_prove(const uint8_t* air_blob, int hash_alg, int exe_queries, int fri
 }
 
 void oracle_free(void* p) { free(p); }
+
+/* ORACLE (test infrastructure): the transforms of galois interpolateRoots / evalPolyAtRoots alone (lib/Stark.ts:106,109), for the
+ * element-by-element K1 parity tests at sizes the Python restatement cannot reach.  in: t = 2^log_t little-endian 16-byte residues;
+ * out: 2^log_n.  inverse != 0: interpolateRoots over the domain of size t (log_n == log_t); else evaluation of the zero-padded
+ * polynomial over the domain of size 2^log_n generated by `root` (16 bytes LE, the field's root of unity of that order). */
+int oracle_transform(const uint8_t* in, int log_t, int log_n, int inverse, const uint8_t* root_le, uint8_t* out) {
+    size_t t = (size_t)1 << log_t, n = (size_t)1 << log_n;
+    u128 root; memcpy(&root, root_le, 16);
+    u128* v;
+    if (inverse) { if (log_n != log_t) return -1; v = interpolate_roots((const u128*)in, log_t, root); }
+    else v = eval_poly_at_roots((const u128*)in, t, log_n, root);
+    memcpy(out, v, n * 16);
+    free(v);
+    return 0;
+}
 int oracle_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -37,6 +37,8 @@ def lib():
         L.oracle_free.argtypes = [C.c_void_p]
         L.oracle_threads.restype = C.c_int
         L.oracle_set_threads.argtypes = [C.c_int]
+        L.oracle_transform.restype = C.c_int
+        L.oracle_transform.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
         _lib = L
     return _lib
 
@@ -73,3 +75,14 @@ def prove(air, options, assertions, inputs=None, seed=None, threads=None, stages
     if stages is not None:
         stages.extend(zip(STAGES, list(st)[:len(STAGES)]))
     return data
+
+
+def transform(raw: bytes, log_t: int, log_n: int, inverse: bool = False) -> bytes:
+    """galois evalPolyAtRoots (zero-padded to 2^log_n) / interpolateRoots of one vector of 2^log_t little-endian residues"""
+    from oracle.field import PrimeField
+    from genstark_b200.air import P128
+    root = PrimeField(P128).get_root_of_unity(1 << log_n)
+    out = C.create_string_buffer(16 << log_n)
+    if lib().oracle_transform(raw, log_t, log_n, 1 if inverse else 0, root.to_bytes(16, 'little'), out) != 0:
+        raise RuntimeError('oracle_transform: bad arguments')
+    return out.raw

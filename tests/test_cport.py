@@ -25,3 +25,20 @@ def test_c_port_rejects_bad_assertion():
     air = airs.mimc128(64)
     with pytest.raises(RuntimeError, match='conflicts with execution trace'):
         cport.prove(air, opts, [dict(step=0, register=0, value=4)], [], [3])
+
+
+@pytest.mark.parametrize('log_t,log_n', [(3, 3), (6, 6), (5, 8), (10, 13), (12, 12)])
+def test_c_transform_equals_python_restatement(log_t, log_n):
+    """oracle_transform (what the large-size K1 parity tests compare with) against oracle/field.py"""
+    import random
+    from oracle.field import PrimeField
+    from genstark_b200.air import P128
+    OF = PrimeField(P128)
+    r = random.Random(log_t * 100 + log_n)
+    v = [r.randrange(P128) for _ in range(1 << log_t)]
+    raw = b''.join(x.to_bytes(16, 'little') for x in v)
+    got = cport.transform(raw, log_t, log_n)
+    dom = OF.get_power_series(OF.get_root_of_unity(1 << log_n), 1 << log_n)
+    assert [int.from_bytes(got[i:i + 16], 'little') for i in range(0, len(got), 16)] == OF.eval_polys_at_roots([v], dom)[0]
+    if log_t == log_n:
+        assert cport.transform(got, log_t, log_t, True) == raw
