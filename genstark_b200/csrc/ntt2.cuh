@@ -55,7 +55,7 @@ struct TileShape {
     __device__ static __forceinline__ int addr(int row, int c) { return row * C + c + ((LOG_R == 10) ? ((row >> 3) << 2) : 0); }
 };
 static constexpr int NTT2_X_ELEMS = 4096 + 512;           // exchange buffer (72 KB)
-static constexpr size_t NTT2_SMEM = (1024 + NTT2_X_ELEMS) * sizeof(fp);
+static constexpr size_t NTT2_SMEM = (1024 + NTT2_X_ELEMS) * sizeof(fp) + 64;      // + mbarriers of the TMA variants
 
 // The multiplication inside the tile code.  Inlined (default): ~80 instructions per site.  As a call (-DGS_NTT2_CALL_MUL) the code
 // shrinks 185 KB -> 82 KB and the "no instruction" stalls vanish, but the loads can no longer be hoisted across the calls and 11 %
@@ -187,6 +187,82 @@ GS_D void tile_final(const fp* X, const fp* s_tw, int t, F&& emit) {
     }
 }
 
+// tile_final with all 16 inputs of the thread read from X up front: after `after_loads` X is no longer needed by this thread,
+// which is what lets the next tile be prefetched into it (TMA variants below).  `mid` runs after the first group.
+template <int LOG_R, typename A, typename M, typename F>
+GS_D void tile_final_split(const fp* X, const fp* s_tw, int t, A&& after_loads, M&& mid, F&& emit) {
+    using S = TileShape<LOG_R>;
+    if (S::D3 == 0) {
+        const int k1 = t >> S::L3, cc = t & (S::C - 1);
+        fp y[16];
+#pragma unroll
+        for (int a2 = 0; a2 < 16; ++a2) y[a2] = ld_fp(&X[S::addr(k1 * 16 + a2, cc)]);
+        after_loads();
+        mid();
+        dif2<4>(y, s_tw, 10);
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) emit(k1 + 16 * k2, cc, y[brev<4>(k2)]);
+    } else {
+        constexpr int R3 = S::D3 > 0 ? S::R3 : 2, D3 = S::D3 > 0 ? S::D3 : 1;
+        constexpr int G3 = 16 / R3, GU = (S::R2 * S::C) / 32;
+        const int warp = t >> 5, lane = t & 31;
+        fp z[16];
+#pragma unroll
+        for (int g = 0; g < G3; ++g) {
+            const int k1 = (g / GU) * 8 + warp, u = (g % GU) * 32 + lane;
+            const int k2 = u >> S::LOG_C, cc = u & (S::C - 1);
+#pragma unroll
+            for (int a3 = 0; a3 < R3; ++a3) z[g * R3 + a3] = ld_fp(&X[S::addr((k1 * S::R2 + k2) * R3 + a3, cc)]);
+        }
+        after_loads();
+#pragma unroll
+        for (int g = 0; g < G3; ++g) {
+            const int k1 = (g / GU) * 8 + warp, u = (g % GU) * 32 + lane;
+            const int k2 = u >> S::LOG_C, cc = u & (S::C - 1);
+            fp w[R3];
+#pragma unroll
+            for (int a3 = 0; a3 < R3; ++a3) w[a3] = z[g * R3 + a3];
+            dif2<D3>(w, s_tw, 10);
+            if (g == 0) mid();
+#pragma unroll
+            for (int k3 = 0; k3 < R3; ++k3) emit(k1 + 16 * k2 + 16 * S::R2 * k3, cc, w[brev<D3>(k3)]);
+        }
+    }
+}
+
+// ---- mbarrier / bulk-copy (TMA) primitives ---------------------------------------------------------------------------
+GS_D unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+GS_D void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+GS_D void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+GS_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+GS_D void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+GS_D void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+GS_D void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier
+GS_D void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 3-D tensor-map tile load (cuTensorMapEncodeTiled on the host): box lands dense, row-major
+GS_D void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
 GS_D void ntt2_load_small_table(fp* s_tw, const fp* tw_small, int inverse) {
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
         unsigned e = (unsigned)i;
@@ -283,6 +359,58 @@ __global__ void __launch_bounds__(256, 2) ntt2_pass2_kernel(const Ntt2Params P) 
         tile_front<LOG_R>(x, X, s_tw, t);
         fp* dst = P.dst + (long long)row * P.dst_row_stride + ucol0;
         tile_final<LOG_R>(X, s_tw, t, [&](int k, int cc, fp v) { st_fp(dst + ((size_t)k << log_ucols) + cc, v); });
+    }
+}
+
+// pass 2 with the next tile prefetched by bulk copies (TMA engine) into the exchange buffer while the last radix of the current
+// tile computes: one elected thread arms `full` with the byte count and issues C row copies; every thread arrives on `empty`
+// once its last reads of X are in registers.
+template <int LOG_R>
+__global__ void __launch_bounds__(256, 2) ntt2_pass2_tma_kernel(const Ntt2Params P) {
+    using S = TileShape<LOG_R>;
+    constexpr int R = 1 << LOG_R, PITCH = R + 2;          // landing pitch: 32 B of padding keeps the column reads off one bank
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fp* s_tw = reinterpret_cast<fp*>(smem_raw);
+    fp* X = s_tw + 1024;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(X + NTT2_X_ELEMS);      // [0] full, [1] empty
+    const int t = threadIdx.x;
+    ntt2_load_small_table(s_tw, P.tw_small, P.inverse);
+    const int rest = t >> S::LOG_C, c = t & (S::C - 1);
+    const unsigned u_begin = (unsigned)(((unsigned long long)P.units * blockIdx.x) / gridDim.x);
+    const unsigned u_end = (unsigned)(((unsigned long long)P.units * (blockIdx.x + 1)) / gridDim.x);
+    const int log_ucols = P.log_r1 + P.log_cosets;
+    const int log_tiles = log_ucols - S::LOG_C;
+    if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 256); mbar_fence_init(); }
+    __syncthreads();
+    auto issue = [&](unsigned u) {
+        const unsigned tile = u & ((1u << log_tiles) - 1u), row = u >> log_tiles;
+        const unsigned ucol0 = tile << S::LOG_C;
+        fence_proxy_async();
+        mbar_expect_tx(&bars[0], 4096u * 16u);
+#pragma unroll 1
+        for (int cc = 0; cc < S::C; ++cc) {
+            const unsigned ucol = ucol0 + cc;
+            const unsigned jl = ucol & ((1u << P.log_cosets) - 1u), k1p = ucol >> P.log_cosets;
+            const fp* src = P.src + (long long)row * P.src_row_stride + ((size_t)jl << P.log_t) + ((size_t)k1p << LOG_R);
+            bulk_g2s(X + cc * PITCH, src, R * 16u, &bars[0]);
+        }
+    };
+    if (t == 0 && u_begin < u_end) issue(u_begin);
+    unsigned phase = 0;
+    for (unsigned u = u_begin; u < u_end; ++u) {
+        const unsigned tile = u & ((1u << log_tiles) - 1u), row = u >> log_tiles;
+        const unsigned ucol0 = tile << S::LOG_C;
+        mbar_wait(&bars[0], phase);
+        fp x[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a) x[a] = ld_fp(X + c * PITCH + a * S::RR + rest);
+        tile_front<LOG_R>(x, X, s_tw, t);                  // its first barrier: every thread holds its inputs, X is free for the exchange
+        fp* dst = P.dst + (long long)row * P.dst_row_stride + ucol0;
+        tile_final_split<LOG_R>(X, s_tw, t,
+            [&]() { mbar_arrive(&bars[1]); },
+            [&]() { if (t == 0 && u + 1 < u_end) { mbar_wait(&bars[1], phase); issue(u + 1); } },
+            [&](int k, int cc, fp v) { st_fp(dst + ((size_t)k << log_ucols) + cc, v); });
+        phase ^= 1u;
     }
 }
 

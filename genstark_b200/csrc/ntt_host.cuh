@@ -137,8 +137,21 @@ static inline cudaError_t ntt2_launch_pass1(const Ntt2Params& P, unsigned grid, 
     ntt2_pass1_kernel<LOG_R, LDE><<<grid, 256, NTT2_SMEM, s>>>(P);
     return cudaGetLastError();
 }
+static inline int ntt2_tma_mode() {      // GS_NTT2_TMA bit 0 (default on): pass 2 prefetches its tiles with bulk copies (TMA engine); 0 = plain loads
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GS_NTT2_TMA"); v = e ? atoi(e) : 1; }
+    return v;
+}
+template <int LOG_R>
+static inline cudaError_t ntt2_launch_pass2_tma(const Ntt2Params& P, unsigned grid, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(ntt2_pass2_tma_kernel<LOG_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT2_SMEM); attr_set = true; }
+    ntt2_pass2_tma_kernel<LOG_R><<<grid, 256, NTT2_SMEM, s>>>(P);
+    return cudaGetLastError();
+}
 template <int LOG_R>
 static inline cudaError_t ntt2_launch_pass2(const Ntt2Params& P, unsigned grid, cudaStream_t s) {
+    if (ntt2_tma_mode() & 1) return ntt2_launch_pass2_tma<LOG_R>(P, grid, s);
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(ntt2_pass2_kernel<LOG_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT2_SMEM); attr_set = true; }
     ntt2_pass2_kernel<LOG_R><<<grid, 256, NTT2_SMEM, s>>>(P);
