@@ -681,6 +681,8 @@ int gs_mat_fill_random(gs_ctx* c, gs_mat* m, uint64_t seed) {
     return GS_OK;
 }
 
+const char* gs_stark_last_error(gs_stark* s) { return (s && s->ctx) ? s->ctx->last_error.c_str() : ""; }
+
 const char* gs_stark_compose_backend(gs_stark* s) {
     static thread_local std::string out;
     out = (s && s->compose_jit) ? s->compose_jit->status : std::string("interpreter");

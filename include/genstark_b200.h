@@ -189,6 +189,8 @@ int gs_stark_verify(const uint8_t* air_blob, size_t blob_len, int hash_alg, int 
 /* which constraint-evaluation kernel this instance launches: "nvrtc <hash>" (the AIR's evaluation function compiled
  * to sm_100a code at creation, as air-assembly compiles it to JavaScript) or "interpreter (<reason>)".
  * GS_COMPOSE_JIT=0 forces the interpreting kernel; results are identical. */
+/* message of the last failure on the context this instance lives on (what a binding throws for a negative status) */
+const char* gs_stark_last_error(gs_stark* s);
 const char* gs_stark_compose_backend(gs_stark* s);
 const char* gs_stark_stage_times(gs_stark* s);
 /* test hooks: keep C(x) and read device-resident intermediates back (0 P evals, 1 C, 2 L, 3 P polys) */
