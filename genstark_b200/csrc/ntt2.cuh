@@ -269,6 +269,7 @@ GS_D void ntt2_load_small_table(fp* s_tw, const fp* tw_small, int inverse) {
         if (inverse) e = (1024u - e) & 1023u;
         s_tw[i] = ldg_fp(tw_small + e);
     }
+    __syncthreads();                                      // the first radix-16 of the first unit reads entries other threads wrote
 }
 
 // ---------------------------------------------------------------------------------------------- pass 1
