@@ -53,9 +53,13 @@ GS_D uint32_t b2s_add3(uint32_t a, uint32_t b, uint32_t x, uint32_t one) {
     a = b2s_add3(a, b, (y), one); d = __byte_perm(d ^ a, 0, 0x0321); \
     c = c + d; b = rotr32(b ^ c, 7);
 
-// one compression; sigma is fully unrolled so message words stay in registers
+// one compression; sigma is fully unrolled so message words stay in registers.  LAT: the latency-bound callers (tree tops, the
+// FRI tail: a handful of warps walking a chain of dependent compressions) take the plain three-input addition -- the
+// multiplier is a literal 1 there, ptxas folds the two multiply-adds back into one IADD3 and the dependency chain of a G
+// function is two operations shorter; pipe balance only matters when the SM is full.
+template <bool LAT = false>
 GS_D void blake2s_compress(uint32_t (&h)[8], const uint32_t (&m)[16], uint32_t t0, bool last) {
-    const uint32_t one = GS_B2S_ONE;
+    const uint32_t one = LAT ? 1u : GS_B2S_ONE;
     uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
     uint32_t v8 = B2S_IV0, v9 = B2S_IV1, v10 = B2S_IV2, v11 = B2S_IV3;
     uint32_t v12 = B2S_IV4 ^ t0, v13 = B2S_IV5, v14 = last ? ~B2S_IV6 : B2S_IV6, v15 = B2S_IV7;
@@ -125,7 +129,7 @@ GS_D uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
 // ------------------------------------------------------------------------------ message -> digest
 // Hash a message given as `nwords` little-endian 32-bit words produced by `get(w)` (nwords % 4 == 0).
-template <int ALG, typename Get>
+template <int ALG, bool LAT = false, typename Get>
 GS_D void hash_words(Get get, int nwords, uint32_t (&out)[8]) {
     uint32_t h[8];
     if (ALG == HASH_BLAKE2S) {
@@ -136,7 +140,7 @@ GS_D void hash_words(Get get, int nwords, uint32_t (&out)[8]) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) { const int w = b * 16 + i; m[i] = (w < nwords) ? get(w) : 0u; }
             const bool last = (b == nblocks - 1);
-            blake2s_compress(h, m, last ? (uint32_t)nwords * 4u : (uint32_t)(b + 1) * 64u, last);
+            blake2s_compress<LAT>(h, m, last ? (uint32_t)nwords * 4u : (uint32_t)(b + 1) * 64u, last);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) out[i] = h[i];
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ 
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { uint4 t = s[4 * j + q]; m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
                 auto getm = [&](int w) -> uint32_t { return m[w]; };
-                hash_words<ALG>(getm, 16, d);
+                hash_words<ALG, true>(getm, 16, d);
             }
             __syncthreads();
             if (j < cnt) {
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(1024) merkle_tail_kernel(uint32_t* __restrict_
             for (int q = 0; q < 4; ++q) { uint4 t = ch[q]; m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
             uint32_t d[8];
             auto getm = [&](int w) -> uint32_t { return m[w]; };
-            hash_words<ALG>(getm, 16, d);
+            hash_words<ALG, true>(getm, 16, d);
             store_digest(nodes + 8 * i, d);
         }
         __syncthreads();

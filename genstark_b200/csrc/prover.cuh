@@ -13,6 +13,7 @@
 #include "batchinv.cuh"
 #include "fri.cuh"
 #include "compose.cuh"
+#include "coeffs.cuh"
 #include "devjit.cuh"
 #include "hostcrypto.h"
 #include "hostfield.h"
@@ -277,6 +278,127 @@ static inline std::vector<uint32_t> first_seen_unique(const std::vector<uint32_t
     return out;
 }
 
+// The tail of the FRI layer chain in ONE launch (LowDegreeProver.ts:176-221 for the layers of at most 2^GS_FRI_TAIL_LOG values).
+// Those layers are pure latency: per layer a row-hash launch, a tree launch (one dependent compression per level), a one-thread
+// SHA-256 for the challenge and a fold launch -- 27-40 us each for a few thousand hashes.  One block walks them all: row hashes,
+// the tree level by level, x* = prng(root), the fold, with block barriers in between; roots, epoch flags and the remainder are
+// written straight into the pinned mailbox (host-mapped), system-fenced, so the host plans the queries behind them as before.
+// Same buffers and layouts as the per-layer kernels, so the query phase does not know the difference.
+struct FriTailParams {
+    fp* v; fp* v_next; uint32_t* trees;
+    int log_l0, depth0, log_n;
+    const fp* tw_lo; const fp* tw_hi; int log_g, log_lo;
+    fp iota_inv, quarter_inv;
+    uint32_t* mb_root; uint32_t* mb_flag; fp* mb_rem;       // pinned host memory (unified addressing)
+    const uint32_t* epoch;
+};
+
+GS_D fp fri_challenge_dev(const uint32_t* root) {
+    uint32_t d[8];
+    auto get = [&](int w) -> uint32_t { return root[w]; };
+    hash_words<HASH_SHA256>(get, 8, d);
+    uint32_t be[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) be[i] = bswap32(d[i]);
+    fp hi, lo;
+    hi.v[3] = be[0]; hi.v[2] = be[1]; hi.v[1] = be[2]; hi.v[0] = be[3];
+    lo.v[3] = be[4]; lo.v[2] = be[5]; lo.v[1] = be[6]; lo.v[0] = be[7];
+    const fp zero = fp_zero();
+    hi = fp_add(hi, zero); lo = fp_add(lo, zero);
+    fp c9; c9.v[0] = 0xFFFFFFFFu; c9.v[1] = 8u; c9.v[2] = 0; c9.v[3] = 0;
+    return fp_add(lo, fp_mul(hi, c9));
+}
+
+// digests of a level live in shared memory (ping-pong between two buffers: one block barrier per tree level, children read
+// at shared-memory latency); every node is also stored to the tree in HBM, where the query phase reads authentication paths
+template <int ALG>
+__global__ void __launch_bounds__(512) fri_tail_kernel(const FriTailParams P) {
+    extern __shared__ __align__(16) unsigned char tail_smem[];
+    __shared__ fp s_x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    fp* v = P.v; fp* vn = P.v_next; uint32_t* tree = P.trees;
+    const unsigned g_mask = (1u << P.log_g) - 1u;
+    const uint32_t epoch = *P.epoch;
+    const int q0 = (1 << P.log_l0) >> 2;
+    uint4* buf_a = reinterpret_cast<uint4*>(tail_smem);           // q0 digests
+    uint4* buf_b = buf_a + 2 * q0;                                // q0 / 2 digests
+    int depth = P.depth0;
+    for (int L = 1 << P.log_l0;; L >>= 2, ++depth) {
+        const int Q = L >> 2;
+        for (int i = tid; i < Q; i += nthr) {                 // row hashes: H(v[i] || v[i+Q] || v[i+2Q] || v[i+3Q])
+            uint32_t m[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const fp e = ld_fp(v + i + c * Q); m[4 * c] = e.v[0]; m[4 * c + 1] = e.v[1]; m[4 * c + 2] = e.v[2]; m[4 * c + 3] = e.v[3]; }
+            uint32_t d[8];
+            auto getm = [&](int w) -> uint32_t { return m[w]; };
+            hash_words<ALG, true>(getm, 16, d);
+            buf_a[2 * i] = make_uint4(d[0], d[1], d[2], d[3]); buf_a[2 * i + 1] = make_uint4(d[4], d[5], d[6], d[7]);
+            store_digest(tree + 8 * (size_t)(Q + i), d);
+        }
+        __syncthreads();
+        uint4* src = buf_a; uint4* dst = buf_b;
+        for (int c = Q >> 1; c >= 1; c >>= 1) {               // tree levels: parents c .. 2c-1 from children in src
+            for (int j = tid; j < c; j += nthr) {
+                uint32_t m[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const uint4 t = src[4 * j + q]; m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
+                uint32_t d[8];
+                auto getm = [&](int w) -> uint32_t { return m[w]; };
+                hash_words<ALG, true>(getm, 16, d);
+                dst[2 * j] = make_uint4(d[0], d[1], d[2], d[3]); dst[2 * j + 1] = make_uint4(d[4], d[5], d[6], d[7]);
+                store_digest(tree + 8 * (size_t)(c + j), d);
+            }
+            __syncthreads();
+            uint4* tmp = src; src = dst; dst = tmp;
+        }
+        // src[0..1] = root (Q >= 2 always: L >= 8 on this path)
+        const uint32_t* root = reinterpret_cast<const uint32_t*>(src);
+        if (tid < 8) { P.mb_root[8 * depth + tid] = root[tid]; __threadfence_system(); }
+        if (L <= 256) {
+            for (int i = tid; i < L; i += nthr) { st_fp(P.mb_rem + i, ld_fp(v + i)); }
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) { P.mb_flag[depth] = epoch; __threadfence_system(); }
+            return;
+        }
+        if (tid == 0) s_x = fri_challenge_dev(root);
+        __syncthreads();
+        if (tid == 0) { P.mb_flag[depth] = epoch; __threadfence_system(); }
+        const fp xs = s_x;
+        const int x_shift = 2 * depth + (P.log_g - P.log_n);
+        for (int i = tid; i < Q; i += nthr) {
+            const fp y0 = ld_fp(v + i), y1 = ld_fp(v + i + Q), y2 = ld_fp(v + i + 2 * Q), y3 = ld_fp(v + i + 3 * Q);
+            const unsigned e = (0u - ((unsigned)i << x_shift)) & g_mask;
+            fp xinv = ldg_fp(P.tw_lo + (e & ((1u << P.log_lo) - 1u)));
+            if (P.log_g > P.log_lo) xinv = fp_mul(xinv, ldg_fp(P.tw_hi + (e >> P.log_lo)));
+            const fp t = fp_mul(xs, xinv);
+            const fp s02 = fp_add(y0, y2), d02 = fp_sub(y0, y2);
+            const fp s13 = fp_add(y1, y3), d13 = fp_mul(fp_sub(y1, y3), P.iota_inv);
+            const fp c0 = fp_add(s02, s13), c2 = fp_sub(s02, s13);
+            const fp c1 = fp_add(d02, d13), c3 = fp_sub(d02, d13);
+            fp acc = fp_add(fp_mul(c3, t), c2);
+            acc = fp_add(fp_mul(acc, t), c1);
+            acc = fp_add(fp_mul(acc, t), c0);
+            st_fp(vn + i, fp_mul(acc, P.quarter_inv));
+        }
+        __syncthreads();
+        tree += (size_t)2 * Q * 8; v = vn; vn += Q;
+    }
+}
+template <int ALG>
+static inline cudaError_t fri_tail_launch(const FriTailParams& F, cudaStream_t st) {
+    const size_t smem = ((size_t)1 << F.log_l0) / 4 * 48;        // q0 * 32 (buffer A) + q0 * 16 (buffer B)
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(fri_tail_kernel<ALG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+    fri_tail_kernel<ALG><<<1, 512, smem, st>>>(F);
+    return cudaGetLastError();
+}
+static inline int fri_tail_log() {       // layers of at most 2^this many values go to fri_tail_kernel; GS_FRI_TAIL_LOG=0: none
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GS_FRI_TAIL_LOG"); v = e ? atoi(e) : 11; if (v > 14) v = 14; if (v < 0) v = 0; }        // 2^14 values: 4096 rows, 192 KB of digests
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------- prove
 // inputs: initial state (R elements), input register traces (n_input x T, register order), shapes blob
 static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, const u128* init_state,
@@ -485,39 +607,17 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         u128 a = 1; for (long long j = 0; j < E; ++j) { delta_tab[j] = a; a = h_mul(a, base); }
     }
     uint8_t ev_root[32];
-    GS_CUDA(c, cudaStreamSynchronize(c->stream));
-    memcpy(ev_root, c->mailbox, 32);
-    mark("Built evaluation merkle tree", false);
-    // one draw covers the composition coefficients (:58-60) and the linear-combination coefficients, which continue
-    // the same stream (LinearCombination.ts:58-59, Stark.ts:129)
-    const std::vector<u128> lc_all = prng_many(ev_root, 32, d_count + b_count + lc_total);
-    const std::vector<u128>& coeffs = lc_all;
-    std::vector<fp> dk(K), dk_adj(K, fp_zero());
-    for (int k = 0; k < K; ++k) { dk[k] = fp_from_u128(coeffs[k]); if (adj_idx[k] >= 0) dk_adj[k] = fp_from_u128(coeffs[adj_idx[k]]); }
-    std::vector<fp> bk(nB), bk_adj(nB, fp_zero());
-    for (int b = 0; b < nB; ++b) { bk[b] = fp_from_u128(coeffs[d_count + b]); if (comp_degree > T) bk_adj[b] = fp_from_u128(coeffs[d_count + nB + b]); }
-    std::vector<fp> lk(n_lc), lk_adj(n_lc, fp_zero());
-    for (int j = 0; j < n_lc; ++j) { lk[j] = fp_from_u128(lc_all[d_count + b_count + j]); if (delta > 0) lk_adj[j] = fp_from_u128(lc_all[d_count + b_count + n_lc + j]); }
-
-    std::vector<fp> cd_tab((size_t)K * E), pf_tab(pf_coef.size() * E), lk_tab((size_t)n_lc * E);
-    for (int k = 0; k < K; ++k)
-        for (long long j = 0; j < E; ++j) {
-            u128 v = fp_to_u128(dk[k]);
-            if (pow_idx[k] >= 0) v = h_add(v, h_mul(fp_to_u128(dk_adj[k]), pow_tab[(size_t)pow_idx[k] * E + j]));
-            cd_tab[(size_t)k * E + j] = fp_from_u128(h_mul(v, inv_num[j]));
-        }
-    for (size_t a = 0; a < pf_coef.size(); ++a)
-        for (long long j = 0; j < E; ++j) {
-            u128 v = fp_to_u128(bk[pf_owner[a]]);
-            if (delta > 0) v = h_add(v, h_mul(fp_to_u128(bk_adj[pf_owner[a]]), delta_tab[j]));
-            pf_tab[a * E + j] = fp_from_u128(h_mul(v, pf_coef[a]));
-        }
-    for (int q = 0; q < n_lc; ++q)
-        for (long long j = 0; j < E; ++j) {
-            u128 v = fp_to_u128(lk[q]);
-            if (delta > 0) v = h_add(v, h_mul(fp_to_u128(lk_adj[q]), delta_tab[j]));
-            lk_tab[(size_t)q * E + j] = fp_from_u128(v);
-        }
+    mark("Built evaluation merkle tree", timing);
+    // The random coefficients (one draw covers the composition coefficients, :58-60, and the linear-combination coefficients,
+    // which continue the same stream: LinearCombination.ts:58-59, Stark.ts:129) are drawn from the evaluation root ON THE DEVICE
+    // (coeffs.cuh) and folded there with the E-periodic factors into cd_tab / pf_tab / lk_tab: no host round trip sits between
+    // the commit chain and compose + FRI.  The host reads the root at the end, for the proof bytes.
+    std::vector<fp> inv_num_fp(E), pow_tab_fp(pow_tab.size()), delta_tab_fp(E), pf_coef_fp(pf_coef.size());
+    for (long long j = 0; j < E; ++j) { inv_num_fp[j] = fp_from_u128(inv_num[j]); delta_tab_fp[j] = fp_from_u128(delta_tab[j]); }
+    for (size_t i = 0; i < pow_tab.size(); ++i) pow_tab_fp[i] = fp_from_u128(pow_tab[i]);
+    for (size_t i = 0; i < pf_coef.size(); ++i) pf_coef_fp[i] = fp_from_u128(pf_coef[i]);
+    const size_t n_cd = (size_t)K * E, n_pf_tab = pf_coef.size() * E, n_lk = (size_t)n_lc * E;
+    const std::vector<fp> cd_tab(n_cd, fp_zero()), pf_tab(n_pf_tab, fp_zero()), lk_tab(n_lk, fp_zero());     // filled by derive_coeffs_kernel
     // small-object upload: one packed buffer
     std::vector<uint8_t> small;
     auto put = [&](const void* p, size_t n) { size_t off = (small.size() + 15) & ~(size_t)15; small.resize(off + n); memcpy(small.data() + off, p, n); return off; };
@@ -527,9 +627,27 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     const size_t o_ip = put(ipoly.data(), ipoly.size() * 16), o_ps = put(pf_shift.data(), pf_shift.size() * 4);
     const size_t o_io = put(ioff.data(), nB * 4), o_il = put(ilen.data(), nB * 4), o_po = put(pfoff.data(), nB * 4), o_pl = put(pflen.data(), nB * 4);
     const size_t o_br = put(breg.data(), nB * 4);
+    const size_t o_inv = put(inv_num_fp.data(), inv_num_fp.size() * 16), o_pow = put(pow_tab_fp.data(), pow_tab_fp.size() * 16),
+                 o_dl = put(delta_tab_fp.data(), delta_tab_fp.size() * 16), o_pc = put(pf_coef_fp.data(), pf_coef_fp.size() * 16),
+                 o_pw = put(pf_owner.data(), pf_owner.size() * 4), o_pi = put(pow_idx.data(), K * 4), o_ai = put(adj_idx.data(), K * 4);
     if (small.size() + 64 > S->d_small.cap) return c->fail(GS_E_UNSUPPORTED, "too many assertions / constraints for the parameter block");
     uint8_t* ds = S->d_small.as<uint8_t>();
     GS_CUDA(c, cudaMemcpyAsync(ds, small.data(), small.size(), cudaMemcpyHostToDevice, c->stream));
+    {
+        CoeffParams Q; memset(&Q, 0, sizeof Q);
+        Q.root = e_tree + 8;
+        Q.K = K; Q.nB = nB; Q.n_lc = n_lc; Q.n_pf = (int)pf_coef.size(); Q.E = (int)E;
+        Q.d_count = d_count; Q.b_count = b_count; Q.has_delta = delta > 0 ? 1 : 0; Q.comp_gt_t = comp_degree > T ? 1 : 0;
+        Q.pow_idx = (const int*)(ds + o_pi); Q.adj_idx = (const int*)(ds + o_ai);
+        Q.inv_num = (const fp*)(ds + o_inv); Q.pow_tab = (const fp*)(ds + o_pow); Q.delta_tab = (const fp*)(ds + o_dl);
+        Q.pf_coef = (const fp*)(ds + o_pc); Q.pf_owner = (const int*)(ds + o_pw);
+        Q.cd_tab = (fp*)(ds + o_cd); Q.pf_tab = (fp*)(ds + o_pf); Q.lk_tab = (fp*)(ds + o_lk);
+        Q.count = d_count + b_count + lc_total;
+        if ((size_t)Q.count * 16 > 40 * 1024) return c->fail(GS_E_UNSUPPORTED, "too many random coefficients (%d)", Q.count);
+        derive_coeffs_kernel<<<1, 256, (size_t)Q.count * 16, c->stream>>>(Q);
+        GS_CUDA(c, cudaGetLastError());
+        c->launches++;
+    }
     {
         ComposeParams P; memset(&P, 0, sizeof P);
         P.n = N; P.log_n = log_n; P.log_e = log_e; P.n_loc = NL; P.log_el = log_el; P.j0 = sh.j0();
@@ -556,15 +674,16 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     // 5b-7 ---- compose + the whole FRI layer chain (second captured region)
     std::vector<FriLayer> layers;
     uint8_t* mb = (uint8_t*)c->mailbox;
-    // mailbox layout: [0, 32) evaluation root, then the compose fail flag; [1024, 1792) FRI layer roots; [2048, 2144) one
+    // mailbox layout: [0, 32) evaluation root, [32, 40) the compose fail flag; [1024, 1792) FRI layer roots; [2048, 2144) one
     // epoch flag per layer; [4096, 8192) remainder; [8192, ...) gathered query data
     const size_t MB_ROOT = 1024, MB_FLAG = 2048, MB_REM = 4096;
     int n_layers = 0;
     // epoch flag: the chain copies it to the mailbox right behind each layer root; the host polls for it
     // (events recorded inside a captured graph cannot be synchronised from the host).  The mailbox belongs to the
     // context, which several Stark instances share, and a prove can fail half way: the epoch counts every ATTEMPT on
-    // the context (never a value an earlier prove left behind) and the flag / root slots are cleared first -- the
-    // stream is idle here (synchronised for the evaluation root above).
+    // the context (never a value an earlier prove left behind) and the flag / root slots are cleared first -- nothing
+    // in flight writes them: the previous prove was synchronised to its end and this prove's commit chain only writes
+    // mailbox[0, 32).
     if (++c->prove_epoch == 0) ++c->prove_epoch;
     const uint32_t epoch = c->prove_epoch;
     memset(mb + MB_ROOT, 0, 32 * 24);
@@ -591,7 +710,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         c->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return c->cuda_fail(e, "compose_kernel");
-        GS_CUDA(c, cudaMemcpyAsync(c->mailbox, ds + o_flag, 8, cudaMemcpyDeviceToHost, c->stream));
+        GS_CUDA(c, cudaMemcpyAsync((uint8_t*)c->mailbox + 32, ds + o_flag, 8, cudaMemcpyDeviceToHost, c->stream));
         }
     // 7 ---- low-degree proof (LowDegreeProver.ts:39-68,176-221)
     const u128 iota_inv = h_inv(c->root_of_order(2));
@@ -602,10 +721,32 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     fp* v_cur = S->d_l.as<fp>();
     // The whole layer chain is enqueued without host round trips: each challenge x* = prng(root_d) is derived on
     // the device; roots are copied to mailbox slots as they appear and the host plans the queries behind them.
+    bool in_tail = false;
     for (int depth = 0;; ++depth) {
         const long long L = N >> (2 * depth), Q = L >> 2;
         const long long QL = (NL >> (2 * depth)) >> 2;          // rows of this layer owned by this rank
         FriLayer ly; ly.v = v_cur; ly.len = L; ly.tree = t_next; ly.split = false; t_next += (size_t)2 * Q * 8;
+        if (in_tail || (!sharded && fri_tail_log() >= 8 && L <= (1ll << fri_tail_log()))) {
+            if (!in_tail) {
+                in_tail = true;
+                if (depth >= 24) return c->fail(GS_E_UNSUPPORTED, "too many FRI layers");
+                FriTailParams F; memset(&F, 0, sizeof F);
+                F.v = v_cur; F.v_next = v_next; F.trees = ly.tree;
+                int ll = 0; while ((1ll << ll) < L) ++ll;
+                F.log_l0 = ll; F.depth0 = depth; F.log_n = log_n;
+                F.tw_lo = c->tw_lo; F.tw_hi = c->tw_hi; F.log_g = c->log_g; F.log_lo = c->log_lo;
+                F.iota_inv = fp_from_u128(iota_inv); F.quarter_inv = fp_from_u128(quarter_inv);
+                F.mb_root = (uint32_t*)(mb + MB_ROOT); F.mb_flag = (uint32_t*)(mb + MB_FLAG); F.mb_rem = (fp*)(mb + MB_REM);
+                F.epoch = S->d_epoch.as<uint32_t>();
+                ProfScope ps(c, "fri_tail");
+                GS_CUDA(c, S->hash_alg == HASH_BLAKE2S ? fri_tail_launch<HASH_BLAKE2S>(F, c->stream) : fri_tail_launch<HASH_SHA256>(F, c->stream));
+                c->launches++;
+            }
+            layers.push_back(ly); ++n_layers;
+            if (L <= 256) break;
+            v_cur = v_next; v_next += QL;
+            continue;
+        }
         HashCols hc; hc.ncols = 4; for (int j = 0; j < 4; ++j) hc.col[j] = v_cur + j * QL;
         if (!sharded) { if ((rc = hash_columns(c, S->hash_alg, hc, Q, ly.tree + 8 * Q))) return rc; }
         else {
@@ -713,7 +854,8 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         }
         memcpy(layers[d].root, mb + MB_ROOT + 32 * d, 32);
         if (d == 0) {
-            const int* fl = (const int*)c->mailbox;
+            memcpy(ev_root, c->mailbox, 32);          // copied behind the commit chain, long before the first FRI root
+            const int* fl = (const int*)((const uint8_t*)c->mailbox + 32);
             if (fl[0] != 0x7FFFFFFF) { cudaStreamSynchronize(c->stream); return c->fail(GS_E_STARK, "Failed to evaluate transition constraints: Constraint %d didn't evaluate to 0 at step %d", fl[0] & 63, fl[0] >> 6); }
             // lcProof and the trace queries depend on root_0 only (LowDegreeProver.ts:50-54, Stark.ts:147-151)
             std::vector<uint32_t> exe_pos;
