@@ -393,6 +393,50 @@ static inline int hash_columns(Ctx* c, int alg, const HashCols& cols, long long 
     return GS_OK;
 }
 
+// Sharded commit over peer memory (NVLink / NVSwitch): a rank hashes the rows of its cosets and stores every digest straight
+// into the leaf array of the rank that owns that leaf RANGE (leaves are dealt to the ranks in W contiguous ranges), through
+// pointers obtained once with cudaIpcOpenMemHandle.  The transfer rides under the hashing arithmetic, tile by tile; what is
+// left of the exchange is one barrier.  Replaces hash -> local buffer -> ncclSend/ncclRecv all-to-all -> permutation kernel
+// (0.34 ms for the evaluation tree at 2 GPUs, 165 - 190 GB/s).  local row il <-> global leaf i = q * E + j0 + jl.
+struct PeerTrees { uint32_t* base[8]; };     // per rank: the tree (2n digests, leaves at [n, 2n)) this commit builds there
+template <int ALG>
+__global__ void __launch_bounds__(256) hash_columns_scatter_kernel(const HashCols cols, long long n_loc, const PeerTrees peers, long long n,
+                                                                   int log_e, int log_el, int j0, int log_range) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long il = (long long)blockIdx.x * blockDim.x + threadIdx.x; il < n_loc; il += stride) {
+        uint32_t d[8];
+        if (cols.ncols <= 4) {
+            uint32_t m[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                fp e = (c < cols.ncols) ? ld_fp(cols.col[c] + il) : fp_zero();
+                m[4 * c] = e.v[0]; m[4 * c + 1] = e.v[1]; m[4 * c + 2] = e.v[2]; m[4 * c + 3] = e.v[3];
+            }
+            auto getm = [&](int w) -> uint32_t { return m[w]; };
+            hash_words<ALG>(getm, cols.ncols * 4, d);
+        } else {
+            auto get = [&](int w) -> uint32_t { return cols.col[w >> 2][il].v[w & 3]; };
+            hash_words<ALG>(get, cols.ncols * 4, d);
+        }
+        const long long i = ((il >> log_el) << log_e) + j0 + (il & ((1ll << log_el) - 1));
+        store_digest(peers.base[i >> log_range] + 8 * (n + i), d);
+    }
+}
+static inline int hash_columns_scatter(Ctx* c, int alg, const HashCols& cols, long long n_loc, const PeerTrees& peers, long long n,
+                                       int log_e, int log_el, int j0, int log_w) {
+    if (cols.ncols < 1 || cols.ncols > GS_MAX_HASH_COLS) return c->fail(GS_E_ARG, "1..%d columns per leaf", GS_MAX_HASH_COLS);
+    int log_n = 0; while ((1ll << log_n) < n) ++log_n;
+    const unsigned g = grid_for(c, n_loc, 256);
+    ProfScope ps(c, "hash_columns");
+    if (alg == HASH_BLAKE2S) hash_columns_scatter_kernel<HASH_BLAKE2S><<<g, 256, 0, c->stream>>>(cols, n_loc, peers, n, log_e, log_el, j0, log_n - log_w);
+    else if (alg == HASH_SHA256) hash_columns_scatter_kernel<HASH_SHA256><<<g, 256, 0, c->stream>>>(cols, n_loc, peers, n, log_e, log_el, j0, log_n - log_w);
+    else return c->fail(GS_E_ARG, "unknown hash algorithm");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return c->cuda_fail(e, "hash_columns_scatter_kernel");
+    c->launches++;
+    return GS_OK;
+}
+
 static inline int hash_rows(Ctx* c, int alg, const void* buf, int row_bytes, long long n, uint32_t* out) {
     if (row_bytes <= 0 || row_bytes % 16) return c->fail(GS_E_ARG, "row size must be a positive multiple of 16 bytes");
     const unsigned g = grid_for(c, n, 256);

@@ -65,6 +65,10 @@ struct Stark : public AirHost {
     std::shared_ptr<ComposeJit> compose_jit;   // K2 specialised for this AIR's constraints (devjit.cuh); fn == null => interpreter
     Shard shard;                      // coset sharding over the ranks of the context (world == 1: everything local)
     DevBuf d_dig_loc, d_dig_all;      // commit boundary: local digests / all-gathered digests before the permutation
+    DevBuf d_fri_rep;                 // sharded prover: the gathered FRI layer and the replicated layers behind it
+    // peer memory (cudaIpc): every rank's d_tree / d_fri_trees as seen from this rank, re-exchanged when an allocation moves
+    struct PeerMap { void* key = nullptr; std::vector<void*> ptr; bool ok = false; } peer_tree, peer_fri;
+    DevBuf d_ipc;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     DevBuf d_epoch;                         // prove counter, copied behind each FRI root so the host can poll for it
     float last_device_ms = 0;         // CUDA-event time from the first enqueue to the last kernel of prove()
@@ -78,7 +82,8 @@ struct Stark : public AirHost {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev2) cudaEventDestroy(ev2);
-        d_epoch.release(); d_dig_loc.release(); d_dig_all.release();
+        d_epoch.release(); d_dig_loc.release(); d_dig_all.release(); d_fri_rep.release(); d_ipc.release();
+        for (PeerMap* m : {&peer_tree, &peer_fri}) for (size_t r = 0; r < m->ptr.size(); ++r) if (m->ptr[r] && (int)r != (ctx ? ctx->rank : 0)) cudaIpcCloseMemHandle(m->ptr[r]);
     }
 };
 
@@ -144,6 +149,74 @@ static inline int commit_gather(Stark* S, const uint32_t* d_local, long long n_l
     permute_digests_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(S->d_dig_all.as<uint4>(), reinterpret_cast<uint4*>(leaves_out), n_loc, sh.log_el, log_w);
     c->launches++;
     return GS_OK;
+}
+
+static inline bool shard_peer_enabled() {      // GS_SHARD_PEER=0: digests travel through ncclSend/ncclRecv as in round 1
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GS_SHARD_PEER"); v = (e && atoi(e) == 0) ? 0 : 1; }
+    return v != 0;
+}
+// (Re)build the table of peer pointers for one allocation: cudaIpcGetMemHandle here, handles all-gathered with NCCL, opened on
+// every rank.  Collective: every rank calls it at the same point of the same prove.  Never called under stream capture (the
+// first prove of an instance runs uncaptured and allocations only move when they grow).  ok == false => NCCL path.
+static inline int peer_map_update(Stark* S, Stark::PeerMap& m, void* base) {
+    Ctx* c = S->ctx;
+    if (m.key == base && !m.ptr.empty()) return GS_OK;
+    const int W = c->world;
+    for (size_t r = 0; r < m.ptr.size(); ++r) if (m.ptr[r] && (int)r != c->rank) cudaIpcCloseMemHandle(m.ptr[r]);
+    m.ptr.assign(W, nullptr); m.ok = false; m.key = base;
+    int rc;
+    if ((rc = S->d_ipc.ensure(c, (size_t)(W + 1) * 128))) return rc;
+    struct Slot { cudaIpcMemHandle_t h; int valid; char pad[128 - sizeof(cudaIpcMemHandle_t) - sizeof(int)]; };
+    static_assert(sizeof(Slot) == 128, "slot size");
+    Slot mine; memset(&mine, 0, sizeof mine);
+    mine.valid = (cudaIpcGetMemHandle(&mine.h, base) == cudaSuccess) ? 1 : 0;
+    if (!mine.valid) cudaGetLastError();
+    uint8_t* d = S->d_ipc.as<uint8_t>();
+    GS_CUDA(c, cudaMemcpyAsync(d, &mine, 128, cudaMemcpyHostToDevice, c->stream));
+    const int nr = nccl().AllGather(d, d + 128, 128, GS_NCCL_UINT8, c->comm, c->stream);
+    if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllGather(ipc handles): %s", nccl().GetErrorString(nr));
+    std::vector<Slot> all(W);
+    GS_CUDA(c, cudaMemcpyAsync(all.data(), d + 128, (size_t)W * 128, cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    bool ok = true;
+    for (int r = 0; r < W; ++r) ok = ok && all[r].valid;
+    for (int r = 0; r < W && ok; ++r) {
+        if (r == c->rank) { m.ptr[r] = base; continue; }
+        if (cudaIpcOpenMemHandle(&m.ptr[r], all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); m.ptr[r] = nullptr; ok = false; }
+    }
+    // every rank must take the same path: agree on the outcome (sum of the failures)
+    unsigned bad = ok ? 0u : 1u;
+    GS_CUDA(c, cudaMemcpyAsync(d, &bad, 4, cudaMemcpyHostToDevice, c->stream));
+    const int nr2 = nccl().AllReduce(d, d, 1, GS_NCCL_UINT32, GS_NCCL_SUM, c->comm, c->stream);
+    if (nr2 != 0) return c->fail(GS_E_CUDA, "ncclAllReduce: %s", nccl().GetErrorString(nr2));
+    GS_CUDA(c, cudaMemcpyAsync(&bad, d, 4, cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    m.ok = (bad == 0);
+    return GS_OK;
+}
+// cross-rank barrier on the stream: a one-word all-reduce (every rank's hashing kernel -- and with it its peer stores -- has
+// completed before any rank's tree kernels start)
+static inline int shard_barrier(Stark* S) {
+    Ctx* c = S->ctx;
+    ProfScope ps(c, "nccl_barrier");
+    uint32_t* w = S->d_ipc.as<uint32_t>();
+    const int nr = nccl().AllReduce(w, w, 1, GS_NCCL_UINT32, GS_NCCL_SUM, c->comm, c->stream);
+    if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllReduce(barrier): %s", nccl().GetErrorString(nr));
+    return GS_OK;
+}
+// split-tree commit with the digests already in place (hash_columns_scatter): barrier, sub-tree, roots, top
+static inline int commit_split_tree_peer(Stark* S, long long n, uint32_t* tree) {
+    Ctx* c = S->ctx;
+    const Shard& sh = S->shard;
+    int log_w = 0; while ((1 << log_w) < sh.world) ++log_w;
+    int rc;
+    if ((rc = shard_barrier(S))) return rc;
+    if ((rc = merkle_build_range(c, S->hash_alg, tree, n, log_w, sh.rank))) return rc;
+    { ProfScope ps(c, "nccl_allgather_roots");
+      const int nr = nccl().AllGather(tree + 8 * (sh.world + sh.rank), tree + 8 * sh.world, 32, GS_NCCL_UINT8, c->comm, c->stream);
+      if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllGather: %s", nccl().GetErrorString(nr)); }
+    return merkle_build_top(c, S->hash_alg, tree, sh.world);
 }
 
 // Merkle commit of the sharded prover for a large tree: instead of gathering all n digests everywhere and building the
@@ -214,6 +287,7 @@ static inline int run_region(Stark* S, GraphSlot& slot, unsigned long long key, 
 struct FriLayer {
     fp* v; long long len; uint32_t* tree; uint8_t root[32];
     bool split;        // sharded prover: the tree is split into W sub-trees (one per rank) below the level with W nodes
+    bool replicated;   // sharded prover: from this layer on every rank holds the whole vector and tree (see shard_gather_log)
 };
 
 static inline double now_ms() {
@@ -393,6 +467,14 @@ static inline cudaError_t fri_tail_launch(const FriTailParams& F, cudaStream_t s
     fri_tail_kernel<ALG><<<1, 512, smem, st>>>(F);
     return cudaGetLastError();
 }
+// Sharded prover: the first FRI layer of at most 2^this many values is all-gathered (one NCCL call, 16 bytes per value) and the
+// rest of the chain runs replicated on every rank with the single-GPU code -- below that size a layer is latency, not work, and
+// every sharded layer costs two or three collectives per commit.  GS_SHARD_GATHER_LOG=0: keep every layer sharded.
+static inline int shard_gather_log() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GS_SHARD_GATHER_LOG"); v = e ? atoi(e) : 21; if (v < 0) v = 0; }
+    return v;
+}
 static inline int fri_tail_log() {       // layers of at most 2^this many values go to fri_tail_kernel; GS_FRI_TAIL_LOG=0: none
     static int v = -1;
     if (v < 0) { const char* e = getenv("GS_FRI_TAIL_LOG"); v = e ? atoi(e) : 11; if (v > 14) v = 14; if (v < 0) v = 0; }        // 2^14 values: 4096 rows, 192 KB of digests
@@ -485,16 +567,25 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     }
     if (e_cols.size() > GS_MAX_HASH_COLS) return c->fail(GS_E_UNSUPPORTED, "more than %d committed registers", GS_MAX_HASH_COLS);
     uint32_t* e_tree = S->d_tree.as<uint32_t>();
-    const bool graphs = S->use_graphs && !c->profiling && !timing && S->proves_done > 0 && !sharded;
+    // the sharded chains are captured too (NCCL calls are stream-ordered and capturable; every rank enqueues the same sequence)
+    static const bool shard_graphs = !(getenv("GS_SHARD_GRAPHS") && atoi(getenv("GS_SHARD_GRAPHS")) == 0);
+    const bool graphs = S->use_graphs && !c->profiling && !timing && S->proves_done > 0 && (!sharded || shard_graphs);
     // any reallocation changes a pointer below and invalidates the captured graphs
     unsigned long long gkey = 1469598103934665603ull;
     for (const DevBuf* b : {&S->d_trace, &S->d_poly, &S->d_pe, &S->d_work, &S->d_tree, &S->d_l, &S->d_fri, &S->d_fri_trees, &S->d_params,
-                            &S->d_small, &S->d_in_trace, &S->d_in_poly, &S->d_in_e, &S->d_c, &S->d_u, &S->d_cyc, &S->d_instrs, &S->d_consts, &S->d_epoch})
+                            &S->d_small, &S->d_in_trace, &S->d_in_poly, &S->d_in_e, &S->d_c, &S->d_u, &S->d_cyc, &S->d_instrs, &S->d_consts, &S->d_epoch,
+                            &S->d_dig_loc, &S->d_dig_all, &S->d_fri_rep})
         gkey = (gkey ^ (unsigned long long)(uintptr_t)b->p) * 1099511628211ull;
     gkey = (gkey ^ (unsigned long long)S->keep_intermediates) * 1099511628211ull;
     // trees with at least 2^14 leaves per ... are split across the ranks; small ones are replicated
     auto split_ok = [&](long long n) { return sharded && n >= (16384ll * sh.world) && (n >> log_e) >= sh.world; };
     const bool e_split = split_ok(N);
+    int log_w_all = 0; while ((1 << log_w_all) < sh.world) ++log_w_all;
+    bool peers_ok = false;
+    if (sharded && shard_peer_enabled() && sh.world <= 8 && e_split) {
+        if ((rc = peer_map_update(S, S->peer_tree, S->d_tree.p)) || (rc = peer_map_update(S, S->peer_fri, S->d_fri_trees.p))) return rc;
+        peers_ok = S->peer_tree.ok && S->peer_fri.ok;
+    }
     auto commit_region = [&]() -> int {
         int r2;
         if ((r2 = ntt_run(c, S->d_trace.as<fp>(), T, S->d_poly.as<fp>(), T, S->d_work.as<fp>(), T, R, log_t, 0, true))) return r2;
@@ -509,12 +600,19 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         HashCols hc; hc.ncols = (int)e_cols.size();
         for (size_t i = 0; i < e_cols.size(); ++i) hc.col[i] = e_cols[i];
         if (!sharded) { if ((r2 = hash_columns(c, S->hash_alg, hc, N, e_tree + 8 * N))) return r2; }
+        else if (e_split && peers_ok) {
+            PeerTrees pt; memset(&pt, 0, sizeof pt);
+            for (int r = 0; r < sh.world; ++r) pt.base[r] = (uint32_t*)S->peer_tree.ptr[r];
+            if ((r2 = hash_columns_scatter(c, S->hash_alg, hc, NL, pt, N, log_e, log_el, sh.j0(), log_w_all))) return r2;
+            if (timing) mark("Serialized evaluations of P(x) and S(x) polynomials", true);
+            if ((r2 = commit_split_tree_peer(S, N, e_tree))) return r2;
+        }
         else {
             if ((r2 = hash_columns(c, S->hash_alg, hc, NL, S->d_dig_loc.as<uint32_t>()))) return r2;
             if (e_split) { if ((r2 = commit_split_tree(S, S->d_dig_loc.as<uint32_t>(), N, e_tree))) return r2; }
             else if ((r2 = commit_gather(S, S->d_dig_loc.as<uint32_t>(), NL, e_tree + 8 * N))) return r2;
         }
-        if (timing) mark("Serialized evaluations of P(x) and S(x) polynomials", true);
+        if (timing && !(e_split && peers_ok)) mark("Serialized evaluations of P(x) and S(x) polynomials", true);
         if (!e_split && (r2 = merkle_build(c, S->hash_alg, e_tree, N))) return r2;
         GS_CUDA(c, cudaMemcpyAsync(c->mailbox, e_tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
         return GS_OK;
@@ -721,12 +819,28 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     fp* v_cur = S->d_l.as<fp>();
     // The whole layer chain is enqueued without host round trips: each challenge x* = prng(root_d) is derived on
     // the device; roots are copied to mailbox slots as they appear and the host plans the queries behind them.
-    bool in_tail = false;
+    bool in_tail = false, replicated = false;
     for (int depth = 0;; ++depth) {
         const long long L = N >> (2 * depth), Q = L >> 2;
-        const long long QL = (NL >> (2 * depth)) >> 2;          // rows of this layer owned by this rank
-        FriLayer ly; ly.v = v_cur; ly.len = L; ly.tree = t_next; ly.split = false; t_next += (size_t)2 * Q * 8;
-        if (in_tail || (!sharded && fri_tail_log() >= 8 && L <= (1ll << fri_tail_log()))) {
+        if (sharded && !replicated && shard_gather_log() > 0 && L <= (1ll << shard_gather_log())) {
+            // all-gather this layer's vector, restore position order, continue replicated
+            int log_w = 0; while ((1 << log_w) < sh.world) ++log_w;
+            const long long LL = L >> log_w;
+            if ((rc = S->d_fri_rep.ensure(c, (size_t)(L * 2 + L / 2 + 1024) * sizeof(fp)))) return rc;
+            fp* gathered = S->d_fri_rep.as<fp>();
+            fp* nat = gathered + L;
+            { ProfScope ps(c, "nccl_allgather_layer");
+              const int nr = nccl().AllGather(v_cur, gathered, (size_t)LL * 16, GS_NCCL_UINT8, c->comm, c->stream);
+              if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllGather: %s", nccl().GetErrorString(nr)); }
+            permute_elems_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<const uint4*>(gathered), reinterpret_cast<uint4*>(nat), LL, log_el, log_w);
+            c->launches++;
+            v_cur = nat; v_next = nat + L;
+            replicated = true;
+        }
+        const bool shl = sharded && !replicated;               // this layer is sharded
+        const long long QL = shl ? (NL >> (2 * depth)) >> 2 : Q;          // rows of this layer held by this rank
+        FriLayer ly; ly.v = v_cur; ly.len = L; ly.tree = t_next; ly.split = false; ly.replicated = replicated; t_next += (size_t)2 * Q * 8;
+        if (in_tail || (!shl && fri_tail_log() >= 8 && L <= (1ll << fri_tail_log()))) {
             if (!in_tail) {
                 in_tail = true;
                 if (depth >= 24) return c->fail(GS_E_UNSUPPORTED, "too many FRI layers");
@@ -748,11 +862,20 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             continue;
         }
         HashCols hc; hc.ncols = 4; for (int j = 0; j < 4; ++j) hc.col[j] = v_cur + j * QL;
-        if (!sharded) { if ((rc = hash_columns(c, S->hash_alg, hc, Q, ly.tree + 8 * Q))) return rc; }
+        if (!shl) { if ((rc = hash_columns(c, S->hash_alg, hc, Q, ly.tree + 8 * Q))) return rc; }
         else {
+            if (split_ok(Q) && peers_ok) {
+                ly.split = true;
+                PeerTrees pt; memset(&pt, 0, sizeof pt);
+                const size_t off = (size_t)(ly.tree - S->d_fri_trees.as<uint32_t>());
+                for (int r = 0; r < sh.world; ++r) pt.base[r] = (uint32_t*)S->peer_fri.ptr[r] + off;
+                if ((rc = hash_columns_scatter(c, S->hash_alg, hc, QL, pt, Q, log_e, log_el, sh.j0(), log_w_all))) return rc;
+                if ((rc = commit_split_tree_peer(S, Q, ly.tree))) return rc;
+            } else {
             if ((rc = hash_columns(c, S->hash_alg, hc, QL, S->d_dig_loc.as<uint32_t>()))) return rc;
             if (split_ok(Q)) { ly.split = true; if ((rc = commit_split_tree(S, S->d_dig_loc.as<uint32_t>(), Q, ly.tree))) return rc; }
             else if ((rc = commit_gather(S, S->d_dig_loc.as<uint32_t>(), QL, ly.tree + 8 * Q))) return rc;
+            }
         }
         if (!ly.split && (rc = merkle_build(c, S->hash_alg, ly.tree, Q))) return rc;
         if (depth >= 24) return c->fail(GS_E_UNSUPPORTED, "too many FRI layers");
@@ -760,7 +883,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_FLAG + 4 * depth, S->d_epoch.p, 4, cudaMemcpyDeviceToHost, c->stream));
         layers.push_back(ly); ++n_layers;
         if (L <= 256) {
-            if (!sharded) GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM, v_cur, L * sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
+            if (!shl) GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM, v_cur, L * sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
             else {
                 // remainder: gather the per-rank pieces and restore position order
                 int log_w = 0; while ((1 << log_w) < sh.world) ++log_w;
@@ -778,7 +901,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         { ProfScope ps(c, "fri_fold");
           fri_challenge_kernel<<<1, 1, 0, c->stream>>>(ly.tree + 8, d_special + (depth & 3));
           FriFoldParams F; F.v = v_cur; F.out = v_next; F.quarter = QL; F.special_x = d_special + (depth & 3);
-          F.log_e = log_e; F.log_el = log_el; F.j0 = sh.j0();
+          F.log_e = log_e; F.log_el = shl ? log_el : log_e; F.j0 = shl ? sh.j0() : 0;
           F.tw_lo = c->tw_lo; F.tw_hi = c->tw_hi; F.log_g = c->log_g; F.log_lo = c->log_lo;
           F.x_shift = 2 * depth + (c->log_g - log_n); F.iota_inv = fp_from_u128(iota_inv); F.quarter_inv = fp_from_u128(quarter_inv);
           fri_fold_kernel<<<grid_for(c, QL, 256), 256, 0, c->stream>>>(F); }
@@ -789,14 +912,21 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     };
     if ((rc = run_region(S, S->g_fri, gkey ^ 0x9E3779B97F4A7C15ull, graphs, fri_region))) return rc;
     if (graphs && layers.empty()) {
-        // replayed graph: rebuild the layer table (pure pointer arithmetic, no launches)
+        // replayed graph: rebuild the layer table (the pointer arithmetic of the loop above, no launches)
         fp* vc = S->d_l.as<fp>(); fp* vn = S->d_fri.as<fp>() + 4; uint32_t* tn = S->d_fri_trees.as<uint32_t>();
+        bool repl = false;
         for (int depth = 0;; ++depth) {
             const long long L = N >> (2 * depth), Q = L >> 2;
-            FriLayer ly; ly.v = vc; ly.len = L; ly.tree = tn; ly.split = false; tn += (size_t)2 * Q * 8;
+            if (sharded && !repl && shard_gather_log() > 0 && L <= (1ll << shard_gather_log())) {
+                fp* nat = S->d_fri_rep.as<fp>() + L;
+                vc = nat; vn = nat + L; repl = true;
+            }
+            const bool shl = sharded && !repl;
+            const long long QL = shl ? (NL >> (2 * depth)) >> 2 : Q;
+            FriLayer ly; ly.v = vc; ly.len = L; ly.tree = tn; ly.split = shl && split_ok(Q); ly.replicated = repl; tn += (size_t)2 * Q * 8;
             layers.push_back(ly); ++n_layers;
             if (L <= 256) break;
-            vc = vn; vn += Q;
+            vc = vn; vn += QL;
         }
     }
     cudaEventRecord(S->ev1, c->stream);     // end of the enqueued chain (remainder copy included)
@@ -815,13 +945,13 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     };
     struct PlannedProof { BatchProof bp; std::vector<size_t> node_chunk; std::vector<size_t> value_chunk; int chunks_per_value = 0; };
     auto plan_proof = [&](PlannedProof& pp, const uint32_t* tree, uint64_t n, const std::vector<uint32_t>& idx,
-                          const std::vector<const fp*>& cols, bool split) -> int {
+                          const std::vector<const fp*>& cols, bool split, bool repl = false) -> int {
         if (merkle_prove_plan(idx, n, pp.bp, err) != 0) return c->fail(GS_E_STARK, "%s", err.c_str());
         for (auto& col : pp.bp.node_ids) for (uint32_t id : col) { pp.node_chunk.push_back(add_chunk(node_ptr(tree, id, split, 0))); add_chunk(node_ptr(tree, id, split, 1)); }
         pp.chunks_per_value = (int)cols.size();
         for (uint32_t i : idx) {
-            const bool mine = !sharded || sh.owner(i) == sh.rank;
-            const long long il = sharded ? sh.to_local(i) : (long long)i;
+            const bool mine = !sharded || (repl ? sh.rank == 0 : sh.owner(i) == sh.rank);
+            const long long il = (sharded && !repl) ? sh.to_local(i) : (long long)i;
             for (const fp* cp : cols) pp.value_chunk.push_back(add_chunk(mine ? (const void*)(cp + il) : zero_block));
         }
         return GS_OK;
@@ -832,7 +962,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         return first_seen_unique(m);
     };
     int log_w_q = 0; while ((1 << log_w_q) < sh.world) ++log_w_q;
-    auto row_cols = [&](const FriLayer& ly) { std::vector<const fp*> cols; for (int j = 0; j < 4; ++j) cols.push_back(ly.v + j * ((ly.len >> log_w_q) >> 2)); return cols; };
+    auto row_cols = [&](const FriLayer& ly) { std::vector<const fp*> cols; for (int j = 0; j < 4; ++j) cols.push_back(ly.v + j * ((ly.len >> (ly.replicated ? 0 : log_w_q)) >> 2)); return cols; };
     PlannedProof lc_pp, ev_pp;
     struct Comp { const uint8_t* root; PlannedProof column, poly; };
     std::vector<Comp> comps(layers.size() - 1);
@@ -861,7 +991,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             std::vector<uint32_t> exe_pos;
             if (pseudorandom_indexes(layers[0].root, (int)std::min<long long>(S->exe_queries, N - N / E), (uint64_t)N, (uint64_t)E, exe_pos, err) != 0) {
                 cudaStreamSynchronize(c->stream); return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str()); }
-            if ((rc = plan_proof(lc_pp, layers[0].tree, (uint64_t)(N >> 2), aug4(exe_pos, N), row_cols(layers[0]), layers[0].split))) return rc;
+            if ((rc = plan_proof(lc_pp, layers[0].tree, (uint64_t)(N >> 2), aug4(exe_pos, N), row_cols(layers[0]), layers[0].split, layers[0].replicated))) return rc;
             std::vector<uint32_t> m;
             for (uint32_t p : exe_pos) { m.push_back(p); m.push_back((uint32_t)((p + E) % N)); }
             if ((rc = plan_proof(ev_pp, e_tree, (uint64_t)N, first_seen_unique(m), e_cols, e_split))) return rc;
@@ -871,8 +1001,8 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             if (pseudorandom_indexes(cl.root, S->fri_queries, (uint64_t)cl.len, (uint64_t)E, positions, err) != 0) {
                 cudaStreamSynchronize(c->stream); return c->fail(GS_E_STARK, "Low degree proof failed: %s", err.c_str()); }
             comps[d - 1].root = cl.root;
-            if ((rc = plan_proof(comps[d - 1].column, cl.tree, (uint64_t)(cl.len >> 2), aug4(positions, cl.len), row_cols(cl), cl.split))) return rc;
-            if ((rc = plan_proof(comps[d - 1].poly, pl.tree, (uint64_t)(pl.len >> 2), positions, row_cols(pl), pl.split))) return rc;
+            if ((rc = plan_proof(comps[d - 1].column, cl.tree, (uint64_t)(cl.len >> 2), aug4(positions, cl.len), row_cols(cl), cl.split, cl.replicated))) return rc;
+            if ((rc = plan_proof(comps[d - 1].poly, pl.tree, (uint64_t)(pl.len >> 2), positions, row_cols(pl), pl.split, pl.replicated))) return rc;
         }
     }
     const uint8_t* lc_root = layers[0].root;
