@@ -67,8 +67,8 @@ struct Stark : public AirHost {
     DevBuf d_dig_loc, d_dig_all;      // commit boundary: local digests / all-gathered digests before the permutation
     DevBuf d_fri_rep;                 // sharded prover: the gathered FRI layer and the replicated layers behind it
     // peer memory (cudaIpc): every rank's d_tree / d_fri_trees as seen from this rank, re-exchanged when an allocation moves
-    struct PeerMap { void* key = nullptr; std::vector<void*> ptr; bool ok = false; } peer_tree, peer_fri;
-    DevBuf d_ipc;
+    struct PeerMap { void* key = nullptr; std::vector<void*> ptr; bool ok = false; } peer_tree, peer_fri, peer_sync;
+    DevBuf d_ipc, d_sync;             // d_sync: [0, 8) barrier flags written by the peers, [8] local barrier counter, [9] timeout flag
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     DevBuf d_epoch;                         // prove counter, copied behind each FRI root so the host can poll for it
     float last_device_ms = 0;         // CUDA-event time from the first enqueue to the last kernel of prove()
@@ -76,6 +76,7 @@ struct Stark : public AirHost {
     ~Stark() {
         for (DevBuf* b : {&d_instrs, &d_consts, &d_cyc, &d_u, &d_trace, &d_poly, &d_pe, &d_in_trace, &d_in_poly, &d_in_e, &d_work, &d_tree,
                           &d_zb, &d_zbs, &d_l, &d_c, &d_fri, &d_fri_trees, &d_params, &d_small, &d_idx, &d_gather}) b->release();
+        d_sync.release();
         if (h_trace) cudaFreeHost(h_trace);
         if (g_commit.exec) cudaGraphExecDestroy(g_commit.exec);
         if (g_fri.exec) cudaGraphExecDestroy(g_fri.exec);
@@ -83,7 +84,7 @@ struct Stark : public AirHost {
         if (ev1) cudaEventDestroy(ev1);
         if (ev2) cudaEventDestroy(ev2);
         d_epoch.release(); d_dig_loc.release(); d_dig_all.release(); d_fri_rep.release(); d_ipc.release();
-        for (PeerMap* m : {&peer_tree, &peer_fri}) for (size_t r = 0; r < m->ptr.size(); ++r) if (m->ptr[r] && (int)r != (ctx ? ctx->rank : 0)) cudaIpcCloseMemHandle(m->ptr[r]);
+        for (PeerMap* m : {&peer_tree, &peer_fri, &peer_sync}) for (size_t r = 0; r < m->ptr.size(); ++r) if (m->ptr[r] && (int)r != (ctx ? ctx->rank : 0)) cudaIpcCloseMemHandle(m->ptr[r]);
     }
 };
 
@@ -195,27 +196,70 @@ static inline int peer_map_update(Stark* S, Stark::PeerMap& m, void* base) {
     m.ok = (bad == 0);
     return GS_OK;
 }
-// cross-rank barrier on the stream: a one-word all-reduce (every rank's hashing kernel -- and with it its peer stores -- has
-// completed before any rank's tree kernels start)
-static inline int shard_barrier(Stark* S) {
+// Cross-rank barrier on the stream, over peer memory: every rank bumps its local epoch, stores it into its slot of every
+// peer's flag array (system scope) and spins until all W slots of its own array have reached the epoch -- a few microseconds
+// on NVSwitch, where a one-word NCCL all-reduce costs ~30.  Stream order puts it behind this rank's hashing kernel, whose peer
+// stores are complete at kernel end, so past the barrier every rank's leaf range is whole.  Optionally carries the sub-tree
+// roots: this rank's root (node W + rank) is stored into every peer's tree first, which replaces the 32-byte all-gather.
+// A peer that never arrives (a rank died) ends the spin after ~2^27 polls and raises the timeout word; the proof then fails
+// the parity / verification checks instead of hanging the box.
+struct PeerSync { uint32_t* flags[8]; uint32_t* local; int rank, world; };
+__global__ void peer_barrier_kernel(const PeerSync ps, const PeerTrees trees, int with_roots) {
+    __shared__ uint32_t epoch;
+    const int t = threadIdx.x;
+    if (t == 0) epoch = ++ps.local[8];
+    __syncthreads();
+    if (with_roots && t < ps.world * 8) {
+        const int peer = t >> 3, w = t & 7;
+        const uint32_t v = trees.base[ps.rank][8 * (ps.world + ps.rank) + w];
+        if (peer != ps.rank) trees.base[peer][8 * (ps.world + ps.rank) + w] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < ps.world) {
+        volatile uint32_t* theirs = ps.flags[t] + ps.rank;
+        *theirs = epoch;
+        __threadfence_system();
+        volatile uint32_t* mine = ps.local + t;
+        unsigned polls = 0;
+        while ((int)(*mine - epoch) < 0) { if (++polls > (1u << 27)) { ps.local[9] = 1u; break; } }
+    }
+    __threadfence_system();
+}
+static inline int shard_barrier(Stark* S, const PeerTrees* trees) {
     Ctx* c = S->ctx;
+    if (S->peer_sync.ok) {
+        ProfScope ps(c, "peer_barrier");
+        PeerSync sy; memset(&sy, 0, sizeof sy);
+        for (int r = 0; r < c->world; ++r) sy.flags[r] = (uint32_t*)S->peer_sync.ptr[r];
+        sy.local = S->d_sync.as<uint32_t>(); sy.rank = c->rank; sy.world = c->world;
+        PeerTrees none; memset(&none, 0, sizeof none);
+        peer_barrier_kernel<<<1, 64, 0, c->stream>>>(sy, trees ? *trees : none, trees ? 1 : 0);
+        GS_CUDA(c, cudaGetLastError());
+        c->launches++;
+        return GS_OK;
+    }
     ProfScope ps(c, "nccl_barrier");
     uint32_t* w = S->d_ipc.as<uint32_t>();
     const int nr = nccl().AllReduce(w, w, 1, GS_NCCL_UINT32, GS_NCCL_SUM, c->comm, c->stream);
     if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllReduce(barrier): %s", nccl().GetErrorString(nr));
+    if (trees) {
+        ProfScope ps2(c, "nccl_allgather_roots");
+        uint32_t* tree = trees->base[c->rank];
+        const int nr2 = nccl().AllGather(tree + 8 * (c->world + c->rank), tree + 8 * c->world, 32, GS_NCCL_UINT8, c->comm, c->stream);
+        if (nr2 != 0) return c->fail(GS_E_CUDA, "ncclAllGather: %s", nccl().GetErrorString(nr2));
+    }
     return GS_OK;
 }
 // split-tree commit with the digests already in place (hash_columns_scatter): barrier, sub-tree, roots, top
-static inline int commit_split_tree_peer(Stark* S, long long n, uint32_t* tree) {
+static inline int commit_split_tree_peer(Stark* S, long long n, uint32_t* tree, const PeerTrees& trees) {
     Ctx* c = S->ctx;
     const Shard& sh = S->shard;
     int log_w = 0; while ((1 << log_w) < sh.world) ++log_w;
     int rc;
-    if ((rc = shard_barrier(S))) return rc;
+    if ((rc = shard_barrier(S, nullptr))) return rc;                       // every leaf range is whole
     if ((rc = merkle_build_range(c, S->hash_alg, tree, n, log_w, sh.rank))) return rc;
-    { ProfScope ps(c, "nccl_allgather_roots");
-      const int nr = nccl().AllGather(tree + 8 * (sh.world + sh.rank), tree + 8 * sh.world, 32, GS_NCCL_UINT8, c->comm, c->stream);
-      if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllGather: %s", nccl().GetErrorString(nr)); }
+    if ((rc = shard_barrier(S, &trees))) return rc;                        // sub-tree roots everywhere
     return merkle_build_top(c, S->hash_alg, tree, sh.world);
 }
 
@@ -472,7 +516,7 @@ static inline cudaError_t fri_tail_launch(const FriTailParams& F, cudaStream_t s
 // every sharded layer costs two or three collectives per commit.  GS_SHARD_GATHER_LOG=0: keep every layer sharded.
 static inline int shard_gather_log() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("GS_SHARD_GATHER_LOG"); v = e ? atoi(e) : 21; if (v < 0) v = 0; }
+    if (v < 0) { const char* e = getenv("GS_SHARD_GATHER_LOG"); v = e ? atoi(e) : 19; if (v < 0) v = 0; }
     return v;
 }
 static inline int fri_tail_log() {       // layers of at most 2^this many values go to fri_tail_kernel; GS_FRI_TAIL_LOG=0: none
@@ -574,7 +618,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     unsigned long long gkey = 1469598103934665603ull;
     for (const DevBuf* b : {&S->d_trace, &S->d_poly, &S->d_pe, &S->d_work, &S->d_tree, &S->d_l, &S->d_fri, &S->d_fri_trees, &S->d_params,
                             &S->d_small, &S->d_in_trace, &S->d_in_poly, &S->d_in_e, &S->d_c, &S->d_u, &S->d_cyc, &S->d_instrs, &S->d_consts, &S->d_epoch,
-                            &S->d_dig_loc, &S->d_dig_all, &S->d_fri_rep})
+                            &S->d_dig_loc, &S->d_dig_all, &S->d_fri_rep, &S->d_sync})
         gkey = (gkey ^ (unsigned long long)(uintptr_t)b->p) * 1099511628211ull;
     gkey = (gkey ^ (unsigned long long)S->keep_intermediates) * 1099511628211ull;
     // trees with at least 2^14 leaves per ... are split across the ranks; small ones are replicated
@@ -583,7 +627,10 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     int log_w_all = 0; while ((1 << log_w_all) < sh.world) ++log_w_all;
     bool peers_ok = false;
     if (sharded && shard_peer_enabled() && sh.world <= 8 && e_split) {
+        if (!S->d_sync.p) { if ((rc = S->d_sync.ensure(c, 256))) return rc; GS_CUDA(c, cudaMemsetAsync(S->d_sync.p, 0, 256, c->stream)); GS_CUDA(c, cudaStreamSynchronize(c->stream)); }
         if ((rc = peer_map_update(S, S->peer_tree, S->d_tree.p)) || (rc = peer_map_update(S, S->peer_fri, S->d_fri_trees.p))) return rc;
+        static const bool peer_barrier = !(getenv("GS_SHARD_PEER_BARRIER") && atoi(getenv("GS_SHARD_PEER_BARRIER")) == 0);
+        if (peer_barrier && (rc = peer_map_update(S, S->peer_sync, S->d_sync.p))) return rc;
         peers_ok = S->peer_tree.ok && S->peer_fri.ok;
     }
     auto commit_region = [&]() -> int {
@@ -605,7 +652,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             for (int r = 0; r < sh.world; ++r) pt.base[r] = (uint32_t*)S->peer_tree.ptr[r];
             if ((r2 = hash_columns_scatter(c, S->hash_alg, hc, NL, pt, N, log_e, log_el, sh.j0(), log_w_all))) return r2;
             if (timing) mark("Serialized evaluations of P(x) and S(x) polynomials", true);
-            if ((r2 = commit_split_tree_peer(S, N, e_tree))) return r2;
+            if ((r2 = commit_split_tree_peer(S, N, e_tree, pt))) return r2;
         }
         else {
             if ((r2 = hash_columns(c, S->hash_alg, hc, NL, S->d_dig_loc.as<uint32_t>()))) return r2;
@@ -772,7 +819,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     // 5b-7 ---- compose + the whole FRI layer chain (second captured region)
     std::vector<FriLayer> layers;
     uint8_t* mb = (uint8_t*)c->mailbox;
-    // mailbox layout: [0, 32) evaluation root, [32, 40) the compose fail flag; [1024, 1792) FRI layer roots; [2048, 2144) one
+    // mailbox layout: [0, 32) evaluation root, [32, 40) the compose fail flag, [48, 52) peer-barrier timeout word; [1024, 1792) FRI layer roots; [2048, 2144) one
     // epoch flag per layer; [4096, 8192) remainder; [8192, ...) gathered query data
     const size_t MB_ROOT = 1024, MB_FLAG = 2048, MB_REM = 4096;
     int n_layers = 0;
@@ -786,6 +833,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     const uint32_t epoch = c->prove_epoch;
     memset(mb + MB_ROOT, 0, 32 * 24);
     memset(mb + MB_FLAG, 0, 4 * 24);
+    memset(mb + 48, 0, 4);
     GS_CUDA(c, cudaMemcpyAsync(S->d_epoch.p, &epoch, 4, cudaMemcpyHostToDevice, c->stream));
     GS_CUDA(c, cudaMemsetAsync(S->d_epoch.as<uint8_t>() + 32, 0, 16, c->stream));
     auto fri_region = [&]() -> int {
@@ -870,7 +918,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
                 const size_t off = (size_t)(ly.tree - S->d_fri_trees.as<uint32_t>());
                 for (int r = 0; r < sh.world; ++r) pt.base[r] = (uint32_t*)S->peer_fri.ptr[r] + off;
                 if ((rc = hash_columns_scatter(c, S->hash_alg, hc, QL, pt, Q, log_e, log_el, sh.j0(), log_w_all))) return rc;
-                if ((rc = commit_split_tree_peer(S, Q, ly.tree))) return rc;
+                if ((rc = commit_split_tree_peer(S, Q, ly.tree, pt))) return rc;
             } else {
             if ((rc = hash_columns(c, S->hash_alg, hc, QL, S->d_dig_loc.as<uint32_t>()))) return rc;
             if (split_ok(Q)) { ly.split = true; if ((rc = commit_split_tree(S, S->d_dig_loc.as<uint32_t>(), Q, ly.tree))) return rc; }
@@ -1021,6 +1069,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             if (nr != 0) return c->fail(GS_E_CUDA, "ncclAllReduce: %s", nccl().GetErrorString(nr));
         }
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM + 4096, S->d_gather.p, nch * 16, cudaMemcpyDeviceToHost, c->stream));
+        if (sharded && S->peer_sync.ok) GS_CUDA(c, cudaMemcpyAsync(mb + 48, S->d_sync.as<uint32_t>() + 9, 4, cudaMemcpyDeviceToHost, c->stream));
         cudaEventRecord(S->ev2, c->stream);
     }
     // the remainder check runs on the host while the gather and its copy back are in flight
@@ -1049,6 +1098,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     }
     cudaEventSynchronize(S->ev2);
     cudaEventElapsedTime(&S->last_device_ms, S->ev0, S->ev2);
+    if (sharded && S->peer_sync.ok && *(const uint32_t*)(mb + 48) != 0) return c->fail(GS_E_CUDA, "peer barrier timed out: a rank of the sharded prover did not arrive");
     S->trace_resident = true;
     S->proves_done++;
     if (c->profiling) c->prof_collect();
