@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
         'gs_stark_read_intermediate': (i32, [vp, i32, vp, C.c_size_t]),
         'gs_debug_modmul_probe': (i32, [vp, i32, i32, P(C.c_float)]),
         'gs_debug_butterfly_probe': (i32, [vp, i32, i32, P(C.c_float)]),
+        'gs_debug_sqr_probe': (i32, [vp, i32, i32, P(C.c_float), P(C.c_uint32)]),
         'gs_field_prng': (i32, [cp, C.c_size_t, i32, C.c_char_p]),
         'gs_poly_interpolate': (i32, [cp, cp, i32, C.c_char_p]),
         'gs_poly_eval_at': (i32, [cp, i32, cp, C.c_char_p]),

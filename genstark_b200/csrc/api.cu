@@ -447,6 +447,27 @@ static int run_probe(gs_ctx* c, int kind, int blocks, int iters, float* ms_out) 
     c->launches += 2;
     return GS_OK;
 }
+/* blocks x 256 threads x 4 chains x iters squarings (fp_sqr); *mismatches = disagreements of fp_sqr with fp_mul(a, a) on edge and chain values */
+int gs_debug_sqr_probe(gs_ctx* c, int blocks, int iters, float* ms_out, int* mismatches) {
+    if (!c || !ms_out || !mismatches) return GS_E_ARG;
+    cudaSetDevice(c->device);
+    int rc = c->ensure_scratch(256);
+    if (rc != GS_OK) return rc;
+    unsigned* d_bad = (unsigned*)((uint8_t*)c->scratch + 128);
+    GS_CUDA(c, cudaMemsetAsync(d_bad, 0, 4, c->stream));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    sqr_probe_kernel<<<blocks, 256, 0, c->stream>>>((fp*)c->scratch, iters, d_bad);          // warm-up + check
+    cudaEventRecord(e0, c->stream);
+    sqr_probe_kernel<<<blocks, 256, 0, c->stream>>>((fp*)c->scratch, iters, nullptr);
+    cudaEventRecord(e1, c->stream);
+    GS_CUDA(c, cudaMemcpyAsync(mismatches, d_bad, 4, cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(ms_out, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->launches += 2;
+    return GS_OK;
+}
 /* blocks x 256 threads x 4 independent chains x iters modular multiplications */
 int gs_debug_modmul_probe(gs_ctx* c, int blocks, int iters, float* ms_out) { return run_probe(c, 0, blocks, iters, ms_out); }
 /* blocks x 256 threads x 2 butterflies (u + v, (u - v) * w) x iters */

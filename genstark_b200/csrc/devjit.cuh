@@ -88,7 +88,9 @@ static inline std::string compose_emit_source(const AirHost& A) {
       << "#define GS_MAX_COLS " << GS_MAX_COLS << "\n"
       << GS_FP_TYPE_SRC << "\n" << GS_FP_BASIC_SRC << "\n" << GS_FP_DEVICE_SRC << "\n" << GS_FP_LDST_SRC << "\n"
       << GS_COMPOSE_PARAMS_SRC << "\n" << GS_COMPOSE_DEVICE_SRC << "\n";
-    o << "extern \"C\" __global__ void __launch_bounds__(256) gs_compose_jit(const ComposeParams* __restrict__ Pp) {\n"
+    // resident CTAs per SM the register allocation aims at (GS_COMPOSE_MINB, default 3: 80 registers; measured in profiles/)
+    int minb = 3; if (const char* e = getenv("GS_COMPOSE_MINB")) { minb = atoi(e); if (minb < 1 || minb > 8) minb = 3; }
+    o << "extern \"C\" __global__ void __launch_bounds__(256, " << minb << ") gs_compose_jit(const ComposeParams* __restrict__ Pp) {\n"
          "  const ComposeParams& P = *Pp;\n"
          "  const long long stride = (long long)gridDim.x * blockDim.x;\n"
          "  const unsigned long long lmask = (unsigned long long)P.n_loc - 1ull;\n"
@@ -116,7 +118,11 @@ static inline std::string compose_emit_source(const AirHost& A) {
                 break;
             case OP_ADD: if (in(a).empty() || in(b).empty()) return ""; o << "    const fp " << v << " = d_add(" << in(a) << ", " << in(b) << ");\n"; break;
             case OP_SUB: if (in(a).empty() || in(b).empty()) return ""; o << "    const fp " << v << " = d_sub(" << in(a) << ", " << in(b) << ");\n"; break;
-            case OP_MUL: if (in(a).empty() || in(b).empty()) return ""; o << "    const fp " << v << " = d_mul(" << in(a) << ", " << in(b) << ");\n"; break;
+            case OP_MUL:
+                if (in(a).empty() || in(b).empty()) return "";
+                if (in(a) == in(b)) o << "    const fp " << v << " = d_sqr(" << in(a) << ");\n";           // 10 limb products instead of 16
+                else o << "    const fp " << v << " = d_mul(" << in(a) << ", " << in(b) << ");\n";
+                break;
             case OP_NEG: if (in(a).empty()) return ""; o << "    const fp " << v << " = d_neg(" << in(a) << ");\n"; break;
             case OP_INV: if (in(a).empty()) return ""; o << "    const fp " << v << " = d_inv(" << in(a) << ");\n"; break;
             case OP_OUT: if (in(a).empty() || (int)d >= A.K) return ""; o << "    acc = compose_out(P, i, ie, " << d << "u, " << in(a) << ", acc);\n"; break;

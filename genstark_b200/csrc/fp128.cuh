@@ -279,12 +279,49 @@ GS_D fp d_mul(const fp& a, const fp& b) {
     return d_reduce256(r);
 }
 
+// a * a with 10 limb products instead of 16: the six cross products a_i a_j (i < j) once, doubled by a one-bit funnel
+// shift, plus the four squares -- 10 IMAD.WIDE and 7 SHF where d_mul issues 16 IMAD.WIDE (the FMA-heavy pipe binds a
+// multiplication, fp128.cuh header / scripts/pipe_probe.cu)
+GS_D fp d_sqr(const fp& a) {
+    const uint32_t a0 = a.v[0], a1 = a.v[1], a2 = a.v[2], a3 = a.v[3];
+    uint32_t c1, c2, c3, c4, c5, c6, c7;
+    asm("mul.lo.u32 %0, %4, %5;\n\t mul.hi.u32 %1, %4, %5;\n\t"
+        "mul.lo.u32 %2, %4, %6;\n\t mul.hi.u32 %3, %4, %6;"
+        : "=r"(c1), "=r"(c2), "=r"(c3), "=r"(c4) : "r"(a0), "r"(a1), "r"(a3));
+    asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\t madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t addc.u32 %3, 0, 0;"
+        : "+r"(c2), "+r"(c3), "+r"(c4), "=r"(c5) : "r"(a0), "r"(a2));
+    asm("mad.lo.cc.u32 %0, %4, %5, %0;\n\t madc.hi.cc.u32 %1, %4, %5, %1;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t addc.u32 %3, 0, 0;"
+        : "+r"(c3), "+r"(c4), "+r"(c5), "=r"(c6) : "r"(a1), "r"(a2));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(c4), "+r"(c5), "+r"(c6) : "r"(a1), "r"(a3));
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, 0, 0;"
+        : "+r"(c5), "+r"(c6), "=r"(c7) : "r"(a2), "r"(a3));
+    // 2 * cross (a^2 < 2^256, so nothing falls off the top)
+    uint32_t r[8];
+    r[7] = __funnelshift_l(c6, c7, 1); r[6] = __funnelshift_l(c5, c6, 1); r[5] = __funnelshift_l(c4, c5, 1);
+    r[4] = __funnelshift_l(c3, c4, 1); r[3] = __funnelshift_l(c2, c3, 1); r[2] = __funnelshift_l(c1, c2, 1);
+    r[1] = c1 << 1;
+    // + squares at limbs 0, 2, 4, 6
+    asm("mul.lo.u32 %0, %8, %8;\n\t"
+        "mad.hi.cc.u32 %1, %8, %8, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %9, %2;\n\t madc.hi.cc.u32 %3, %9, %9, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %10, %4;\n\t madc.hi.cc.u32 %5, %10, %10, %5;\n\t"
+        "madc.lo.cc.u32 %6, %11, %11, %6;\n\t madc.hi.u32 %7, %11, %11, %7;"
+        : "=r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3));
+    return d_reduce256(r);
+}
+
 GS_D fp d_inv(const fp& a) {
     const uint32_t e[4] = {0xFFFFFFFFu, 0xFFFFFFF6u, 0xFFFFFFFFu, 0xFFFFFFFFu};
     fp r = fp_one();
     for (int w = 3; w >= 0; --w) {
         for (int bit = 31; bit >= 0; --bit) {
-            r = d_mul(r, r);
+            r = d_sqr(r);
             if ((e[w] >> bit) & 1u) r = d_mul(r, a);
         }
     }
@@ -315,7 +352,13 @@ GS_HD fp fp_mul(const fp& a, const fp& b) {
 #endif
 }
 GS_HD fp fp_neg(const fp& a) { return fp_sub(fp_zero(), a); }
-GS_HD fp fp_sqr(const fp& a) { return fp_mul(a, a); }
+GS_HD fp fp_sqr(const fp& a) {
+#ifdef __CUDA_ARCH__
+    return d_sqr(a);
+#else
+    return fp_mul(a, a);
+#endif
+}
 
 // shared between host and device -----------------------------------------------------------------
 GS_HD fp fp_pow(fp b, uint64_t e) {

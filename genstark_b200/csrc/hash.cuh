@@ -394,14 +394,17 @@ static inline int hash_columns(Ctx* c, int alg, const HashCols& cols, long long 
 }
 
 // Sharded commit over peer memory (NVLink / NVSwitch): a rank hashes the rows of its cosets and stores every digest straight
-// into the leaf array of the rank that owns that leaf RANGE (leaves are dealt to the ranks in W contiguous ranges), through
-// pointers obtained once with cudaIpcOpenMemHandle.  The transfer rides under the hashing arithmetic, tile by tile; what is
-// left of the exchange is one barrier.  Replaces hash -> local buffer -> ncclSend/ncclRecv all-to-all -> permutation kernel
-// (0.34 ms for the evaluation tree at 2 GPUs, 165 - 190 GB/s).  local row il <-> global leaf i = q * E + j0 + jl.
-struct PeerTrees { uint32_t* base[8]; };     // per rank: the tree (2n digests, leaves at [n, 2n)) this commit builds there
+// into the memory of the rank that owns that leaf RANGE (leaves are dealt to the ranks in W contiguous ranges), through
+// pointers obtained once with cudaIpcOpenMemHandle.  The transfer rides under the hashing arithmetic; what is left of the
+// exchange is one barrier.  Replaces hash -> local buffer -> ncclSend/ncclRecv all-to-all (0.34 ms for the evaluation tree
+// at 2 GPUs, 165 - 190 GB/s).  The digests land in the owner's STAGING buffer in the sender's order -- block [sender][k], the
+// layout the all-to-all produced -- so a warp stores 1 KB of consecutive bytes per instruction pair; storing each digest at its
+// final leaf position instead (32 isolated bytes every E * 32) was measured at 93 GB/s per rank on 8 GPUs.  The owner puts its
+// range in leaf order with permute_digests_kernel after the barrier (local, 64 bytes of traffic per leaf).
+// local row il of this rank: block s = il / blk goes to rank s, at [rank][il - s * blk].
+struct PeerStage { uint32_t* base[8]; };     // per rank: its staging buffer (W * blk digests)
 template <int ALG>
-__global__ void __launch_bounds__(256) hash_columns_scatter_kernel(const HashCols cols, long long n_loc, const PeerTrees peers, long long n,
-                                                                   int log_e, int log_el, int j0, int log_range) {
+__global__ void __launch_bounds__(256) hash_columns_scatter_kernel(const HashCols cols, long long n_loc, const PeerStage peers, long long blk, int rank) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long il = (long long)blockIdx.x * blockDim.x + threadIdx.x; il < n_loc; il += stride) {
         uint32_t d[8];
@@ -418,24 +421,23 @@ __global__ void __launch_bounds__(256) hash_columns_scatter_kernel(const HashCol
             auto get = [&](int w) -> uint32_t { return cols.col[w >> 2][il].v[w & 3]; };
             hash_words<ALG>(get, cols.ncols * 4, d);
         }
-        const long long i = ((il >> log_el) << log_e) + j0 + (il & ((1ll << log_el) - 1));
-        store_digest(peers.base[i >> log_range] + 8 * (n + i), d);
+        const long long s = il / blk;
+        store_digest(peers.base[s] + 8 * ((long long)rank * blk + (il - s * blk)), d);
     }
 }
-static inline int hash_columns_scatter(Ctx* c, int alg, const HashCols& cols, long long n_loc, const PeerTrees& peers, long long n,
-                                       int log_e, int log_el, int j0, int log_w) {
+static inline int hash_columns_scatter(Ctx* c, int alg, const HashCols& cols, long long n_loc, const PeerStage& peers, long long blk, int rank) {
     if (cols.ncols < 1 || cols.ncols > GS_MAX_HASH_COLS) return c->fail(GS_E_ARG, "1..%d columns per leaf", GS_MAX_HASH_COLS);
-    int log_n = 0; while ((1ll << log_n) < n) ++log_n;
     const unsigned g = grid_for(c, n_loc, 256);
     ProfScope ps(c, "hash_columns");
-    if (alg == HASH_BLAKE2S) hash_columns_scatter_kernel<HASH_BLAKE2S><<<g, 256, 0, c->stream>>>(cols, n_loc, peers, n, log_e, log_el, j0, log_n - log_w);
-    else if (alg == HASH_SHA256) hash_columns_scatter_kernel<HASH_SHA256><<<g, 256, 0, c->stream>>>(cols, n_loc, peers, n, log_e, log_el, j0, log_n - log_w);
+    if (alg == HASH_BLAKE2S) hash_columns_scatter_kernel<HASH_BLAKE2S><<<g, 256, 0, c->stream>>>(cols, n_loc, peers, blk, rank);
+    else if (alg == HASH_SHA256) hash_columns_scatter_kernel<HASH_SHA256><<<g, 256, 0, c->stream>>>(cols, n_loc, peers, blk, rank);
     else return c->fail(GS_E_ARG, "unknown hash algorithm");
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return c->cuda_fail(e, "hash_columns_scatter_kernel");
     c->launches++;
     return GS_OK;
 }
+struct PeerTrees { uint32_t* base[8]; };     // per rank: the tree a commit builds there (sub-tree roots are stored into all of them)
 
 static inline int hash_rows(Ctx* c, int alg, const void* buf, int row_bytes, long long n, uint32_t* out) {
     if (row_bytes <= 0 || row_bytes % 16) return c->fail(GS_E_ARG, "row size must be a positive multiple of 16 bytes");

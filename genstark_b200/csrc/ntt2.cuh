@@ -23,6 +23,7 @@
 // (tile x coset) and every CTA takes one contiguous range of units (2 CTAs per SM, 148 SMs: a 2^20 LDE is 2048 units,
 // 6.9 per CTA -- 98.8 % balanced, where 256 tiles over 296 CTA slots would be 86 %).
 #pragma once
+#include <cuda.h>
 #include "ntt.cuh"
 
 namespace gs {
@@ -276,8 +277,8 @@ GS_D void ntt2_load_small_table(fp* s_tw, const fp* tw_small, int inverse) {
 template <int LOG_R, bool LDE>
 __global__ void __launch_bounds__(256, 2) ntt2_pass1_kernel(const Ntt2Params P) {
     using S = TileShape<LOG_R>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    fp* s_tw = reinterpret_cast<fp*>(smem_raw);
+    extern __shared__ __align__(128) unsigned char ntt2_smem[];
+    fp* s_tw = reinterpret_cast<fp*>(ntt2_smem);
     fp* X = s_tw + 1024;
     const int t = threadIdx.x;
     ntt2_load_small_table(s_tw, P.tw_small, P.inverse);
@@ -339,8 +340,8 @@ __global__ void __launch_bounds__(256, 2) ntt2_pass1_kernel(const Ntt2Params P) 
 template <int LOG_R>
 __global__ void __launch_bounds__(256, 2) ntt2_pass2_kernel(const Ntt2Params P) {
     using S = TileShape<LOG_R>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    fp* s_tw = reinterpret_cast<fp*>(smem_raw);
+    extern __shared__ __align__(128) unsigned char ntt2_smem[];
+    fp* s_tw = reinterpret_cast<fp*>(ntt2_smem);
     fp* X = s_tw + 1024;
     const int t = threadIdx.x;
     ntt2_load_small_table(s_tw, P.tw_small, P.inverse);
@@ -370,8 +371,8 @@ template <int LOG_R>
 __global__ void __launch_bounds__(256, 2) ntt2_pass2_tma_kernel(const Ntt2Params P) {
     using S = TileShape<LOG_R>;
     constexpr int R = 1 << LOG_R, PITCH = R + 2;          // landing pitch: 32 B of padding keeps the column reads off one bank
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    fp* s_tw = reinterpret_cast<fp*>(smem_raw);
+    extern __shared__ __align__(128) unsigned char ntt2_smem[];
+    fp* s_tw = reinterpret_cast<fp*>(ntt2_smem);
     fp* X = s_tw + 1024;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(X + NTT2_X_ELEMS);      // [0] full, [1] empty
     const int t = threadIdx.x;
@@ -411,6 +412,60 @@ __global__ void __launch_bounds__(256, 2) ntt2_pass2_tma_kernel(const Ntt2Params
             [&]() { mbar_arrive(&bars[1]); },
             [&]() { if (t == 0 && u + 1 < u_end) { mbar_wait(&bars[1], phase); issue(u + 1); } },
             [&](int k, int cc, fp v) { st_fp(dst + ((size_t)k << log_ucols) + cc, v); });
+        phase ^= 1u;
+    }
+}
+
+// plain (non-LDE) pass 1 with its tiles fetched by the TMA engine: a tile is R rows of C * 16 contiguous bytes at a stride of
+// m * 16 bytes -- a 2-D box of the source seen as a [rows][R][m * 4 x u32] tensor (cuTensorMapEncodeTiled on the host, boxes of at
+// most 256 rows).  Same prefetch protocol as ntt2_pass2_tma_kernel; the box lands dense, row-major, which is the layout the
+// first radix reads.  A/B against the plain-load kernel in profiles/ (GS_NTT2_TMA bit 1).
+template <int LOG_R>
+__global__ void __launch_bounds__(256, 2) ntt2_pass1_tma_kernel(const Ntt2Params P, const __grid_constant__ CUtensorMap tmap) {
+    using S = TileShape<LOG_R>;
+    constexpr int R = 1 << LOG_R, BOX_ROWS = R < 256 ? R : 256;
+    extern __shared__ __align__(128) unsigned char ntt2_smem[];
+    fp* s_tw = reinterpret_cast<fp*>(ntt2_smem);
+    fp* X = s_tw + 1024;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(X + NTT2_X_ELEMS);
+    const int t = threadIdx.x;
+    ntt2_load_small_table(s_tw, P.tw_small, P.inverse);
+    const int rest = t >> S::LOG_C, c = t & (S::C - 1);
+    const unsigned u_begin = (unsigned)(((unsigned long long)P.units * blockIdx.x) / gridDim.x);
+    const unsigned u_end = (unsigned)(((unsigned long long)P.units * (blockIdx.x + 1)) / gridDim.x);
+    const int log_tiles = P.log_m - S::LOG_C;
+    if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 256); mbar_fence_init(); }
+    __syncthreads();
+    auto issue = [&](unsigned u) {
+        const unsigned tile = u & ((1u << log_tiles) - 1u), row = u >> log_tiles;
+        fence_proxy_async();
+        mbar_expect_tx(&bars[0], 4096u * 16u);
+#pragma unroll 1
+        for (int b = 0; b < R / BOX_ROWS; ++b)
+            tma_load_3d(X + b * BOX_ROWS * S::C, &tmap, (int)(tile << S::LOG_C) * 4, b * BOX_ROWS, (int)row, &bars[0]);
+    };
+    if (t == 0 && u_begin < u_end) issue(u_begin);
+    unsigned phase = 0;
+    const unsigned long long pol_keep = l2_policy_keep(), pol_stream = l2_policy_stream();
+    for (unsigned u = u_begin; u < u_end; ++u) {
+        const unsigned tile = u & ((1u << log_tiles) - 1u), row = u >> log_tiles;
+        const unsigned col0 = tile << S::LOG_C;
+        mbar_wait(&bars[0], phase);
+        fp x[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a) x[a] = ld_fp(X + (a * S::RR + rest) * S::C + c);
+        tile_front<LOG_R>(x, X, s_tw, t);
+        fp* dst = P.dst + (long long)row * P.dst_row_stride + col0;
+        const fp* twi = P.tw_inter + col0;
+        const int log_m = P.log_m, inverse = P.inverse;
+        tile_final_split<LOG_R>(X, s_tw, t,
+            [&]() { mbar_arrive(&bars[1]); },
+            [&]() { if (t == 0 && u + 1 < u_end) { mbar_wait(&bars[1], phase); issue(u + 1); } },
+            [&](int k, int cc, fp v) {
+                const size_t idx = ((size_t)k << log_m) + cc;
+                if (k != 0 || inverse) v = NTT2_MUL(v, ldg_hint_fp(twi + idx, pol_keep));
+                st_hint_fp(dst + idx, v, pol_stream);
+            });
         phase ^= 1u;
     }
 }

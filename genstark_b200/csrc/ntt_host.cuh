@@ -137,10 +137,44 @@ static inline cudaError_t ntt2_launch_pass1(const Ntt2Params& P, unsigned grid, 
     ntt2_pass1_kernel<LOG_R, LDE><<<grid, 256, NTT2_SMEM, s>>>(P);
     return cudaGetLastError();
 }
-static inline int ntt2_tma_mode() {      // GS_NTT2_TMA bit 0 (default on): pass 2 prefetches its tiles with bulk copies (TMA engine); 0 = plain loads
+static inline int ntt2_tma_mode() {      // GS_NTT2_TMA bit 0 (default on): pass 2 prefetches its tiles with bulk copies (TMA engine); bit 1: the plain pass 1 fetches its
+                                         // tiles through a tensor map (cp.async.bulk.tensor); 0 = plain loads
     static int v = -1;
     if (v < 0) { const char* e = getenv("GS_NTT2_TMA"); v = e ? atoi(e) : 1; }
     return v;
+}
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*GsTensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                           const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline GsTensorMapEncodeTiled tensor_map_encoder() {
+    static GsTensorMapEncodeTiled fn = nullptr; static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr; cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess) fn = (GsTensorMapEncodeTiled)p;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+// the source of a plain pass 1 as a [rows][R][m * 4 x u32] tensor, boxes of C * 4 words x min(R, 256) rows
+template <int LOG_R>
+static inline bool ntt2_pass1_tensor_map(CUtensorMap* tm, const fp* src, long long src_row_stride, int rows, int log_m) {
+    GsTensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc) return false;
+    constexpr int R = 1 << LOG_R, C = 1 << (12 - LOG_R);
+    const cuuint64_t dims[3] = {(cuuint64_t)4 << log_m, (cuuint64_t)R, (cuuint64_t)rows};
+    const cuuint64_t strides[2] = {(cuuint64_t)16 << log_m, (cuuint64_t)src_row_stride * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)C * 4, (cuuint32_t)(R < 256 ? R : 256), 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<fp*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+template <int LOG_R>
+static inline cudaError_t ntt2_launch_pass1_tma(const Ntt2Params& P, const CUtensorMap& tm, unsigned grid, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(ntt2_pass1_tma_kernel<LOG_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT2_SMEM + 128); attr_set = true; }
+    ntt2_pass1_tma_kernel<LOG_R><<<grid, 256, NTT2_SMEM + 128, s>>>(P, tm);
+    return cudaGetLastError();
 }
 template <int LOG_R>
 static inline cudaError_t ntt2_launch_pass2_tma(const Ntt2Params& P, unsigned grid, cudaStream_t s) {
@@ -197,7 +231,13 @@ static inline int ntt2_try(Ctx* c, const fp* src, long long src_stride, fp* dst,
     {
         ProfScope ps(c, lde ? "ntt_column_coset" : "ntt_column");
         if (lde) e = lr1 == 10 ? ntt2_launch_pass1<10, true>(P, grid, c->stream) : lr1 == 9 ? ntt2_launch_pass1<9, true>(P, grid, c->stream) : ntt2_launch_pass1<8, true>(P, grid, c->stream);
-        else e = lr1 == 10 ? ntt2_launch_pass1<10, false>(P, grid, c->stream) : lr1 == 9 ? ntt2_launch_pass1<9, false>(P, grid, c->stream) : ntt2_launch_pass1<8, false>(P, grid, c->stream);
+        else {
+            CUtensorMap tm;
+            const bool tma1 = (ntt2_tma_mode() & 2) && (lr1 == 10 ? ntt2_pass1_tensor_map<10>(&tm, src, src_stride, rows, lr2) : lr1 == 9 ? ntt2_pass1_tensor_map<9>(&tm, src, src_stride, rows, lr2)
+                                                                                                                                        : ntt2_pass1_tensor_map<8>(&tm, src, src_stride, rows, lr2));
+            if (tma1) e = lr1 == 10 ? ntt2_launch_pass1_tma<10>(P, tm, grid, c->stream) : lr1 == 9 ? ntt2_launch_pass1_tma<9>(P, tm, grid, c->stream) : ntt2_launch_pass1_tma<8>(P, tm, grid, c->stream);
+            else e = lr1 == 10 ? ntt2_launch_pass1<10, false>(P, grid, c->stream) : lr1 == 9 ? ntt2_launch_pass1<9, false>(P, grid, c->stream) : ntt2_launch_pass1<8, false>(P, grid, c->stream);
+        }
         if (e != cudaSuccess) return c->cuda_fail(e, "ntt2_pass1_kernel");
         c->launches++;
     }

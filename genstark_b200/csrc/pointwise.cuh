@@ -174,6 +174,32 @@ __global__ void __launch_bounds__(256) modmul_probe_kernel(fp* out, int iters) {
     if (r.v[0] == 0xFFFFFFFFu && r.v[3] == 0x12345u) st_fp(out, r);   // keep the chains alive
 }
 
+// squaring chains (fp_sqr: 10 limb products) at the same shape as modmul_probe_kernel, and a check of fp_sqr against fp_mul(a, a)
+// on edge values and the chain values themselves; *mismatch counts differences
+__global__ void __launch_bounds__(256) sqr_probe_kernel(fp* out, int iters, unsigned* mismatch) {
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    fp a = fp_from_u64(0x9E3779B97F4A7C15ull * (t + 1)), b = fp_from_u64(0xD1B54A32D192ED03ull * (t + 3));
+    fp c2 = fp_from_u64(0x94D049BB133111EBull * (t + 5)), d = fp_from_u64(0xBF58476D1CE4E5B9ull * (t + 7));
+    if (mismatch) {
+        fp edge[6];
+        edge[0] = fp_zero(); edge[1] = fp_one();
+        edge[2].v[0] = 0; edge[2].v[1] = 0xFFFFFFF7u; edge[2].v[2] = 0xFFFFFFFFu; edge[2].v[3] = 0xFFFFFFFFu;      // p - 1
+        edge[3].v[0] = 0xFFFFFFFFu; edge[3].v[1] = 0xFFFFFFFFu; edge[3].v[2] = 0xFFFFFFFFu; edge[3].v[3] = 0x7FFFFFFFu;
+        edge[4].v[0] = 0; edge[4].v[1] = 0; edge[4].v[2] = 0; edge[4].v[3] = 0x80000000u;
+        edge[5].v[0] = 0xFFFFFFFFu; edge[5].v[1] = 8u; edge[5].v[2] = 0; edge[5].v[3] = 0;
+        unsigned bad = 0;
+        for (int k = 0; k < 6; ++k) bad += fp_eq(fp_sqr(edge[k]), fp_mul(edge[k], edge[k])) ? 0u : 1u;
+        fp x = a;
+        for (int k = 0; k < 64; ++k) { const fp s1 = fp_sqr(x), s2 = fp_mul(x, x); bad += fp_eq(s1, s2) ? 0u : 1u; x = fp_add(s1, b); }
+        if (bad) atomicAdd(mismatch, bad);
+    }
+    for (int i = 0; i < iters; ++i) {     // 4 independent chains per thread
+        a = fp_sqr(a); b = fp_sqr(b); c2 = fp_sqr(c2); d = fp_sqr(d);
+    }
+    fp r = fp_add(fp_add(a, b), fp_add(c2, d));
+    if (r.v[0] == 0xFFFFFFFFu && r.v[3] == 0x12345u) st_fp(out, r);
+}
+
 // the NTT's instruction mix: (u, v) -> (u + v, (u - v) * w); 2 butterflies per thread per iteration (scripts/pipe_probe.cu)
 __global__ void __launch_bounds__(256) butterfly_probe_kernel(fp* out, int iters) {
     const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -67,7 +67,8 @@ struct Stark : public AirHost {
     DevBuf d_dig_loc, d_dig_all;      // commit boundary: local digests / all-gathered digests before the permutation
     DevBuf d_fri_rep;                 // sharded prover: the gathered FRI layer and the replicated layers behind it
     // peer memory (cudaIpc): every rank's d_tree / d_fri_trees as seen from this rank, re-exchanged when an allocation moves
-    struct PeerMap { void* key = nullptr; std::vector<void*> ptr; bool ok = false; } peer_tree, peer_fri, peer_sync;
+    struct PeerMap { void* key = nullptr; std::vector<void*> ptr; bool ok = false; } peer_tree, peer_fri, peer_sync, peer_stage;
+    DevBuf d_stage;                   // staging buffer the peers store their digest blocks into (never reallocated inside a prove)
     DevBuf d_ipc, d_sync;             // d_sync: [0, 8) barrier flags written by the peers, [8] local barrier counter, [9] timeout flag
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     DevBuf d_epoch;                         // prove counter, copied behind each FRI root so the host can poll for it
@@ -76,7 +77,7 @@ struct Stark : public AirHost {
     ~Stark() {
         for (DevBuf* b : {&d_instrs, &d_consts, &d_cyc, &d_u, &d_trace, &d_poly, &d_pe, &d_in_trace, &d_in_poly, &d_in_e, &d_work, &d_tree,
                           &d_zb, &d_zbs, &d_l, &d_c, &d_fri, &d_fri_trees, &d_params, &d_small, &d_idx, &d_gather}) b->release();
-        d_sync.release();
+        d_sync.release(); d_stage.release();
         if (h_trace) cudaFreeHost(h_trace);
         if (g_commit.exec) cudaGraphExecDestroy(g_commit.exec);
         if (g_fri.exec) cudaGraphExecDestroy(g_fri.exec);
@@ -84,7 +85,7 @@ struct Stark : public AirHost {
         if (ev1) cudaEventDestroy(ev1);
         if (ev2) cudaEventDestroy(ev2);
         d_epoch.release(); d_dig_loc.release(); d_dig_all.release(); d_fri_rep.release(); d_ipc.release();
-        for (PeerMap* m : {&peer_tree, &peer_fri, &peer_sync}) for (size_t r = 0; r < m->ptr.size(); ++r) if (m->ptr[r] && (int)r != (ctx ? ctx->rank : 0)) cudaIpcCloseMemHandle(m->ptr[r]);
+        for (PeerMap* m : {&peer_tree, &peer_fri, &peer_sync, &peer_stage}) for (size_t r = 0; r < m->ptr.size(); ++r) if (m->ptr[r] && (int)r != (ctx ? ctx->rank : 0)) cudaIpcCloseMemHandle(m->ptr[r]);
     }
 };
 
@@ -257,7 +258,13 @@ static inline int commit_split_tree_peer(Stark* S, long long n, uint32_t* tree, 
     const Shard& sh = S->shard;
     int log_w = 0; while ((1 << log_w) < sh.world) ++log_w;
     int rc;
-    if ((rc = shard_barrier(S, nullptr))) return rc;                       // every leaf range is whole
+    if ((rc = shard_barrier(S, nullptr))) return rc;                       // every rank's block has landed in the staging buffer
+    // leaves of this rank's range, in leaf order: leaf[(q - q0) * E + s * El + jl] = stage[s][(q - q0) * El + jl]
+    const long long blk = ((n >> sh.log_e) >> log_w) << sh.log_el;
+    uint32_t* leaves = tree + 8 * (n + (long long)sh.rank * (n >> log_w));
+    const long long total = (blk << log_w) * 2;
+    permute_digests_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(S->d_stage.as<uint4>(), reinterpret_cast<uint4*>(leaves), blk, sh.log_el, log_w);
+    c->launches++;
     if ((rc = merkle_build_range(c, S->hash_alg, tree, n, log_w, sh.rank))) return rc;
     if ((rc = shard_barrier(S, &trees))) return rc;                        // sub-tree roots everywhere
     return merkle_build_top(c, S->hash_alg, tree, sh.world);
@@ -618,7 +625,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     unsigned long long gkey = 1469598103934665603ull;
     for (const DevBuf* b : {&S->d_trace, &S->d_poly, &S->d_pe, &S->d_work, &S->d_tree, &S->d_l, &S->d_fri, &S->d_fri_trees, &S->d_params,
                             &S->d_small, &S->d_in_trace, &S->d_in_poly, &S->d_in_e, &S->d_c, &S->d_u, &S->d_cyc, &S->d_instrs, &S->d_consts, &S->d_epoch,
-                            &S->d_dig_loc, &S->d_dig_all, &S->d_fri_rep, &S->d_sync})
+                            &S->d_dig_loc, &S->d_dig_all, &S->d_fri_rep, &S->d_sync, &S->d_stage})
         gkey = (gkey ^ (unsigned long long)(uintptr_t)b->p) * 1099511628211ull;
     gkey = (gkey ^ (unsigned long long)S->keep_intermediates) * 1099511628211ull;
     // trees with at least 2^14 leaves per ... are split across the ranks; small ones are replicated
@@ -628,10 +635,12 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
     bool peers_ok = false;
     if (sharded && shard_peer_enabled() && sh.world <= 8 && e_split) {
         if (!S->d_sync.p) { if ((rc = S->d_sync.ensure(c, 256))) return rc; GS_CUDA(c, cudaMemsetAsync(S->d_sync.p, 0, 256, c->stream)); GS_CUDA(c, cudaStreamSynchronize(c->stream)); }
-        if ((rc = peer_map_update(S, S->peer_tree, S->d_tree.p)) || (rc = peer_map_update(S, S->peer_fri, S->d_fri_trees.p))) return rc;
+        if ((rc = S->d_stage.ensure(c, (size_t)NL * 32))) return rc;            // W blocks of NL / W digests (the largest commit)
+        if ((rc = peer_map_update(S, S->peer_tree, S->d_tree.p)) || (rc = peer_map_update(S, S->peer_fri, S->d_fri_trees.p)) ||
+            (rc = peer_map_update(S, S->peer_stage, S->d_stage.p))) return rc;
         static const bool peer_barrier = !(getenv("GS_SHARD_PEER_BARRIER") && atoi(getenv("GS_SHARD_PEER_BARRIER")) == 0);
         if (peer_barrier && (rc = peer_map_update(S, S->peer_sync, S->d_sync.p))) return rc;
-        peers_ok = S->peer_tree.ok && S->peer_fri.ok;
+        peers_ok = S->peer_tree.ok && S->peer_fri.ok && S->peer_stage.ok;
     }
     auto commit_region = [&]() -> int {
         int r2;
@@ -649,8 +658,9 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         if (!sharded) { if ((r2 = hash_columns(c, S->hash_alg, hc, N, e_tree + 8 * N))) return r2; }
         else if (e_split && peers_ok) {
             PeerTrees pt; memset(&pt, 0, sizeof pt);
-            for (int r = 0; r < sh.world; ++r) pt.base[r] = (uint32_t*)S->peer_tree.ptr[r];
-            if ((r2 = hash_columns_scatter(c, S->hash_alg, hc, NL, pt, N, log_e, log_el, sh.j0(), log_w_all))) return r2;
+            PeerStage pst; memset(&pst, 0, sizeof pst);
+            for (int r = 0; r < sh.world; ++r) { pt.base[r] = (uint32_t*)S->peer_tree.ptr[r]; pst.base[r] = (uint32_t*)S->peer_stage.ptr[r]; }
+            if ((r2 = hash_columns_scatter(c, S->hash_alg, hc, NL, pst, NL >> log_w_all, sh.rank))) return r2;
             if (timing) mark("Serialized evaluations of P(x) and S(x) polynomials", true);
             if ((r2 = commit_split_tree_peer(S, N, e_tree, pt))) return r2;
         }
@@ -915,9 +925,10 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             if (split_ok(Q) && peers_ok) {
                 ly.split = true;
                 PeerTrees pt; memset(&pt, 0, sizeof pt);
+                PeerStage pst; memset(&pst, 0, sizeof pst);
                 const size_t off = (size_t)(ly.tree - S->d_fri_trees.as<uint32_t>());
-                for (int r = 0; r < sh.world; ++r) pt.base[r] = (uint32_t*)S->peer_fri.ptr[r] + off;
-                if ((rc = hash_columns_scatter(c, S->hash_alg, hc, QL, pt, Q, log_e, log_el, sh.j0(), log_w_all))) return rc;
+                for (int r = 0; r < sh.world; ++r) { pt.base[r] = (uint32_t*)S->peer_fri.ptr[r] + off; pst.base[r] = (uint32_t*)S->peer_stage.ptr[r]; }
+                if ((rc = hash_columns_scatter(c, S->hash_alg, hc, QL, pst, QL >> log_w_all, sh.rank))) return rc;
                 if ((rc = commit_split_tree_peer(S, Q, ly.tree, pt))) return rc;
             } else {
             if ((rc = hash_columns(c, S->hash_alg, hc, QL, S->d_dig_loc.as<uint32_t>()))) return rc;

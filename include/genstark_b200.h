@@ -214,6 +214,8 @@ int gs_lde_cosets_into(gs_ctx* ctx, const gs_mat* src, gs_mat* dst, gs_mat* work
 int gs_mat_fill_random(gs_ctx* ctx, gs_mat* m, uint64_t seed);
 /* runs blocks x 256 threads x (4*iters) dependent modular multiplications; returns kernel ms */
 int gs_debug_modmul_probe(gs_ctx* ctx, int blocks, int iters, float* ms_out);
+/* squaring chains (dedicated 10-product squaring) at the same shape; *mismatches counts disagreements with a * a */
+int gs_debug_sqr_probe(gs_ctx* ctx, int blocks, int iters, float* ms_out, int* mismatches);
 /* same for the NTT's instruction mix: blocks x 256 threads x 2 butterflies (u + v, (u - v) * w) x iters */
 int gs_debug_butterfly_probe(gs_ctx* ctx, int blocks, int iters, float* ms_out);
 

@@ -33,3 +33,12 @@ def test_mul_extremes():
     assert f.mulVectorElements(A, B).toValues() == [(x * y) % P128 for x, y in zip(a, b)]
     assert f.addVectorElements(A, B).toValues() == [(x + y) % P128 for x, y in zip(a, b)]
     assert f.subVectorElements(A, B).toValues() == [(x - y) % P128 for x, y in zip(a, b)]
+
+
+def test_dedicated_squaring_equals_multiplication():
+    """fp_sqr (10 limb products, csrc/fp128.cuh) against fp_mul(a, a): edge values and 64-step chains on 2^15 threads"""
+    import ctypes as C
+    f = gpu_field()
+    ms, bad = C.c_float(), C.c_uint32(12345)
+    f.ctx.check(f._lib.gs_debug_sqr_probe(f.ctx.handle, 128, 16, C.byref(ms), C.byref(bad)))
+    assert bad.value == 0
