@@ -88,9 +88,11 @@ static inline std::string compose_emit_source(const AirHost& A) {
       << "#define GS_MAX_COLS " << GS_MAX_COLS << "\n"
       << GS_FP_TYPE_SRC << "\n" << GS_FP_BASIC_SRC << "\n" << GS_FP_DEVICE_SRC << "\n" << GS_FP_LDST_SRC << "\n"
       << GS_COMPOSE_PARAMS_SRC << "\n" << GS_COMPOSE_DEVICE_SRC << "\n";
-    // resident CTAs per SM the register allocation aims at (GS_COMPOSE_MINB, default 3: 80 registers; measured in profiles/)
-    int minb = 3; if (const char* e = getenv("GS_COMPOSE_MINB")) { minb = atoi(e); if (minb < 1 || minb > 8) minb = 3; }
-    o << "extern \"C\" __global__ void __launch_bounds__(256, " << minb << ") gs_compose_jit(const ComposeParams* __restrict__ Pp) {\n"
+    // GS_COMPOSE_MINB = resident CTAs per SM the register allocation is held to (experiment knob).  Default: none -- MiMC's evaluator
+    // takes 80 registers either way (3 / 4 / 5: 0.444 / 0.443 / 0.456 ms), while a cap of 85 registers spills Poseidon's 12-register
+    // evaluator (config 5: compose 3.9 -> 4.9 ms)
+    int minb = 0; if (const char* e = getenv("GS_COMPOSE_MINB")) { minb = atoi(e); if (minb < 1 || minb > 8) minb = 0; }
+    o << "extern \"C\" __global__ void __launch_bounds__(256" << (minb ? ", " + std::to_string(minb) : std::string()) << ") gs_compose_jit(const ComposeParams* __restrict__ Pp) {\n"
          "  const ComposeParams& P = *Pp;\n"
          "  const long long stride = (long long)gridDim.x * blockDim.x;\n"
          "  const unsigned long long lmask = (unsigned long long)P.n_loc - 1ull;\n"

@@ -1,11 +1,13 @@
 """Summarise an `ncu --set full` report into profiles/: per-launch table (markdown) + per-class DRAM traffic (JSON).
-Usage (CPU box): ncu -i gpurun_out/prof.ncu-rep --page raw --csv > raw.csv; python scripts/ncu_summarize.py raw.csv OUT_PREFIX"""
+Usage (CPU box): ncu -i gpurun_out/prof.ncu-rep --page raw --csv > raw.csv; python scripts/ncu_summarize.py raw.csv OUT_PREFIX [LAST_N]
+LAST_N: only the last N launches of the capture (the launches of the last prove)."""
 import csv
 import json
 import sys
 
 CLASSES = [('hash_columns', 'hash_columns'), ('merkle_level', 'merkle_build'), ('merkle_top', 'merkle_build'), ('merkle_sub', 'merkle_build'),
-           ('merkle_tail', 'merkle_build'), ('compose', 'compose'), ('ntt_pass', 'ntt'), ('fri_fold', 'fri_fold')]
+           ('merkle_tail', 'merkle_build'), ('compose', 'compose'), ('ntt_pass', 'ntt'), ('ntt2_', 'ntt'), ('fri_fold', 'fri_fold'),
+           ('fri_challenge', 'fri_fold'), ('fri_tail', 'fri_tail'), ('derive_coeffs', 'derive_coeffs'), ('gather_chunks', 'gather_queries')]
 COLS = [('time_us', 'gpu__time_duration.sum'), ('regs', 'launch__registers_per_thread'), ('grid', 'launch__grid_size'),
         ('dram_rd_MB', 'dram__bytes_read.sum'), ('dram_wr_MB', 'dram__bytes_write.sum'),
         ('sm_thr_pct', 'sm__throughput.avg.pct_of_peak_sustained_elapsed'), ('dram_thr_pct', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'),
@@ -13,9 +15,11 @@ COLS = [('time_us', 'gpu__time_duration.sum'), ('regs', 'launch__registers_per_t
         ('fmaheavy_pipe_pct', 'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed'), ('warps_active_pct', 'sm__warps_active.avg.pct_of_peak_sustained_active')]
 
 
-def main(raw, prefix):
+def main(raw, prefix, last_n=0):
     rows = list(csv.reader(open(raw)))
     hdr, units = rows[0], rows[1]
+    if last_n:
+        rows = rows[:2] + rows[2:][-last_n:]
     ki = hdr.index('Kernel Name')
     table, classes = [], {}
     for r in rows[2:]:
@@ -51,4 +55,4 @@ def main(raw, prefix):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
