@@ -103,6 +103,11 @@ export class B200Field {
     }
     subMatrixElementsFromVectors(vectors: B200Matrix[], m: B200Matrix): B200Matrix { return guarded(() => this.binary(1, this.newMatrixFromVectors(vectors), m)); }
     divMatrixElements(a: B200Matrix, b: B200Matrix): B200Matrix { return this.wrap(guarded(() => native.vecDiv(this.ctx, a.handle, b.handle))); }
+    expVectorElements(a: B200Matrix, exponent: bigint): B200Matrix {
+        if (exponent < 0n) return this.expVectorElements(this.divVectorElements(this.newVectorFrom(new Array(a.length).fill(1n)), a), -exponent);
+        return this.wrap(guarded(() => native.vecExp(this.ctx, a.handle, toBytes16(exponent))));
+    }
+    mulMatrixByVector(m: B200Matrix, v: B200Matrix): B200Matrix { return this.wrap(guarded(() => native.matMulVector(this.ctx, m.handle, v.handle))); }
     combineVectors(a: B200Matrix, b: B200Matrix): bigint { return fromBytes16(guarded(() => native.vecCombine(this.ctx, a.handle, b.handle))); }
     combineManyVectors(vectors: B200Matrix[], coefficients: B200Matrix): B200Matrix {
         return this.wrap(guarded(() => native.vecCombineMany(this.ctx, vectors.map(v => v.handle), coefficients.toBuffer())));

@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
         'gs_timer_end': (i32, [vp, P(C.c_float)]),
         'gs_ntt_into': (i32, [vp, vp, vp, vp, i32]),
         'gs_stark_last_error': (cp, [vp]),
+        'gs_vec_exp': (i32, [vp, vp, cp, P(vp)]),
+        'gs_mat_mul_vector': (i32, [vp, vp, vp, P(vp)]),
         'gs_lde_cosets_into': (i32, [vp, vp, vp, vp, i32, i32]),
         'gs_mat_fill_random': (i32, [vp, vp, C.c_uint64]),
         'gs_stark_verify': (i32, [cp, C.c_size_t, i32, i32, i32, cp, i32, cp, C.c_size_t, cp, C.c_char_p, C.c_size_t]),

@@ -232,6 +232,36 @@ int gs_vec_binary(gs_ctx* c, int op, const gs_mat* a, const gs_mat* b, const uin
     return rc;
 }
 
+// expVectorElements(a, e) with a non-negative exponent below 2^128 (16 little-endian bytes); the Python / TypeScript wrappers turn a
+// negative exponent into the inverse first, as galois does
+int gs_vec_exp(gs_ctx* c, const gs_mat* a, const uint8_t* exponent16, gs_mat** out) {
+    if (!c || !a || !exponent16 || !out) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    int rc = gs_mat_alloc(c, a->rows, a->cols, out);
+    if (rc != GS_OK) return rc;
+    fp e; memcpy(&e, exponent16, 16);
+    const long long n = a->rows * a->cols;
+    long long blocks = (n + 255) / 256; const long long cap = (long long)c->sm_count * 16; if (blocks > cap) blocks = cap;
+    vec_exp_kernel<<<(unsigned)(blocks > 0 ? blocks : 1), 256, 0, c->stream>>>(a->data, e, (*out)->data, n);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { gs_mat_free(*out); *out = nullptr; return c->cuda_fail(err, "vec_exp_kernel"); }
+    c->launches++;
+    return GS_OK;
+}
+// mulMatrixByVector(m, v): m is rows x cols, v holds cols elements (any shape); out is a vector of `rows` elements
+int gs_mat_mul_vector(gs_ctx* c, const gs_mat* m, const gs_mat* v, gs_mat** out) {
+    if (!c || !m || !v || !out) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    if (v->rows * v->cols != m->cols) return c->fail(GS_E_ARG, "vector length %lld does not match the matrix (%lld columns)", v->rows * v->cols, m->cols);
+    cudaSetDevice(c->device);
+    int rc = gs_mat_alloc(c, 1, m->rows, out);
+    if (rc != GS_OK) return rc;
+    mat_vec_kernel<<<(unsigned)((m->rows + 127) / 128), 128, 0, c->stream>>>(m->data, v->data, (*out)->data, m->rows, m->cols);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) { gs_mat_free(*out); *out = nullptr; return c->cuda_fail(err, "mat_vec_kernel"); }
+    c->launches++;
+    return GS_OK;
+}
+
 // divVectorElements(a, b) = a * inv(b) with inv(0) = 0   (CompositionPolynomial.ts:117, BoundaryConstraints.ts:92)
 int gs_vec_div(gs_ctx* c, const gs_mat* a, const gs_mat* b, gs_mat** out) {
     if (!c || !a || !b || !out) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;

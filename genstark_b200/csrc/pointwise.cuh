@@ -44,6 +44,34 @@ static inline int vec_binary(Ctx* c, int op, const fp* a, const fp* b, const fp*
     return GS_OK;
 }
 
+// expVectorElements(v, e): out[i] = v[i]^e, e < 2^128 given as four 32-bit words (examples/poseidon/utils.ts:37: the S-box of the
+// plain Poseidon implementation the example checks its STARK against)
+__global__ void __launch_bounds__(256) vec_exp_kernel(const fp* __restrict__ a, fp e, fp* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int top = 127;
+    while (top > 0 && !((e.v[top >> 5] >> (top & 31)) & 1u)) --top;
+    const bool zero_exp = (e.v[0] | e.v[1] | e.v[2] | e.v[3]) == 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const fp x = ld_fp(a + i);
+        fp r = fp_one();
+        if (!zero_exp) {
+            for (int bit = top; bit >= 0; --bit) {
+                r = fp_sqr(r);
+                if ((e.v[bit >> 5] >> (bit & 31)) & 1u) r = fp_mul(r, x);
+            }
+        }
+        st_fp(out + i, r);
+    }
+}
+// mulMatrixByVector(m, v): out[r] = sum_c m[r][c] * v[c]   (examples/poseidon/utils.ts:45: the MDS layer); one thread per row
+__global__ void __launch_bounds__(128) mat_vec_kernel(const fp* __restrict__ m, const fp* __restrict__ v, fp* __restrict__ out, long long rows, long long cols) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    fp acc = fp_zero();
+    for (long long c = 0; c < cols; ++c) acc = fp_add(acc, fp_mul(ld_fp(m + r * cols + c), ld_fp(v + c)));
+    st_fp(out + r, acc);
+}
+
 // combineManyVectors(V, k): out[i] = sum_m k[m] * V[m][i]   (CompositionPolynomial.ts:105,142; LinearCombination.ts:60)
 struct CombineParams { const fp* v[64]; fp k[64]; int m; };
 __global__ void __launch_bounds__(256) combine_many_kernel(const CombineParams* __restrict__ P, fp* __restrict__ out, long long n) {

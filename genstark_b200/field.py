@@ -218,6 +218,31 @@ class GpuField:
 
     divMatrixElements = divVectorElements
 
+    def expVectorElements(self, a: Matrix, exponent: int) -> Matrix:
+        """a[i]^exponent element-wise; a negative exponent inverts first (galois; examples/poseidon/utils.ts:37)"""
+        exponent = int(exponent)
+        if exponent < 0:
+            inv = self.divVectorElements(self._ones_like(a), a)
+            return self.expVectorElements(inv, -exponent)
+        if exponent >= 1 << 128:
+            exponent %= (P128 - 1)                      # a^(p-1) = 1 for a != 0, and 0^e = 0 for e > 0 either way
+            if exponent == 0:
+                exponent = P128 - 1
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_vec_exp(self.ctx.handle, a.handle, exponent.to_bytes(16, 'little'), C.byref(h)))
+        return Matrix(self.ctx, h)
+
+    def _ones_like(self, a: Matrix) -> Matrix:
+        rows, cols = C.c_int64(), C.c_int64()
+        self._lib.gs_mat_shape(a.handle, C.byref(rows), C.byref(cols))
+        return self._from_bytes((1).to_bytes(16, 'little') * (rows.value * cols.value), rows.value, cols.value)
+
+    def mulMatrixByVector(self, m: Matrix, v: Matrix) -> Matrix:
+        """sum_c m[r][c] * v[c] (examples/poseidon/utils.ts:45)"""
+        h = C.c_void_p()
+        self.ctx.check(self._lib.gs_mat_mul_vector(self.ctx.handle, m.handle, v.handle, C.byref(h)))
+        return Matrix(self.ctx, h)
+
     def combineManyVectors(self, vectors: Sequence[Matrix], coefficients) -> Matrix:
         ks = coefficients.toValues() if isinstance(coefficients, Matrix) else list(coefficients)
         arr = (C.c_void_p * len(vectors))(*[v.handle for v in vectors])

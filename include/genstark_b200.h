@@ -87,6 +87,10 @@ int gs_vec_binary(gs_ctx* ctx, int op, const gs_mat* a, const gs_mat* b, const u
 
 /* field.divVectorElements(a, b) = a * inv(b), inv(0) = 0          CompositionPolynomial.ts:117, BoundaryConstraints.ts:92 */
 int gs_vec_div(gs_ctx* ctx, const gs_mat* a, const gs_mat* b, gs_mat** out);
+/* field.expVectorElements(a, e), 0 <= e < 2^128, and field.mulMatrixByVector(m, v): not called from lib/, used by the plain Poseidon
+ * implementation of /root/reference/examples/poseidon/utils.ts:31-45 that the example compares its STARK with */
+int gs_vec_exp(gs_ctx* ctx, const gs_mat* a, const uint8_t* exponent16, gs_mat** out);
+int gs_mat_mul_vector(gs_ctx* ctx, const gs_mat* m, const gs_mat* v, gs_mat** out);
 /* field.combineManyVectors(vectors, coefficients) -> vector        CompositionPolynomial.ts:105,142; LinearCombination.ts:60 */
 int gs_vec_combine_many(gs_ctx* ctx, const gs_mat* const* vectors, int count, const uint8_t* coefficients16, gs_mat** out);
 /* field.getPowerSeries(base, n)                                     CompositionPolynomial.ts:94,132; LowDegreeProver.ts:233 */

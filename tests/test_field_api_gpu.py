@@ -183,3 +183,40 @@ def test_prng_small_polys_digest_and_verify_batch_through_the_mirror():
     proof = tree.proveBatch(idx)
     assert MerkleTree.verifyBatch(tree.root, idx, proof, h)
     assert not MerkleTree.verifyBatch(tree.root, [9, 8, 200, 30], proof, h)
+
+
+def test_exp_vector_elements_and_mul_matrix_by_vector_run_the_examples_plain_poseidon():
+    """examples/poseidon/utils.ts:25-45 written with the FiniteField methods it uses (addVectorElements, expVectorElements,
+    mulMatrixByVector, exp, newVectorFrom / toValues): same digest as the independent integer implementation; plus the two new
+    methods against Python integers, negative and zero exponents included"""
+    import random
+    from genstark_b200 import airs
+    f = gpu_field()
+    p = P128
+    m, rf, rp = airs.POSEIDON_WIDTH, airs.POSEIDON_RF, airs.POSEIDON_RP
+    mds_rows, ark_rows = airs.poseidon_mds(p), airs.poseidon_round_constants(p, m, rf + rp)
+    mds = f.newMatrixFrom(mds_rows)
+    ark = [f.newVectorFrom(r) for r in ark_rows]
+    inputs = [42, 43]
+    state = f.newVectorFrom(inputs + [0] * (m - len(inputs)))
+    for i in range(rf + rp):
+        state = f.addVectorElements(state, ark[i])
+        if i < rf // 2 or i >= rf // 2 + rp:
+            state = f.expVectorElements(state, airs.POSEIDON_ALPHA)
+        else:
+            vals = state.toValues()
+            vals[m - 1] = f.exp(vals[m - 1], airs.POSEIDON_ALPHA)
+            state = f.newVectorFrom(vals)
+        state = f.mulMatrixByVector(mds, state)
+    assert state.toValues()[:2] == airs.poseidon_hash(inputs, p)
+    r = random.Random(7)
+    v = [0, 1, p - 1, 2**127] + [r.randrange(p) for _ in range(29)]
+    V = f.newVectorFrom(v)
+    for e in (0, 1, 5, 2**64 + 3, p - 2, -1, -3):
+        want = [pow(x, e, p) if e >= 0 else (pow(pow(x, p - 2, p), -e, p) if x else 0) for x in v]
+        assert f.expVectorElements(V, e).toValues() == want, e
+    rows = [[r.randrange(p) for _ in range(33)] for _ in range(7)]
+    got = f.mulMatrixByVector(f.newMatrixFrom(rows), V).toValues()
+    assert got == [sum(a * b for a, b in zip(row, v)) % p for row in rows]
+    with pytest.raises(Exception):
+        f.mulMatrixByVector(f.newMatrixFrom(rows), f.newVectorFrom([1, 2, 3]))
