@@ -263,11 +263,31 @@ __global__ void __launch_bounds__(1024) merkle_subtree_kernel(uint32_t* __restri
 // narrow levels.  merkle_build stayed at 0.708 ms: a level is bound by the ~240-deep dependency chain of one compression,
 // which four lanes do not shorten, not by the ~1100 instructions a single lane issues.)
 // Top of a tree in ONE launch: the level with `level_nodes` nodes (heap indices level_nodes .. 2*level_nodes) is cut into
+// x* = field.prng(root) = SHA-256(root) as a big-endian integer mod p (LowDegreeProver.ts:194) computed on the device, so a FRI
+// layer can be folded without a host round trip
+GS_D fp fri_challenge_dev(const uint32_t* root) {
+    uint32_t d[8];
+    auto get = [&](int w) -> uint32_t { return root[w]; };
+    hash_words<HASH_SHA256>(get, 8, d);
+    // d[] holds the digest bytes as little-endian words of the byte string; big-endian integer: byte 0 is most significant
+    uint32_t be[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) be[i] = bswap32(d[i]);          // be[0] = most significant 32 bits
+    fp hi, lo;
+    hi.v[3] = be[0]; hi.v[2] = be[1]; hi.v[1] = be[2]; hi.v[0] = be[3];
+    lo.v[3] = be[4]; lo.v[2] = be[5]; lo.v[1] = be[6]; lo.v[0] = be[7];
+    // canonical residues of the two halves, then lo + hi * 2^128 = lo + hi * (9*2^32 - 1)
+    const fp zero = fp_zero();
+    hi = fp_add(hi, zero); lo = fp_add(lo, zero);                 // fp_add canonicalises (adds 2^128 - p when >= p)
+    fp c9; c9.v[0] = 0xFFFFFFFFu; c9.v[1] = 8u; c9.v[2] = 0; c9.v[3] = 0;
+    return fp_add(lo, fp_mul(hi, c9));
+}
+
 // 512-node subtrees, one per block, reduced in shared memory (every intermediate node is written out); the block that
 // finishes last then reduces the subtree roots to the root.  Replaces a launch per level where a level is a handful of
 // dependent ~1 us compressions and the launch gap costs more than the work.  *counter must be zero and is left zero.
 template <int ALG>
-__global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ nodes, int level_nodes, unsigned* counter) {
+__global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ nodes, int level_nodes, unsigned* counter, fp* challenge_out) {
     __shared__ uint4 s[1024];                                       // 512 digests
     __shared__ int is_last;
     const int leaves = level_nodes < 512 ? level_nodes : 512;
@@ -297,7 +317,12 @@ __global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ 
             }
             __syncthreads();
         }
-        if (pass == 1 || gridDim.x == 1) return;
+        if (pass == 1 || gridDim.x == 1) {
+            // the block that wrote the root also derives the FRI challenge from it (thread 0 holds the root it just stored):
+            // saves the one-thread launch that used to sit between the tree and the fold
+            if (challenge_out && threadIdx.x == 0) st_fp(challenge_out, fri_challenge_dev(reinterpret_cast<const uint32_t*>(&s[0])));
+            return;
+        }
         // the last block to get here owns the remaining gridDim.x subtree roots
         __threadfence();
         if (threadIdx.x == 0) {
@@ -331,25 +356,7 @@ __global__ void __launch_bounds__(1024) merkle_tail_kernel(uint32_t* __restrict_
     }
 }
 
-// x* = field.prng(root) = SHA-256(root) as a big-endian integer mod p (LowDegreeProver.ts:194) computed on the
-// device, so a FRI layer can be folded without a host round trip.  One thread.
-__global__ void fri_challenge_kernel(const uint32_t* __restrict__ root, fp* __restrict__ out) {
-    uint32_t d[8];
-    auto get = [&](int w) -> uint32_t { return root[w]; };
-    hash_words<HASH_SHA256>(get, 8, d);
-    // d[] holds the digest bytes as little-endian words of the byte string; big-endian integer: byte 0 is most significant
-    uint32_t be[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) be[i] = bswap32(d[i]);          // be[0] = most significant 32 bits
-    fp hi, lo;
-    hi.v[3] = be[0]; hi.v[2] = be[1]; hi.v[1] = be[2]; hi.v[0] = be[3];
-    lo.v[3] = be[4]; lo.v[2] = be[5]; lo.v[1] = be[6]; lo.v[0] = be[7];
-    // canonical residues of the two halves, then lo + hi * 2^128 = lo + hi * (9*2^32 - 1)
-    const fp zero = fp_zero();
-    hi = fp_add(hi, zero); lo = fp_add(lo, zero);                 // fp_add canonicalises (adds 2^128 - p when >= p)
-    fp c9; c9.v[0] = 0xFFFFFFFFu; c9.v[1] = 8u; c9.v[2] = 0; c9.v[3] = 0;
-    st_fp(out, fp_add(lo, fp_mul(hi, c9)));
-}
+__global__ void fri_challenge_kernel(const uint32_t* __restrict__ root, fp* __restrict__ out) { st_fp(out, fri_challenge_dev(root)); }
 
 // sharded tree: this rank's slice of every level from `count_local` parents per rank down to its sub-tree root
 // (node 2^log_w + rank), inside one block
@@ -453,7 +460,8 @@ static inline int hash_rows(Ctx* c, int alg, const void* buf, int row_bytes, lon
 
 // nodes: 2n digests with the leaves already at [n, 2n).  log_w > 0: this rank builds only its 1/W slice of every
 // level down to its sub-tree root (node W + rank); the caller gathers the W roots and finishes the top.
-static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long n, int log_w, int rank) {
+// challenge_out (single-GPU trees only): where the block that writes the root also stores x* = prng(root); *challenge_done says whether it did
+static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long n, int log_w, int rank, fp* challenge_out = nullptr, bool* challenge_done = nullptr) {
     if (alg != HASH_BLAKE2S && alg != HASH_SHA256) return c->fail(GS_E_ARG, "unknown hash algorithm");
     long long count = n >> 1;                  // parents of the current level (whole level)
     ProfScope ps(c, "merkle_build");
@@ -469,8 +477,9 @@ static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long
         // the rest of the tree in one launch; the level with 2 * count nodes holds at most 2^16 of them here
         const int level_nodes = (int)(2 * count);
         const unsigned blocks = level_nodes <= 512 ? 1u : (unsigned)(level_nodes / 512);
-        if (alg == HASH_BLAKE2S) merkle_top_kernel<HASH_BLAKE2S><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters);
-        else merkle_top_kernel<HASH_SHA256><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters);
+        if (alg == HASH_BLAKE2S) merkle_top_kernel<HASH_BLAKE2S><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, challenge_out);
+        else merkle_top_kernel<HASH_SHA256><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, challenge_out);
+        if (challenge_done) *challenge_done = challenge_out != nullptr;
         c->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return c->cuda_fail(e, "merkle_top_kernel");
@@ -507,7 +516,9 @@ static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long
     if (e != cudaSuccess) return c->cuda_fail(e, "merkle kernels");
     return GS_OK;
 }
-static inline int merkle_build(Ctx* c, int alg, uint32_t* nodes, long long n) { return merkle_build_range(c, alg, nodes, n, 0, 0); }
+static inline int merkle_build(Ctx* c, int alg, uint32_t* nodes, long long n, fp* challenge_out = nullptr, bool* challenge_done = nullptr) {
+    return merkle_build_range(c, alg, nodes, n, 0, 0, challenge_out, challenge_done);
+}
 // top of a sharded tree once the W sub-tree roots sit at nodes[W .. 2W)
 static inline int merkle_build_top(Ctx* c, int alg, uint32_t* nodes, int world) {
     if (world < 2) return GS_OK;

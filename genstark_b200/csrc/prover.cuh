@@ -418,22 +418,6 @@ struct FriTailParams {
     const uint32_t* epoch;
 };
 
-GS_D fp fri_challenge_dev(const uint32_t* root) {
-    uint32_t d[8];
-    auto get = [&](int w) -> uint32_t { return root[w]; };
-    hash_words<HASH_SHA256>(get, 8, d);
-    uint32_t be[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) be[i] = bswap32(d[i]);
-    fp hi, lo;
-    hi.v[3] = be[0]; hi.v[2] = be[1]; hi.v[1] = be[2]; hi.v[0] = be[3];
-    lo.v[3] = be[4]; lo.v[2] = be[5]; lo.v[1] = be[6]; lo.v[0] = be[7];
-    const fp zero = fp_zero();
-    hi = fp_add(hi, zero); lo = fp_add(lo, zero);
-    fp c9; c9.v[0] = 0xFFFFFFFFu; c9.v[1] = 8u; c9.v[2] = 0; c9.v[3] = 0;
-    return fp_add(lo, fp_mul(hi, c9));
-}
-
 // digests of a level live in shared memory (ping-pong between two buffers: one block barrier per tree level, children read
 // at shared-memory latency); every node is also stored to the tree in HBM, where the query phase reads authentication paths
 template <int ALG>
@@ -936,7 +920,8 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             else if ((rc = commit_gather(S, S->d_dig_loc.as<uint32_t>(), QL, ly.tree + 8 * Q))) return rc;
             }
         }
-        if (!ly.split && (rc = merkle_build(c, S->hash_alg, ly.tree, Q))) return rc;
+        bool have_challenge = false;
+        if (!ly.split && (rc = merkle_build(c, S->hash_alg, ly.tree, Q, (L > 256) ? d_special + (depth & 3) : nullptr, &have_challenge))) return rc;
         if (depth >= 24) return c->fail(GS_E_UNSUPPORTED, "too many FRI layers");
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_ROOT + 32 * depth, ly.tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
         GS_CUDA(c, cudaMemcpyAsync(mb + MB_FLAG + 4 * depth, S->d_epoch.p, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -958,13 +943,13 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             break;
         }
         { ProfScope ps(c, "fri_fold");
-          fri_challenge_kernel<<<1, 1, 0, c->stream>>>(ly.tree + 8, d_special + (depth & 3));
+          if (!have_challenge) { fri_challenge_kernel<<<1, 1, 0, c->stream>>>(ly.tree + 8, d_special + (depth & 3)); c->launches++; }
           FriFoldParams F; F.v = v_cur; F.out = v_next; F.quarter = QL; F.special_x = d_special + (depth & 3);
           F.log_e = log_e; F.log_el = shl ? log_el : log_e; F.j0 = shl ? sh.j0() : 0;
           F.tw_lo = c->tw_lo; F.tw_hi = c->tw_hi; F.log_g = c->log_g; F.log_lo = c->log_lo;
           F.x_shift = 2 * depth + (c->log_g - log_n); F.iota_inv = fp_from_u128(iota_inv); F.quarter_inv = fp_from_u128(quarter_inv);
           fri_fold_kernel<<<grid_for(c, QL, 256), 256, 0, c->stream>>>(F); }
-        c->launches += 2;
+        c->launches += 1;
         v_cur = v_next; v_next += QL;
     }
         return GS_OK;
