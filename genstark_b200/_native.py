@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
         'gs_timer_end': (i32, [vp, P(C.c_float)]),
         'gs_ntt_into': (i32, [vp, vp, vp, vp, i32]),
         'gs_stark_last_error': (cp, [vp]),
+        'gs_host_stark_prove': (i32, [cp, C.c_size_t, i32, i32, i32, cp, i32, cp, cp, cp, C.c_size_t, P(P(C.c_uint8)), P(C.c_size_t), C.c_char_p, C.c_size_t]),
+        'gs_host_stark_verify': (i32, [cp, C.c_size_t, i32, i32, i32, cp, i32, cp, C.c_size_t, cp, C.c_char_p, C.c_size_t]),
         'gs_vec_exp': (i32, [vp, vp, cp, P(vp)]),
         'gs_mat_mul_vector': (i32, [vp, vp, vp, P(vp)]),
         'gs_lde_cosets_into': (i32, [vp, vp, vp, vp, i32, i32]),

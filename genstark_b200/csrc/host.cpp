@@ -3,6 +3,7 @@
 #include "hostair.h"
 #include "hostjit.h"
 #include "verifier.h"
+#include "hoststark64.h"
 
 extern "C" int gs_stark_verify(const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,
                                const uint8_t* assertions, int n_assertions, const uint8_t* proof, size_t proof_len,
@@ -60,4 +61,75 @@ extern "C" int gs_merkle_verify_batch(int alg, const uint8_t root32[32], const u
     Digest root; memcpy(root.data(), root32, 32);
     HostHash H{alg};
     return verify_batch(root, std::vector<uint32_t>(indexes, indexes + count), values, nodes, (int)depth, H) ? 1 : 0;
+}
+
+// ---- prime fields of at most 64 bits: Stark.prove / Stark.verify on the host (hoststark64.h).  Elements cross the ABI as the same
+// 16-byte little-endian values as everywhere else (assertion values, initial state, input traces); the proof uses the field's own
+// element size.  Refuses the 128-bit STARK field: that one has a GPU path and no CPU fallback.
+namespace {
+thread_local std::vector<uint8_t> g_small_proof;
+bool small_elem(const gs::small::Field& F, const uint8_t* p16, uint64_t* v) {
+    for (int i = 8; i < 16; ++i) if (p16[i]) return false;
+    uint64_t x = 0; for (int i = 0; i < 8; ++i) x |= (uint64_t)p16[i] << (8 * i);
+    *v = x; return x < F.p;
+}
+int small_setup(const uint8_t* air_blob, size_t blob_len, const uint8_t* assertions, int n_assertions, gs::small::Air& A,
+                std::vector<gs::small::Assertion64>& as, std::string& err) {
+    int code = GS_OK;
+    err = gs::small::parse_air64(air_blob, blob_len, A, &code);
+    if (code != GS_OK) return code;
+    as.resize(n_assertions > 0 ? n_assertions : 0);
+    for (int i = 0; i < n_assertions; ++i) {
+        const uint8_t* p = assertions + 24 * (size_t)i;
+        memcpy(&as[i].reg, p, 4); memcpy(&as[i].step, p + 4, 4);
+        if (!small_elem(A.F, p + 8, &as[i].value)) { err = "non-canonical assertion value"; return GS_E_ARG; }
+    }
+    return GS_OK;
+}
+bool small_traces(const gs::small::Air& A, const uint8_t* blob, int count, std::vector<gs::small::Vec>& out) {
+    const size_t T = (size_t)1 << A.log_t;
+    out.assign(count, gs::small::Vec(T));
+    for (int k = 0; k < count; ++k) for (size_t s = 0; s < T; ++s) if (!small_elem(A.F, blob + 16 * ((size_t)k * T + s), &out[k][s])) return false;
+    return true;
+}
+}  // namespace
+
+extern "C" int gs_host_stark_prove(const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,
+                                   const uint8_t* assertions, int n_assertions, const uint8_t* init_state16, const uint8_t* input_traces,
+                                   const uint8_t* shapes_blob, size_t shapes_len, const uint8_t** proof_out, size_t* proof_len,
+                                   char* err_buf, size_t err_cap) {
+    using namespace gs;
+    auto fail = [&](int code, const std::string& m) { if (err_buf && err_cap) snprintf(err_buf, err_cap, "%s", m.c_str()); return code; };
+    if (!air_blob || !assertions || !init_state16 || !proof_out || !proof_len) return fail(GS_E_ARG, "null argument");
+    if ((hash_alg != 0 && hash_alg != 1) || exe_queries < 1 || exe_queries > 128 || fri_queries < 1 || fri_queries > 64) return fail(GS_E_ARG, "bad security options");
+    small::Air A; std::vector<small::Assertion64> as; std::string err;
+    int rc = small_setup(air_blob, blob_len, assertions, n_assertions, A, as, err);
+    if (rc != GS_OK) return fail(rc, err);
+    small::Vec init(A.R);
+    for (int r = 0; r < A.R; ++r) if (!small_elem(A.F, init_state16 + 16 * r, &init[r])) return fail(GS_E_ARG, "non-canonical initial state");
+    std::vector<small::Vec> in;
+    const int n_in = A.n_secret + A.n_public;
+    if (n_in > 0 && (!input_traces || !small_traces(A, input_traces, n_in, in))) return fail(GS_E_ARG, "input register traces required (canonical 16-byte elements)");
+    err = small::prove(A, hash_alg, exe_queries, fri_queries, as, init, in, shapes_blob, shapes_len, g_small_proof);
+    if (!err.empty()) return fail(GS_E_STARK, err);
+    *proof_out = g_small_proof.data(); *proof_len = g_small_proof.size();
+    if (err_buf && err_cap) err_buf[0] = 0;
+    return GS_OK;
+}
+
+extern "C" int gs_host_stark_verify(const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,
+                                    const uint8_t* assertions, int n_assertions, const uint8_t* proof, size_t proof_len,
+                                    const uint8_t* public_traces, char* err_buf, size_t err_cap) {
+    using namespace gs;
+    auto fail = [&](int code, const std::string& m) { if (err_buf && err_cap) snprintf(err_buf, err_cap, "%s", m.c_str()); return code; };
+    if (!air_blob || !assertions || !proof) return fail(GS_E_ARG, "null argument");
+    small::Air A; std::vector<small::Assertion64> as; std::string err;
+    int rc = small_setup(air_blob, blob_len, assertions, n_assertions, A, as, err);
+    if (rc != GS_OK) return fail(rc, err);
+    std::vector<small::Vec> pub;
+    if (A.n_public > 0 && (!public_traces || !small_traces(A, public_traces, A.n_public, pub))) return fail(GS_E_ARG, "public input traces required");
+    err = small::verify(A, hash_alg, exe_queries, fri_queries, as, proof, proof_len, pub);
+    if (!err.empty()) return fail(GS_E_STARK, err);
+    if (err_buf && err_cap) err_buf[0] = 0;
+    return GS_OK;
 }

@@ -286,6 +286,96 @@ def _read_merkle_proof(buf: bytes, off: int, leaf_size: int, node_size: int):   
     return BatchMerkleProof(values, nodes, depth), off
 
 
+class HostStark(Stark):
+    """Stark over a prime field of at most 64 bits (BASELINE config 1: the Foo demo over 2^32 - 3*2^25 + 1, README.md:22-50):
+    prove() and verify() run on the HOST inside libgenstark_b200.so (csrc/hoststark64.h) -- the counterpart of the reference's own
+    fallback to unoptimised arithmetic for fields without a WASM backend (lib/Stark.ts:41-43).  Same surface as ``Stark``; needs no
+    GPU.  The 128-bit field never comes here (it has the device path and no CPU one)."""
+
+    def __init__(self, air: AirModule, options: Optional[dict] = None, logger=None, context=None):
+        options = options or {}
+        self.air = air.with_options(options.get('extensionFactor'))
+        if self.air.modulus.bit_length() > 64:
+            raise StarkError(f'field modulus {self.air.modulus} is not supported by the host path (at most 64 bits)')
+        exe = options.get('exeQueryCount') or DEFAULT_EXE_QUERY_COUNT
+        if exe < 1 or exe > MAX_EXE_QUERY_COUNT or int(exe) != exe:
+            raise TypeError(f'Execution sample size must be an integer between 1 and {MAX_EXE_QUERY_COUNT}')
+        fri = options.get('friQueryCount') or DEFAULT_FRI_QUERY_COUNT
+        if fri < 1 or fri > MAX_FRI_QUERY_COUNT or int(fri) != fri:
+            raise TypeError(f'FRI sample size must be an integer between 1 and {MAX_FRI_QUERY_COUNT}')
+        alg = options.get('hashAlgorithm') or DEFAULT_HASH_ALGORITHM
+        if alg not in HASH_ALGORITHMS:
+            raise TypeError(f'Hash algorithm {alg} is not supported')
+        if not self.air.extension_factor:
+            raise TypeError('Extension factor is undefined')
+        self.exeQueryCount, self.friQueryCount, self.hashAlgorithm = int(exe), int(fri), alg
+        self.digestSize = 32
+        self.elementSize = self.air.element_size
+        self.logger = logger
+        self._lib = _native.lib()
+        self.context = None
+        self._handle = None
+
+    def close(self):
+        pass
+
+    def prove_bytes(self, assertions: Sequence[dict], inputs=None, seed=None, _reuse_resident_trace: bool = False) -> bytes:
+        if not isinstance(assertions, (list, tuple)):
+            raise TypeError('Assertions parameter must be an array')
+        if len(assertions) == 0:
+            raise TypeError('At least one assertion must be provided')
+        air = self.air
+        p = air.modulus
+        init = [int(v) % p for v in air.init(inputs or [], seed or [])]
+        if len(init) != air.trace_register_count:
+            raise StarkError('Failed to generate the execution trace: initial state has the wrong width')
+        a_blob = b''.join(struct.pack('<II', int(a['register']), int(a['step'])) + (int(a['value']) % p).to_bytes(16, 'little')
+                          for a in assertions)
+        in_blob = input_blob(air, inputs)
+        shapes = air.input_shapes(inputs or [])
+        s_blob = bytes([len(shapes)]) + b''.join(bytes([len(s)]) + b''.join(struct.pack('<I', x) for x in s) for s in shapes)
+        blob = pack_air(air)
+        out_p, out_n, err = C.POINTER(C.c_uint8)(), C.c_size_t(), C.create_string_buffer(512)
+        rc = self._lib.gs_host_stark_prove(blob, len(blob), HASH_ALGORITHMS.index(self.hashAlgorithm), self.exeQueryCount, self.friQueryCount,
+                                           a_blob, len(assertions), b''.join(v.to_bytes(16, 'little') for v in init), in_blob,
+                                           s_blob, len(s_blob), C.byref(out_p), C.byref(out_n), err, 512)
+        if rc == -4:
+            raise StarkError(err.value.decode())
+        if rc != 0:
+            raise _native.NativeError(rc, err.value.decode())
+        return C.string_at(out_p, out_n.value)
+
+    def verify(self, assertions: Sequence[dict], proof, publicInputs=None) -> bool:
+        if len(assertions) < 1:
+            raise TypeError('At least one assertion must be provided')
+        buf = proof if isinstance(proof, (bytes, bytearray)) else self.serialize(proof)
+        air = self.air
+        p = air.modulus
+        a_blob = b''.join(struct.pack('<II', int(a['register']), int(a['step'])) + (int(a['value']) % p).to_bytes(16, 'little')
+                          for a in assertions)
+        pub = air.expand_public_inputs(publicInputs or []) if air.expand_public_inputs else []
+        pub_blob = b''.join((int(v) % p).to_bytes(16, 'little') for t in pub for v in t) if pub else None
+        blob = pack_air(air)
+        err = C.create_string_buffer(512)
+        rc = self._lib.gs_host_stark_verify(blob, len(blob), HASH_ALGORITHMS.index(self.hashAlgorithm), self.exeQueryCount, self.friQueryCount,
+                                            a_blob, len(assertions), bytes(buf), len(buf), pub_blob, err, 512)
+        if rc != 0:
+            raise StarkError(err.value.decode() or f'verification failed (status {rc})')
+        return True
+
+    def generateExecutionTrace(self, inputs=None, seed=None):
+        raise StarkError('generateExecutionTrace is not provided on the host path for small fields')
+
+    def compose_backend(self) -> str:
+        return 'host (field of at most 64 bits)'
+
+    def stage_times(self):
+        return []
+
+    def last_timing(self):
+        return 0.0, 0.0
+
+
 def verify_proof(air: AirModule, options: dict, assertions: Sequence[dict], proof_bytes: bytes, publicInputs=None) -> bool:
     """Stark.verify without a device: O(queries log N) host work inside libgenstark_b200.so (gs_stark_verify)."""
     if len(assertions) < 1:
@@ -423,13 +513,17 @@ def instantiate(source, component: str = 'default', options: Optional[dict] = No
     if isinstance(source, AirModule):
         if isinstance(component, dict) and options is None:
             component, options = 'default', component
+        if source.modulus.bit_length() <= 64:
+            return HostStark(source, options, logger)            # fields of at most 64 bits: host path (no WASM backend in the reference either)
         return Stark(source, options, logger, context=context)
     from . import assembly
     comp = assembly.compile(source).component(component)
+    if comp.modulus.bit_length() <= 64 and comp.input_count == 0:
+        return HostStark(comp.module([], (options or {}).get('extensionFactor')), options, logger)
     if comp.modulus.bit_length() > 128 or comp.modulus != (2**128 - 9 * 2**32 + 1):
-        # the reference falls back to JS bigint arithmetic for such fields (README.md:118,224); there is no such
-        # fallback here: the device path is p128 only
-        raise StarkError(f'field modulus {comp.modulus} is not supported by the B200 backend (p128 only)')
+        # the reference falls back to JS bigint arithmetic for such fields (README.md:118,224); here fields of at most 64 bits
+        # have a host path (HostStark) and the device path is p128 only
+        raise StarkError(f'field modulus {comp.modulus} is not supported by the B200 backend (p128 on the device, at most 64 bits on the host)')
     if comp.input_count == 0:
         return Stark(comp.module([], (options or {}).get('extensionFactor')), options, logger, context=context)
     return ScriptStark(comp, options, logger, context=context)

@@ -195,6 +195,17 @@ int gs_stark_verify(const uint8_t* air_blob, size_t blob_len, int hash_alg, int 
  * GS_COMPOSE_JIT=0 forces the interpreting kernel; results are identical. */
 /* message of the last failure on the context this instance lives on (what a binding throws for a negative status) */
 const char* gs_stark_last_error(gs_stark* s);
+/* Prime fields of at most 64 bits (BASELINE config 1: Foo over 2^32 - 3*2^25 + 1): Stark.prove / Stark.verify on the HOST -- the
+ * counterpart of the reference's own fallback to unoptimised arithmetic for fields without a WASM backend (lib/Stark.ts:41-43).
+ * Same arguments as gs_stark_prove / gs_stark_verify (16-byte little-endian elements at the boundary); the 128-bit field is
+ * refused here: it has the GPU path and no CPU one.  The proof buffer is owned by the library until the thread's next call. */
+int gs_host_stark_prove(const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,
+                        const uint8_t* assertions, int n_assertions, const uint8_t* init_state16, const uint8_t* input_traces,
+                        const uint8_t* shapes_blob, size_t shapes_len, const uint8_t** proof_out, size_t* proof_len,
+                        char* err_buf, size_t err_cap);
+int gs_host_stark_verify(const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,
+                         const uint8_t* assertions, int n_assertions, const uint8_t* proof, size_t proof_len,
+                         const uint8_t* public_traces, char* err_buf, size_t err_cap);
 const char* gs_stark_compose_backend(gs_stark* s);
 const char* gs_stark_stage_times(gs_stark* s);
 /* test hooks: keep C(x) and read device-resident intermediates back (0 P evals, 1 C, 2 L, 3 P polys) */

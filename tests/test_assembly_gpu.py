@@ -66,7 +66,8 @@ def test_sponge_component_with_input_registers(blocks, words, e):
 
 
 def test_unsupported_field_is_refused_loudly():
-    src = MIMC_SOURCE.replace('STEPS', '64').replace('340282366920938463463374607393113505793', '4194304001')
+    # a 224-bit field (assembly/lib224.aa's modulus): no device path and no host path -- the reference runs it on JS bigints
+    src = MIMC_SOURCE.replace('STEPS', '64').replace('340282366920938463463374607393113505793', str(2**224 - 2**96 + 1))
     with pytest.raises(StarkError, match='not supported'):
         instantiate(src, 'mimc', dict(extensionFactor=8))
 
