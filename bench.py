@@ -527,7 +527,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--config', default=os.environ.get('GS_BENCH_CONFIG', 'ns'), choices=sorted(METRICS))
+    ap.add_argument('--config', default=os.environ.get('GS_BENCH_CONFIG', 'ns'), choices=sorted(METRICS))      # config 1 (Foo, p32) is a host-path parity case, not a bench line
     ap.add_argument('--quick-ntt', action='store_true', help='NTT table at two sizes only (development runs)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

@@ -353,6 +353,18 @@ class HostStark(Stark):
         p = air.modulus
         a_blob = b''.join(struct.pack('<II', int(a['register']), int(a['step'])) + (int(a['value']) % p).to_bytes(16, 'little')
                           for a in assertions)
+        # the proof carries the input shapes it was generated for (Serializer.ts:66-76): they have to be this instance's
+        es = self.elementSize
+        try:
+            claimed = parse_proof(bytes(buf), (air.trace_register_count + air.secret_input_count) * es, 4 * es, es, 32)['iShapes']
+        except (IndexError, struct.error):
+            raise StarkError('Verification failed: malformed proof')
+        try:
+            expected = [list(x) for x in air.input_shapes(None)]
+        except Exception:
+            expected = None
+        if expected is not None and [list(x) for x in claimed] != expected:
+            raise StarkError(f'Verification failed: the proof was generated for input shapes {claimed}, this instance is built for {expected}')
         pub = air.expand_public_inputs(publicInputs or []) if air.expand_public_inputs else []
         pub_blob = b''.join((int(v) % p).to_bytes(16, 'little') for t in pub for v in t) if pub else None
         blob = pack_air(air)

@@ -63,8 +63,19 @@ def poseidon(depth, proofs, e=32, alg='blake2s256', seed=11):
     return air, opts, a, inputs, []
 
 
+def foo(steps=64, e=None, alg='sha256'):
+    """config 1: the Foo demo (README.md:22-50): x_{n+1} = x_n + 2 over 2^32 - 3*2^25 + 1, 64 steps, start value 1 -- proved on the host
+    (genstark_b200.stark.HostStark); options of the README example: extensionFactor default, 80 / 40 queries capped by the domain"""
+    opts = dict(hashAlgorithm=alg, exeQueryCount=32, friQueryCount=16)
+    if e:
+        opts['extensionFactor'] = e
+    a = [dict(step=0, register=0, value=1), dict(step=steps - 1, register=0, value=1 + 2 * (steps - 1))]
+    return airs.foo(steps), opts, a, [[1]], []
+
+
 CONFIGS = {
     # name: (builder, args, description)  -- SURVEY.md section 8 config legend
+    '1': ('foo', (64,), 'Foo demo (x_{n+1} = x_n + 2), 64 steps over 2^32 - 3*2^25 + 1, host path, no GPU (BASELINE config 1)'),
     'ns': ('mimc', (1 << 20, 8), 'MiMC-128 prove(), 2^20 steps, extensionFactor 8, blake2s256, 48/24 queries (north-star target)'),
     '2': ('mimc', (1 << 13, 8), 'MiMC-128 prove(), 2^13 steps, extensionFactor 8, blake2s256, 48/24 queries (BASELINE config 2)'),
     '3': ('rescue', (128, 16), 'Rescue 4x128 hash chain prove(), 128 instances = 2^12 steps, 4 registers, extensionFactor 16, blake2s256, 68/24 queries (BASELINE config 3)'),

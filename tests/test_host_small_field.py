@@ -159,6 +159,9 @@ def test_tampered_proofs_and_wrong_assertions_are_rejected():
         st.verify([dict(step=0, register=0, value=2), dict(step=63, register=0, value=127)], good)
     with pytest.raises(StarkError, match='conflicts with execution trace'):
         st.prove_bytes([dict(step=0, register=0, value=1), dict(step=63, register=0, value=128)], [[1]], [])
+    shapes_changed = bytearray(good); shapes_changed[-4] ^= 3                  # iShapes [[1]] -> [[2]]: well-formed, not this instance's
+    with pytest.raises(StarkError, match='input shapes'):
+        st.verify(a, bytes(shapes_changed))
     for cut in list(range(0, len(good) - 1, 61)) + [len(good) - 1]:          # every truncation is an error, never a crash
         with pytest.raises(StarkError):
             st.verify(a, good[:cut])
@@ -197,3 +200,58 @@ def test_airassembly_source_over_the_32_bit_field_takes_the_host_path():
     ora = OracleStark(module, opts)
     assert got == ora.serialize(ora.prove(a, [], [3]))
     assert st.verify(a, got)
+
+
+from hypothesis import given, settings, strategies as hst          # noqa: E402
+
+_fuzz_case = {}
+
+
+def _fuzz_proof():
+    if not _fuzz_case:
+        p = P32
+        r = random.Random(11)
+        consts = [r.randrange(p) for _ in range(8)]
+        steps = 128
+        ctl = airs.run_mimc(steps, consts, 5, p)
+        opts = dict(hashAlgorithm='sha256', extensionFactor=8, exeQueryCount=24, friQueryCount=12)
+        a = [dict(step=0, register=0, value=5), dict(step=steps - 1, register=0, value=ctl[-1])]
+        st = instantiate(_mimc(p, steps, consts), opts)
+        _fuzz_case.update(st=st, a=a, buf=st.prove_bytes(a, [], [5]))
+    return _fuzz_case['st'], _fuzz_case['a'], _fuzz_case['buf']
+
+
+@settings(max_examples=300, deadline=None)
+@given(data=hst.data())
+def test_small_field_verifier_rejects_mutations_without_crashing(data):
+    """gs_host_stark_verify reads attacker-controlled bytes: every mutation (the input-shape tail included: this parser checks the final
+    offset) is a StarkError, never an acceptance, never a crash"""
+    st, a, buf = _fuzz_proof()
+    kind = data.draw(hst.sampled_from(['flip', 'truncate', 'byte', 'splice', 'zero_run', 'extend']))
+    t = bytearray(buf)
+    if kind == 'flip':
+        pos = data.draw(hst.integers(0, len(t) - 1)); t[pos] ^= 1 << data.draw(hst.integers(0, 7))
+    elif kind == 'truncate':
+        t = t[:data.draw(hst.integers(0, len(t) - 1))]
+    elif kind == 'byte':
+        pos = data.draw(hst.integers(0, len(t) - 1)); old = t[pos]; t[pos] = data.draw(hst.integers(0, 255).filter(lambda v: v != old))
+    elif kind == 'splice':
+        i = data.draw(hst.integers(0, len(t) - 2)); j = data.draw(hst.integers(i + 1, min(len(t), i + 200)))
+        k = data.draw(hst.integers(0, len(t) - (j - i)))
+        t[k:k + j - i] = t[i:j]
+    elif kind == 'extend':
+        t += bytes(data.draw(hst.integers(1, 9)))
+    else:
+        i = data.draw(hst.integers(0, len(t) - 1)); n = data.draw(hst.integers(1, 40))
+        t[i:i + n] = bytes(len(t[i:i + n]))
+    if bytes(t) == buf:
+        return
+    with pytest.raises(StarkError):
+        st.verify(a, bytes(t))
+
+
+def test_baseline_config_1_through_the_workload_table():
+    from genstark_b200 import workloads
+    air, opts, a, inputs, seed, desc = workloads.config('1')
+    assert 'config 1' in desc
+    _check(air, opts, a, inputs, seed)
