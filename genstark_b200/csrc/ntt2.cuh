@@ -470,6 +470,86 @@ __global__ void __launch_bounds__(256, 2) ntt2_pass1_tma_kernel(const Ntt2Params
     }
 }
 
+// ---- warp-shuffle variant of the inner exchange (north-star item, measured in profiles/r2_k1_ab.md section 5) ---------------------
+// For R = 1024 x 4 columns the exchange between radix steps 2 and 3 is an 8 x 8 transpose between the register index k_2 and lane
+// bits 2..4 (a_3), for a fixed column c (lane bits 0..1): three rounds of butterfly swaps with __shfl_xor_sync, four shuffles per
+// 128-bit element.  Steps 2 and 3 then run back to back on registers for each group and the tile never goes back to shared memory
+// after the step-1 exchange.
+GS_D fp shfl_xor_fp(const fp& a, int mask) {
+    fp r;
+    r.v[0] = __shfl_xor_sync(0xFFFFFFFFu, a.v[0], mask); r.v[1] = __shfl_xor_sync(0xFFFFFFFFu, a.v[1], mask);
+    r.v[2] = __shfl_xor_sync(0xFFFFFFFFu, a.v[2], mask); r.v[3] = __shfl_xor_sync(0xFFFFFFFFu, a.v[3], mask);
+    return r;
+}
+template <typename F>
+GS_D void tile_tail_shfl_1024(const fp* X, const fp* s_tw, int t, F&& emit) {
+    using S = TileShape<10>;
+    const int warp = t >> 5, lane = t & 31, r = (lane >> 2) & 7, cc = lane & 3;
+#pragma unroll 1
+    for (int g = 0; g < 2; ++g) {
+        const int k1 = g * 8 + warp;
+        // step 2: this lane is (a3 = r, c): radix 8 over a2
+        fp y[8];
+#pragma unroll
+        for (int a2 = 0; a2 < 8; ++a2) y[a2] = ld_fp(&X[S::addr(k1 * 64 + a2 * 8 + r, cc)]);
+        dif2<3>(y, s_tw, 10);
+        fp v[8];
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) { v[k2] = y[brev<3>(k2)]; if (k2 != 0) v[k2] = NTT2_MUL(v[k2], s_tw[(r * k2) << 4]); }
+        // transpose: afterwards this lane is (k2 = r, c) and v[a3] = element (k1, k2 = r, a3, c)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const bool bit = (r >> b) & 1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i & (1 << b)) continue;
+                const int i2 = i | (1 << b);
+                const fp send = bit ? v[i] : v[i2];
+                const fp recv = shfl_xor_fp(send, 4 << b);
+                if (bit) v[i] = recv; else v[i2] = recv;
+            }
+        }
+        // step 3: radix 8 over a3
+        dif2<3>(v, s_tw, 10);
+#pragma unroll
+        for (int k3 = 0; k3 < 8; ++k3) emit(k1 + 16 * r + 128 * k3, cc, v[brev<3>(k3)]);
+    }
+}
+__global__ void __launch_bounds__(256, 2) ntt2_pass2_shfl_kernel(const Ntt2Params P) {
+    using S = TileShape<10>;
+    extern __shared__ __align__(128) unsigned char ntt2_smem[];
+    fp* s_tw = reinterpret_cast<fp*>(ntt2_smem);
+    fp* X = s_tw + 1024;
+    const int t = threadIdx.x;
+    ntt2_load_small_table(s_tw, P.tw_small, P.inverse);
+    const int rest = t >> S::LOG_C, c = t & (S::C - 1);
+    const unsigned u_begin = (unsigned)(((unsigned long long)P.units * blockIdx.x) / gridDim.x);
+    const unsigned u_end = (unsigned)(((unsigned long long)P.units * (blockIdx.x + 1)) / gridDim.x);
+    const int log_ucols = P.log_r1 + P.log_cosets;
+    const int log_tiles = log_ucols - S::LOG_C;
+    for (unsigned u = u_begin; u < u_end; ++u) {
+        const unsigned tile = u & ((1u << log_tiles) - 1u), row = u >> log_tiles;
+        const unsigned ucol0 = tile << S::LOG_C, ucol = ucol0 + c;
+        const unsigned jl = ucol & ((1u << P.log_cosets) - 1u), k1p = ucol >> P.log_cosets;
+        const fp* col = P.src + (long long)row * P.src_row_stride + ((size_t)jl << P.log_t) + ((size_t)k1p << 10) + rest;
+        fp x[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a) x[a] = ld_fp(col + a * S::RR);
+        // step 1 as in tile_front (radix 16, twiddle, exchange through X)
+        dif2<4>(x, s_tw, 10);
+        __syncthreads();
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) {
+            fp v = x[brev<4>(k1)];
+            if (k1 != 0) v = NTT2_MUL(v, s_tw[rest * k1]);
+            st_fp(&X[S::addr(k1 * S::RR + rest, c)], v);
+        }
+        __syncthreads();
+        fp* dst = P.dst + (long long)row * P.dst_row_stride + ucol0;
+        tile_tail_shfl_1024(X, s_tw, t, [&](int k, int cc, fp v) { st_fp(dst + ((size_t)k << log_ucols) + cc, v); });
+    }
+}
+
 // tables ------------------------------------------------------------------------------------------
 // [k_1][n_2] = w_T^(+-n_2 k_1) (times `scale` = T^-1 for the inverse transform, so the final pass has nothing left to scale)
 __global__ void tw2_inter_table_kernel(Ntt2Params P, fp scale, int has_scale, fp* __restrict__ out) {

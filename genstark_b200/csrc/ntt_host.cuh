@@ -183,8 +183,19 @@ static inline cudaError_t ntt2_launch_pass2_tma(const Ntt2Params& P, unsigned gr
     ntt2_pass2_tma_kernel<LOG_R><<<grid, 256, NTT2_SMEM, s>>>(P);
     return cudaGetLastError();
 }
+static inline bool ntt2_shfl_mode() {     // GS_NTT2_SHFL=1: 1024-point final passes exchange steps 2 -> 3 through warp shuffles (A/B only)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("GS_NTT2_SHFL"); v = (e && atoi(e) != 0) ? 1 : 0; }
+    return v != 0;
+}
 template <int LOG_R>
 static inline cudaError_t ntt2_launch_pass2(const Ntt2Params& P, unsigned grid, cudaStream_t s) {
+    if (LOG_R == 10 && ntt2_shfl_mode()) {
+        static bool attr_set_s = false;
+        if (!attr_set_s) { cudaFuncSetAttribute(ntt2_pass2_shfl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT2_SMEM); attr_set_s = true; }
+        ntt2_pass2_shfl_kernel<<<grid, 256, NTT2_SMEM, s>>>(P);
+        return cudaGetLastError();
+    }
     if (ntt2_tma_mode() & 1) return ntt2_launch_pass2_tma<LOG_R>(P, grid, s);
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(ntt2_pass2_kernel<LOG_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NTT2_SMEM); attr_set = true; }
