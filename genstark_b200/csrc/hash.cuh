@@ -286,8 +286,12 @@ GS_D fp fri_challenge_dev(const uint32_t* root) {
 // 512-node subtrees, one per block, reduced in shared memory (every intermediate node is written out); the block that
 // finishes last then reduces the subtree roots to the root.  Replaces a launch per level where a level is a handful of
 // dependent ~1 us compressions and the launch gap costs more than the work.  *counter must be zero and is left zero.
+// what the block that writes the root does with it besides storing it in the tree: the FRI challenge x* = prng(root), and the
+// root + epoch flag straight into the pinned (host-mapped) mailbox the host polls -- instead of a one-thread launch and two
+// 32-byte / 4-byte device-to-host copies per layer
+struct RootSink { fp* challenge_out; uint32_t* mb_root; uint32_t* mb_flag; const uint32_t* epoch; };
 template <int ALG>
-__global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ nodes, int level_nodes, unsigned* counter, fp* challenge_out) {
+__global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ nodes, int level_nodes, unsigned* counter, const RootSink sink) {
     __shared__ uint4 s[1024];                                       // 512 digests
     __shared__ int is_last;
     const int leaves = level_nodes < 512 ? level_nodes : 512;
@@ -320,7 +324,13 @@ __global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ 
         if (pass == 1 || gridDim.x == 1) {
             // the block that wrote the root also derives the FRI challenge from it (thread 0 holds the root it just stored):
             // saves the one-thread launch that used to sit between the tree and the fold
-            if (challenge_out && threadIdx.x == 0) st_fp(challenge_out, fri_challenge_dev(reinterpret_cast<const uint32_t*>(&s[0])));
+            const uint32_t* root = reinterpret_cast<const uint32_t*>(&s[0]);
+            if (sink.mb_root && threadIdx.x < 8) { sink.mb_root[threadIdx.x] = root[threadIdx.x]; __threadfence_system(); }
+            if (sink.challenge_out && threadIdx.x == 0) st_fp(sink.challenge_out, fri_challenge_dev(root));
+            if (sink.mb_root) {
+                __syncthreads();                          // all eight root words are fenced before the flag
+                if (threadIdx.x == 0) { *sink.mb_flag = *sink.epoch; __threadfence_system(); }
+            }
             return;
         }
         // the last block to get here owns the remaining gridDim.x subtree roots
@@ -460,8 +470,8 @@ static inline int hash_rows(Ctx* c, int alg, const void* buf, int row_bytes, lon
 
 // nodes: 2n digests with the leaves already at [n, 2n).  log_w > 0: this rank builds only its 1/W slice of every
 // level down to its sub-tree root (node W + rank); the caller gathers the W roots and finishes the top.
-// challenge_out (single-GPU trees only): where the block that writes the root also stores x* = prng(root); *challenge_done says whether it did
-static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long n, int log_w, int rank, fp* challenge_out = nullptr, bool* challenge_done = nullptr) {
+// sink (single-GPU trees only): what the block that writes the root also does with it (RootSink); *sink_done says whether it did
+static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long n, int log_w, int rank, const RootSink* sink = nullptr, bool* sink_done = nullptr) {
     if (alg != HASH_BLAKE2S && alg != HASH_SHA256) return c->fail(GS_E_ARG, "unknown hash algorithm");
     long long count = n >> 1;                  // parents of the current level (whole level)
     ProfScope ps(c, "merkle_build");
@@ -477,9 +487,11 @@ static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long
         // the rest of the tree in one launch; the level with 2 * count nodes holds at most 2^16 of them here
         const int level_nodes = (int)(2 * count);
         const unsigned blocks = level_nodes <= 512 ? 1u : (unsigned)(level_nodes / 512);
-        if (alg == HASH_BLAKE2S) merkle_top_kernel<HASH_BLAKE2S><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, challenge_out);
-        else merkle_top_kernel<HASH_SHA256><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, challenge_out);
-        if (challenge_done) *challenge_done = challenge_out != nullptr;
+        RootSink none; memset(&none, 0, sizeof none);
+        const RootSink& sk = sink ? *sink : none;
+        if (alg == HASH_BLAKE2S) merkle_top_kernel<HASH_BLAKE2S><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, sk);
+        else merkle_top_kernel<HASH_SHA256><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, sk);
+        if (sink_done) *sink_done = sink != nullptr;
         c->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return c->cuda_fail(e, "merkle_top_kernel");
@@ -516,8 +528,8 @@ static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long
     if (e != cudaSuccess) return c->cuda_fail(e, "merkle kernels");
     return GS_OK;
 }
-static inline int merkle_build(Ctx* c, int alg, uint32_t* nodes, long long n, fp* challenge_out = nullptr, bool* challenge_done = nullptr) {
-    return merkle_build_range(c, alg, nodes, n, 0, 0, challenge_out, challenge_done);
+static inline int merkle_build(Ctx* c, int alg, uint32_t* nodes, long long n, const RootSink* sink = nullptr, bool* sink_done = nullptr) {
+    return merkle_build_range(c, alg, nodes, n, 0, 0, sink, sink_done);
 }
 // top of a sharded tree once the W sub-tree roots sit at nodes[W .. 2W)
 static inline int merkle_build_top(Ctx* c, int alg, uint32_t* nodes, int world) {

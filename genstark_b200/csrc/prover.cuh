@@ -920,11 +920,15 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             else if ((rc = commit_gather(S, S->d_dig_loc.as<uint32_t>(), QL, ly.tree + 8 * Q))) return rc;
             }
         }
-        bool have_challenge = false;
-        if (!ly.split && (rc = merkle_build(c, S->hash_alg, ly.tree, Q, (L > 256) ? d_special + (depth & 3) : nullptr, &have_challenge))) return rc;
         if (depth >= 24) return c->fail(GS_E_UNSUPPORTED, "too many FRI layers");
-        GS_CUDA(c, cudaMemcpyAsync(mb + MB_ROOT + 32 * depth, ly.tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
-        GS_CUDA(c, cudaMemcpyAsync(mb + MB_FLAG + 4 * depth, S->d_epoch.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        bool have_challenge = false;
+        RootSink sink; sink.challenge_out = (L > 256) ? d_special + (depth & 3) : nullptr;
+        sink.mb_root = (uint32_t*)(mb + MB_ROOT + 32 * depth); sink.mb_flag = (uint32_t*)(mb + MB_FLAG + 4 * depth); sink.epoch = S->d_epoch.as<uint32_t>();
+        if (!ly.split && (rc = merkle_build(c, S->hash_alg, ly.tree, Q, &sink, &have_challenge))) return rc;
+        if (!have_challenge) {          // split (sharded) trees and the multi-launch paths: root and flag by copies
+            GS_CUDA(c, cudaMemcpyAsync(mb + MB_ROOT + 32 * depth, ly.tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
+            GS_CUDA(c, cudaMemcpyAsync(mb + MB_FLAG + 4 * depth, S->d_epoch.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        }
         layers.push_back(ly); ++n_layers;
         if (L <= 256) {
             if (!shl) GS_CUDA(c, cudaMemcpyAsync(mb + MB_REM, v_cur, L * sizeof(fp), cudaMemcpyDeviceToHost, c->stream));
@@ -943,7 +947,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             break;
         }
         { ProfScope ps(c, "fri_fold");
-          if (!have_challenge) { fri_challenge_kernel<<<1, 1, 0, c->stream>>>(ly.tree + 8, d_special + (depth & 3)); c->launches++; }
+          if (!have_challenge || !sink.challenge_out) { fri_challenge_kernel<<<1, 1, 0, c->stream>>>(ly.tree + 8, d_special + (depth & 3)); c->launches++; }
           FriFoldParams F; F.v = v_cur; F.out = v_next; F.quarter = QL; F.special_x = d_special + (depth & 3);
           F.log_e = log_e; F.log_el = shl ? log_el : log_e; F.j0 = shl ? sh.j0() : 0;
           F.tw_lo = c->tw_lo; F.tw_hi = c->tw_hi; F.log_g = c->log_g; F.log_lo = c->log_lo;
