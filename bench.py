@@ -162,18 +162,23 @@ def fri_layers(n):
         n >>= 2
 
 
-def algorithmic_bytes(cls, log_t, log_e, r, s, n_boundary):
-    """SURVEY.md section 8d / App. A.9 per-unit figures x units of ONE prove, per kernel class."""
+def algorithmic_bytes(cls, log_t, log_e, r, s, n_boundary, fused=False):
+    """SURVEY.md section 8d / App. A.9 per-unit figures x units of ONE prove, per kernel class.
+    fused: the single-GPU commit (class merkle_commit) hashes leaves of at most four columns inside the tree launches --
+    every FRI layer, and the evaluation tree when r + s <= 4; its floor is columns read once + every digest written once."""
     T, N = 1 << log_t, 1 << (log_t + log_e)
     B, D = 16, 32
     fri = fri_layers(N)
+    ev_fused = fused and (r + s) <= 4
     if cls.startswith('ntt'):
         # iNTT(T) + LDE(T -> N) for R (+S) rows: 32 B/point of the transform actually computed
         return (r + s) * (2 * B * T + B * (T + N))
     if cls == 'hash_columns':
-        return N * ((r + s) * B + D) + sum((l // 4) * (4 * B + D) for l in fri)
-    if cls == 'merkle_build':
-        return 2 * N * D + sum(2 * (l // 4) * D for l in fri)      # 64 B per tree node: read two digests, write one
+        return (0 if ev_fused else N * ((r + s) * B + D)) + (0 if fused else sum((l // 4) * (4 * B + D) for l in fri))
+    if cls == 'merkle_build':                                      # 64 B per tree node: read two digests, write one
+        return (0 if ev_fused else 2 * N * D) + (0 if fused else sum(2 * (l // 4) * D for l in fri))
+    if cls == 'merkle_commit':
+        return (N * ((r + s) * B + 2 * D) if ev_fused else 0) + sum((l // 4) * (4 * B + 2 * D) for l in fri)
     if cls == 'compose':
         return N * B * (r + s + n_boundary + 1)
     if cls in ('batch_inverse', 'zb_eval'):
@@ -422,7 +427,8 @@ def run_ours(args, rank, local_rank, world):
     n_reg, n_sec = air.trace_register_count, air.secret_input_count
     n_boundary = len({int(a['register']) for a in assertions})
     # sharded runs: kernel times are rank 0's, which holds 1/world of the evaluation domain
-    alg = algorithmic_bytes(dom, log_t, log_e, n_reg, n_sec, n_boundary) // world
+    fused = 'merkle_commit' in grouped
+    alg = algorithmic_bytes(dom, log_t, log_e, n_reg, n_sec, n_boundary, fused) // world
     achieved = alg / (grouped[dom] * 1e-3) / 1e9
     # DRAM traffic of that kernel class: ncu counters of this code on this workload (profiles/ncu_summary.json records the
     # commit and the workload of the capture); single GPU only -- no counters were taken on the sharded path
@@ -455,10 +461,14 @@ def run_ours(args, rank, local_rank, world):
         n_eval = steps * ext
         fri_rows = sum(l // 4 for l in fri_layers(n_eval))
         leaf_blocks = -(-((n_reg + n_sec) * 16) // 64)              # 64-byte blake2s blocks per leaf
-        comp_hash_cols = n_eval * leaf_blocks + fri_rows
-        comp_merkle = (n_eval - 1) + fri_rows
-        hash_ms = grouped.get('hash_columns', 0) + grouped.get('fri_tail', 0)
+        ev_fused = fused and (n_reg + n_sec) <= 4
+        comp_hash_cols = (0 if ev_fused else n_eval * leaf_blocks) + (0 if fused else fri_rows)
+        comp_merkle = (0 if ev_fused else n_eval - 1) + (0 if fused else fri_rows)
+        comp_commit = (n_eval * leaf_blocks + n_eval - 1 if ev_fused else 0) + 2 * fri_rows
+        hash_ms = grouped.get('hash_columns', 0) + (0 if fused else grouped.get('fri_tail', 0))
         issue_roofline = {
+            'merkle_commit': {'unit': 'blake2s compressions/s', 'achieved': comp_commit / (grouped['merkle_commit'] * 1e-3) if grouped.get('merkle_commit') else None,
+                              'peak': comp_peak, 'peak_how': 'leaf hashing and tree levels in the same launches; same ALU-pipe bound; the top 17 levels of every tree are latency-bound'},
             'hash_columns': {'unit': 'blake2s compressions/s', 'achieved': comp_hash_cols / (hash_ms * 1e-3) if hash_ms else None,
                              'peak': comp_peak, 'peak_how': 'ALU pipe: SMs*4*32 lanes*f / (2 cycles * 648 ALU instructions per compression)'},
             'merkle_build': {'unit': 'blake2s compressions/s', 'achieved': comp_merkle / (grouped.get('merkle_build', 0) * 1e-3) if grouped.get('merkle_build') else None,

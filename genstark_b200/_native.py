@@ -95,6 +95,8 @@ def lib() -> C.CDLL:
         'gs_debug_modmul_probe': (i32, [vp, i32, i32, P(C.c_float)]),
         'gs_debug_butterfly_probe': (i32, [vp, i32, i32, P(C.c_float)]),
         'gs_debug_sqr_probe': (i32, [vp, i32, i32, P(C.c_float), P(C.c_uint32)]),
+        'gs_debug_commit_columns': (i32, [vp, i32, P(vp), i32, P(vp)]),
+        'gs_debug_tree_nodes': (i32, [vp, vp, vp, C.c_size_t]),
         'gs_field_prng': (i32, [cp, C.c_size_t, i32, C.c_char_p]),
         'gs_poly_interpolate': (i32, [cp, cp, i32, C.c_char_p]),
         'gs_poly_eval_at': (i32, [cp, i32, cp, C.c_char_p]),

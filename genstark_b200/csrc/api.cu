@@ -410,9 +410,44 @@ int gs_merkle_create(gs_ctx* c, int alg, const gs_digests* leaves, gs_tree** out
     if (e != cudaSuccess) { delete t; return c->cuda_fail(e, "cudaMalloc(tree)"); }
     cudaMemsetAsync(t->nodes, 0, 32, c->stream);
     cudaMemcpyAsync(t->nodes + 8 * n, leaves->data, (size_t)n * 32, cudaMemcpyDeviceToDevice, c->stream);
-    int rc = merkle_build(c, alg, t->nodes, n);
+    int rc = merkle_commit(c, alg, nullptr, t->nodes, n);
     if (rc != GS_OK) { cudaFree(t->nodes); delete t; return rc; }
     *out = t;
+    return GS_OK;
+}
+
+/* test hook: hash.mergeVectorRows + MerkleTree.create the way the prover commits (leaves and tree in the same launches) */
+int gs_debug_commit_columns(gs_ctx* c, int alg, const gs_mat* const* mats, int count, gs_tree** out) {
+    if (!c || !mats || !out || count < 1) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    cudaSetDevice(c->device);
+    HashCols hc; memset(&hc, 0, sizeof hc);
+    const long long n = mats[0] ? mats[0]->cols : 0;
+    if (n < 1 || (n & (n - 1))) return c->fail(GS_E_ARG, "leaf count must be a power of two");
+    for (int m = 0; m < count; ++m) {
+        if (!mats[m] || mats[m]->cols != n) return c->fail(GS_E_ARG, "all vectors must have the same length");
+        for (long long r = 0; r < mats[m]->rows; ++r) {
+            if (hc.ncols >= GS_MAX_HASH_COLS) return c->fail(GS_E_UNSUPPORTED, "more than %d columns", GS_MAX_HASH_COLS);
+            hc.col[hc.ncols++] = mats[m]->data + r * n;
+        }
+    }
+    gs_tree* t = new gs_tree(); t->ctx = c; t->n = n; t->alg = alg; t->nodes = nullptr;
+    cudaError_t e = cudaMalloc(&t->nodes, (size_t)2 * n * 32);
+    if (e != cudaSuccess) { delete t; return c->cuda_fail(e, "cudaMalloc(tree)"); }
+    cudaMemsetAsync(t->nodes, 0, 32, c->stream);
+    int rc = merkle_commit(c, alg, &hc, t->nodes, n);
+    if (rc != GS_OK) { cudaFree(t->nodes); delete t; return rc; }
+    *out = t;
+    return GS_OK;
+}
+
+/* test hook: the 2n digests of a tree as stored (slot 0 unused and zero, nodes[1] = root, leaves at [n, 2n)) */
+int gs_debug_tree_nodes(gs_ctx* c, const gs_tree* t, void* out, size_t out_bytes) {
+    if (!c || !t || !out) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
+    const size_t bytes = (size_t)2 * t->n * 32;
+    if (out_bytes < bytes) return c->fail(GS_E_ARG, "buffer too small for %lld digests", 2 * t->n);
+    cudaSetDevice(c->device);
+    GS_CUDA(c, cudaMemcpyAsync(out, t->nodes, bytes, cudaMemcpyDeviceToHost, c->stream));
+    GS_CUDA(c, cudaStreamSynchronize(c->stream));
     return GS_OK;
 }
 

@@ -171,6 +171,29 @@ GS_D void store_digest(uint32_t* dst, const uint32_t (&d)[8]) {
     reinterpret_cast<uint4*>(dst)[1] = make_uint4(d[4], d[5], d[6], d[7]);
 }
 
+// leaf `row` of at most four columns (one 64-byte block: MiMC leaves, every FRI row)
+template <int ALG>
+GS_D void hash_leaf4(const HashCols& cols, long long row, uint32_t (&d)[8]) {
+    uint32_t m[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        fp e = (c < cols.ncols) ? ld_fp(cols.col[c] + row) : fp_zero();
+        m[4 * c] = e.v[0]; m[4 * c + 1] = e.v[1]; m[4 * c + 2] = e.v[2]; m[4 * c + 3] = e.v[3];
+    }
+    if (ALG == HASH_BLAKE2S) {
+        // one (final) block, zero padded, counter = message bytes: the message words never leave the registers
+        // (the general loop of hash_words indexes them with the block number, which puts them in local memory)
+        uint32_t h[8];
+        blake2s_init(h);
+        blake2s_compress<false>(h, m, (uint32_t)cols.ncols * 16u, true);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) d[q] = h[q];
+    } else {
+        auto getm = [&](int w) -> uint32_t { return m[w]; };
+        hash_words<ALG>(getm, cols.ncols * 4, d);
+    }
+}
+
 // leaf i = H(col[0][i] || col[1][i] || ...)   ->  out[i] (32 bytes)
 template <int ALG>
 __global__ void __launch_bounds__(256) hash_columns_kernel(const HashCols cols, long long n, uint32_t* __restrict__ out) {
@@ -180,14 +203,7 @@ __global__ void __launch_bounds__(256) hash_columns_kernel(const HashCols cols, 
         auto get = [&](int w) -> uint32_t { return cols.col[w >> 2][i].v[w & 3]; };
         if (cols.ncols <= 4) {
             // common case (MiMC leaves, every FRI row): one block, words straight from registers
-            uint32_t m[16];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                fp e = (c < cols.ncols) ? ld_fp(cols.col[c] + i) : fp_zero();
-                m[4 * c] = e.v[0]; m[4 * c + 1] = e.v[1]; m[4 * c + 2] = e.v[2]; m[4 * c + 3] = e.v[3];
-            }
-            auto getm = [&](int w) -> uint32_t { return m[w]; };
-            hash_words<ALG>(getm, cols.ncols * 4, d);
+            hash_leaf4<ALG>(cols, i, d);
         } else {
             hash_words<ALG>(get, cols.ncols * 4, d);
         }
@@ -224,6 +240,72 @@ __global__ void __launch_bounds__(256) merkle_level_kernel(uint32_t* __restrict_
         auto getm = [&](int w) -> uint32_t { return m[w]; };
         hash_words<ALG>(getm, 16, d);
         store_digest(nodes + 8 * i, d);
+    }
+}
+
+// K consecutive levels of the throughput-bound part of a tree in ONE launch, every thread busy in every level: a block
+// owns S = 256 * 2^(K-1) adjacent parents of the level with `count` parents (nodes[count + p0 ..]); a thread hashes
+// 2^(K-1) of them (parent p0 + r * 256 + t: a warp reads 2 KB of consecutive children), the block keeps that level in
+// shared memory, then 2^(K-2) nodes per thread of the level above, ... down to one node per thread.  Per level this is
+// the work of merkle_level_kernel without reading the level below back from L2 / HBM, and K levels cost one launch.
+// LEAF: the children of the first level are the leaves themselves -- the thread hashes rows 2p and 2p+1 of the columns
+// (hash_columns_kernel's job), stores the two digests and goes on with their parent, so the leaf digests are written once
+// and never read back (evaluation tree of the north-star shape: 268 MB less HBM traffic and 8 launches less).
+template <int ALG, int K, bool LEAF>
+__global__ void __launch_bounds__(256) merkle_span_kernel(uint32_t* __restrict__ nodes, long long count, const HashCols cols) {
+    extern __shared__ __align__(16) unsigned char span_raw[];
+    constexpr int S = 256 << (K - 1);
+    uint4* src = reinterpret_cast<uint4*>(span_raw);                 // S digests (K > 1)
+    uint4* dst = src + (K > 1 ? 2 * S : 0);                          // S / 2 digests; LEAF: at least one 64-byte slot per thread
+    const long long p0 = (long long)blockIdx.x * S;
+#pragma unroll 1
+    for (int r = 0; r < (1 << (K - 1)); ++r) {
+        const int j = r * 256 + threadIdx.x;
+        const long long i = count + p0 + j;                          // heap index of the parent
+        uint32_t m[16];
+        const uint4* ch;
+        if (LEAF) {
+            // the two leaf digests go through a thread-private 64-byte slot of the (still unused) second buffer, so that
+            // nothing but the slot index is live across a leaf compression (48 registers instead of 75)
+            uint4* slot = dst + 4 * threadIdx.x;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                uint32_t d[8];
+                hash_leaf4<ALG>(cols, 2 * (p0 + j) + h, d);
+                store_digest(nodes + 8 * (2 * i + h), d);
+                slot[2 * h] = make_uint4(d[0], d[1], d[2], d[3]); slot[2 * h + 1] = make_uint4(d[4], d[5], d[6], d[7]);
+            }
+            ch = slot;
+        } else {
+            ch = reinterpret_cast<const uint4*>(nodes + 16 * i);                  // nodes[2i], nodes[2i+1]
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { uint4 t = ch[q]; m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
+        uint32_t d[8];
+        auto getm = [&](int w) -> uint32_t { return m[w]; };
+        hash_words<ALG>(getm, 16, d);
+        store_digest(nodes + 8 * i, d);
+        if (K > 1) { src[2 * j] = make_uint4(d[0], d[1], d[2], d[3]); src[2 * j + 1] = make_uint4(d[4], d[5], d[6], d[7]); }
+    }
+    long long cl = count >> 1, pl = p0 >> 1;
+#pragma unroll 1
+    for (int l = 1; l < K; ++l) {
+        __syncthreads();                                             // the level below is complete; its buffer two levels down is free
+        const int reps = 1 << (K - 1 - l);
+#pragma unroll 1
+        for (int r = 0; r < reps; ++r) {
+            const int j = r * 256 + threadIdx.x;
+            uint32_t m[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { uint4 t = src[4 * j + q]; m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w; }
+            uint32_t d[8];
+            auto getm = [&](int w) -> uint32_t { return m[w]; };
+            hash_words<ALG>(getm, 16, d);
+            store_digest(nodes + 8 * (cl + pl + j), d);
+            if (l < K - 1) { dst[2 * j] = make_uint4(d[0], d[1], d[2], d[3]); dst[2 * j + 1] = make_uint4(d[4], d[5], d[6], d[7]); }
+        }
+        uint4* t = src; src = dst; dst = t;
+        cl >>= 1; pl >>= 1;
     }
 }
 
@@ -290,8 +372,10 @@ GS_D fp fri_challenge_dev(const uint32_t* root) {
 // root + epoch flag straight into the pinned (host-mapped) mailbox the host polls -- instead of a one-thread launch and two
 // 32-byte / 4-byte device-to-host copies per layer
 struct RootSink { fp* challenge_out; uint32_t* mb_root; uint32_t* mb_flag; const uint32_t* epoch; };
-template <int ALG>
-__global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ nodes, int level_nodes, unsigned* counter, const RootSink sink) {
+// LEAF: the level with `level_nodes` nodes is the leaf level and is hashed here from the rows of `cols` (<= 4 columns), so a
+// tree of at most 2^17 leaves -- the third and later FRI layers -- is committed by this one launch.
+template <int ALG, bool LEAF = false>
+__global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ nodes, int level_nodes, unsigned* counter, const RootSink sink, const HashCols cols) {
     __shared__ uint4 s[1024];                                       // 512 digests
     __shared__ int is_last;
     const int leaves = level_nodes < 512 ? level_nodes : 512;
@@ -301,7 +385,18 @@ __global__ void __launch_bounds__(256) merkle_top_kernel(uint32_t* __restrict__ 
         // stage the n descendants of `top` (contiguous in the heap layout); .cg: pass 1 reads what other blocks just wrote
         int log_n = 0; while ((1 << log_n) < n) ++log_n;
         const uint4* src = reinterpret_cast<const uint4*>(nodes + 8 * ((long long)top << log_n));
-        for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s[i] = __ldcg(src + i);
+        if (LEAF && pass == 0) {
+#pragma unroll 1
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const long long row = (long long)blockIdx.x * leaves + i;
+                uint32_t d[8];
+                hash_leaf4<ALG>(cols, row, d);
+                s[2 * i] = make_uint4(d[0], d[1], d[2], d[3]); s[2 * i + 1] = make_uint4(d[4], d[5], d[6], d[7]);
+                store_digest(nodes + 8 * ((long long)level_nodes + row), d);
+            }
+        } else {
+            for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s[i] = __ldcg(src + i);
+        }
         __syncthreads();
         for (int l = log_n - 1; l >= 0; --l) {
             const int cnt = 1 << l;
@@ -426,14 +521,7 @@ __global__ void __launch_bounds__(256) hash_columns_scatter_kernel(const HashCol
     for (long long il = (long long)blockIdx.x * blockDim.x + threadIdx.x; il < n_loc; il += stride) {
         uint32_t d[8];
         if (cols.ncols <= 4) {
-            uint32_t m[16];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                fp e = (c < cols.ncols) ? ld_fp(cols.col[c] + il) : fp_zero();
-                m[4 * c] = e.v[0]; m[4 * c + 1] = e.v[1]; m[4 * c + 2] = e.v[2]; m[4 * c + 3] = e.v[3];
-            }
-            auto getm = [&](int w) -> uint32_t { return m[w]; };
-            hash_words<ALG>(getm, cols.ncols * 4, d);
+            hash_leaf4<ALG>(cols, il, d);
         } else {
             auto get = [&](int w) -> uint32_t { return cols.col[w >> 2][il].v[w & 3]; };
             hash_words<ALG>(get, cols.ncols * 4, d);
@@ -489,8 +577,9 @@ static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long
         const unsigned blocks = level_nodes <= 512 ? 1u : (unsigned)(level_nodes / 512);
         RootSink none; memset(&none, 0, sizeof none);
         const RootSink& sk = sink ? *sink : none;
-        if (alg == HASH_BLAKE2S) merkle_top_kernel<HASH_BLAKE2S><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, sk);
-        else merkle_top_kernel<HASH_SHA256><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, sk);
+        HashCols nocols; memset(&nocols, 0, sizeof nocols);
+        if (alg == HASH_BLAKE2S) merkle_top_kernel<HASH_BLAKE2S><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, sk, nocols);
+        else merkle_top_kernel<HASH_SHA256><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, sk, nocols);
         if (sink_done) *sink_done = sink != nullptr;
         c->launches++;
         cudaError_t e = cudaGetLastError();
@@ -530,6 +619,77 @@ static inline int merkle_build_range(Ctx* c, int alg, uint32_t* nodes, long long
 }
 static inline int merkle_build(Ctx* c, int alg, uint32_t* nodes, long long n, const RootSink* sink = nullptr, bool* sink_done = nullptr) {
     return merkle_build_range(c, alg, nodes, n, 0, 0, sink, sink_done);
+}
+
+// One commit on a single GPU: leaves (rows of `cols`; nullptr: the digests already sit at nodes[n, 2n)) and the whole tree
+// above them.  The throughput-bound levels (more than 2^16 parents) go in spans of up to three levels per launch
+// (merkle_span_kernel), the first of them hashing the leaves itself when a leaf is a single block; everything from 2^17
+// nodes down is the one-launch tree top (which hashes the leaves itself for trees that small).  The evaluation tree of
+// the north-star shape (2^23 leaves): 3 launches instead of 9 (leaf kernel + 7 levels + top), a FRI layer of 2^19 rows:
+// 2 instead of 5.  GS_MERKLE_FUSE=0: the separate leaf kernel and one launch per level (the round-1 structure, kept for A/B).
+static inline bool merkle_fuse_enabled() {
+    static const bool on = !(getenv("GS_MERKLE_FUSE") && atoi(getenv("GS_MERKLE_FUSE")) == 0);
+    return on;
+}
+template <int ALG, int K, bool LEAF>
+static inline void merkle_span_launch(Ctx* c, uint32_t* nodes, long long count, const HashCols& cols) {
+    constexpr int S = 256 << (K - 1);
+    constexpr int second = (LEAF && 16 * S < 256 * 64) ? 256 * 64 : (K > 1 ? 16 * S : 0);
+    constexpr int smem = (K > 1 ? 32 * S : 0) + second;
+    static bool attr = false;
+    if (!attr && smem >= 48 * 1024) { cudaFuncSetAttribute(merkle_span_kernel<ALG, K, LEAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    merkle_span_kernel<ALG, K, LEAF><<<(unsigned)(count / S), 256, smem, c->stream>>>(nodes, count, cols);
+}
+template <int ALG>
+static inline int merkle_commit_alg(Ctx* c, const HashCols* cols, uint32_t* nodes, long long n, const RootSink* sink, bool* sink_done) {
+    // the tree top takes the level with 2^(TOP_LOG + 1) nodes; GS_MERKLE_TOP_LOG (13..17) and GS_MERKLE_SPAN (1..3 levels per
+    // launch) are measurement knobs
+    static const int TOP_LOG = []() { const char* e = getenv("GS_MERKLE_TOP_LOG"); const int v = e ? atoi(e) : 16; return v < 13 ? 13 : (v > 17 ? 17 : v); }();
+    static const int SPAN = []() { const char* e = getenv("GS_MERKLE_SPAN"); const int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 3 ? 3 : v); }();
+    HashCols hc; memset(&hc, 0, sizeof hc);
+    if (cols) hc = *cols;
+    bool leaf = cols != nullptr;                             // leaves still to be hashed by the next launch
+    long long count = n >> 1;
+    int rem = 0; while ((count >> rem) > (1ll << TOP_LOG)) ++rem;      // levels with more than 2^TOP_LOG parents
+    int groups = (rem + SPAN - 1) / SPAN;
+    for (int g = 0; g < groups; ++g) {
+        const int k = (rem + (groups - g) - 1) / (groups - g);          // balanced: 4 levels -> 2 + 2, 6 -> 3 + 3
+        if (leaf) {
+            if (k == 1) merkle_span_launch<ALG, 1, true>(c, nodes, count, hc);
+            else if (k == 2) merkle_span_launch<ALG, 2, true>(c, nodes, count, hc);
+            else merkle_span_launch<ALG, 3, true>(c, nodes, count, hc);
+        } else {
+            if (k == 1) merkle_span_launch<ALG, 1, false>(c, nodes, count, hc);
+            else if (k == 2) merkle_span_launch<ALG, 2, false>(c, nodes, count, hc);
+            else merkle_span_launch<ALG, 3, false>(c, nodes, count, hc);
+        }
+        c->launches++;
+        leaf = false; count >>= k; rem -= k;
+    }
+    const int level_nodes = (int)(2 * count);                // <= 2^(TOP_LOG + 1)
+    const unsigned blocks = level_nodes <= 512 ? 1u : (unsigned)(level_nodes / 512);
+    RootSink none; memset(&none, 0, sizeof none);
+    const RootSink& sk = sink ? *sink : none;
+    if (leaf) merkle_top_kernel<ALG, true><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, sk, hc);
+    else merkle_top_kernel<ALG, false><<<blocks, 256, 0, c->stream>>>(nodes, level_nodes, c->counters, sk, hc);
+    c->launches++;
+    if (sink_done) *sink_done = sink != nullptr;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return c->cuda_fail(e, "merkle commit kernels");
+    return GS_OK;
+}
+static inline int merkle_commit(Ctx* c, int alg, const HashCols* cols, uint32_t* nodes, long long n, const RootSink* sink = nullptr, bool* sink_done = nullptr) {
+    if (alg != HASH_BLAKE2S && alg != HASH_SHA256) return c->fail(GS_E_ARG, "unknown hash algorithm");
+    if (n < 1 || (n & (n - 1))) return c->fail(GS_E_ARG, "a tree needs a power-of-two number of leaves");
+    if (cols && (cols->ncols < 1 || cols->ncols > GS_MAX_HASH_COLS)) return c->fail(GS_E_ARG, "1..%d columns per leaf", GS_MAX_HASH_COLS);
+    const bool fuse = merkle_fuse_enabled() && n >= 2;
+    // leaves of more than one block (wide traces), or the A/B switch: the leaf kernel on its own
+    int rc;
+    if (cols && (!fuse || cols->ncols > 4)) { if ((rc = hash_columns(c, alg, *cols, n, nodes + 8 * n))) return rc; cols = nullptr; }
+    if (!fuse) return n >= 2 ? merkle_build(c, alg, nodes, n, sink, sink_done) : GS_OK;
+    ProfScope ps(c, cols ? "merkle_commit" : "merkle_build");          // merkle_commit = leaf hashing + tree in the same launches
+    return alg == HASH_BLAKE2S ? merkle_commit_alg<HASH_BLAKE2S>(c, cols, nodes, n, sink, sink_done)
+                               : merkle_commit_alg<HASH_SHA256>(c, cols, nodes, n, sink, sink_done);
 }
 // top of a sharded tree once the W sub-tree roots sit at nodes[W .. 2W)
 static inline int merkle_build_top(Ctx* c, int alg, uint32_t* nodes, int world) {

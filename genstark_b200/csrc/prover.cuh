@@ -639,7 +639,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         if (timing) mark("Low-degree extended P(x) polynomials over evaluation domain", true);
         HashCols hc; hc.ncols = (int)e_cols.size();
         for (size_t i = 0; i < e_cols.size(); ++i) hc.col[i] = e_cols[i];
-        if (!sharded) { if ((r2 = hash_columns(c, S->hash_alg, hc, N, e_tree + 8 * N))) return r2; }
+        if (!sharded) { if ((r2 = merkle_commit(c, S->hash_alg, &hc, e_tree, N))) return r2; }       // leaves + tree
         else if (e_split && peers_ok) {
             PeerTrees pt; memset(&pt, 0, sizeof pt);
             PeerStage pst; memset(&pst, 0, sizeof pst);
@@ -654,7 +654,7 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             else if ((r2 = commit_gather(S, S->d_dig_loc.as<uint32_t>(), NL, e_tree + 8 * N))) return r2;
         }
         if (timing && !(e_split && peers_ok)) mark("Serialized evaluations of P(x) and S(x) polynomials", true);
-        if (!e_split && (r2 = merkle_build(c, S->hash_alg, e_tree, N))) return r2;
+        if (sharded && !e_split && (r2 = merkle_build(c, S->hash_alg, e_tree, N))) return r2;
         GS_CUDA(c, cudaMemcpyAsync(c->mailbox, e_tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
         return GS_OK;
     };
@@ -904,7 +904,8 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
             continue;
         }
         HashCols hc; hc.ncols = 4; for (int j = 0; j < 4; ++j) hc.col[j] = v_cur + j * QL;
-        if (!shl) { if ((rc = hash_columns(c, S->hash_alg, hc, Q, ly.tree + 8 * Q))) return rc; }
+        if (!sharded) { /* single GPU: leaves and tree in the same launches (merkle_commit below) */ }
+        else if (!shl) { if ((rc = hash_columns(c, S->hash_alg, hc, Q, ly.tree + 8 * Q))) return rc; }
         else {
             if (split_ok(Q) && peers_ok) {
                 ly.split = true;
@@ -924,7 +925,8 @@ static inline int stark_prove(Stark* S, const Assertion* asserts, int n_assert, 
         bool have_challenge = false;
         RootSink sink; sink.challenge_out = (L > 256) ? d_special + (depth & 3) : nullptr;
         sink.mb_root = (uint32_t*)(mb + MB_ROOT + 32 * depth); sink.mb_flag = (uint32_t*)(mb + MB_FLAG + 4 * depth); sink.epoch = S->d_epoch.as<uint32_t>();
-        if (!ly.split && (rc = merkle_build(c, S->hash_alg, ly.tree, Q, &sink, &have_challenge))) return rc;
+        if (!sharded) { if ((rc = merkle_commit(c, S->hash_alg, &hc, ly.tree, Q, &sink, &have_challenge))) return rc; }
+        else if (!ly.split && (rc = merkle_build(c, S->hash_alg, ly.tree, Q, &sink, &have_challenge))) return rc;
         if (!have_challenge) {          // split (sharded) trees and the multi-launch paths: root and flag by copies
             GS_CUDA(c, cudaMemcpyAsync(mb + MB_ROOT + 32 * depth, ly.tree + 8, 32, cudaMemcpyDeviceToHost, c->stream));
             GS_CUDA(c, cudaMemcpyAsync(mb + MB_FLAG + 4 * depth, S->d_epoch.p, 4, cudaMemcpyDeviceToHost, c->stream));

@@ -281,7 +281,8 @@ class GpuField:
         rc = self._lib.gs_field_prng(sb, len(sb), n, out)
         if rc != 0:
             raise _native.NativeError(rc, 'prng')
-        vals = [int.from_bytes(out.raw[i:i + 16], 'little') for i in range(0, 16 * max(n, 1), 16)]
+        raw = out.raw
+        vals = [int.from_bytes(raw[i:i + 16], 'little') for i in range(0, 16 * max(n, 1), 16)]
         return vals[0] if length is None else self.newVectorFrom(vals)
 
     @staticmethod
@@ -395,7 +396,8 @@ class Digests:
     def toBuffers(self) -> List[bytes]:
         buf = C.create_string_buffer(self.length * 32)
         self.ctx.check(self.ctx._lib.gs_digests_to_bytes(self.ctx.handle, self.handle, buf))
-        return [buf.raw[i:i + 32] for i in range(0, self.length * 32, 32)]
+        raw = buf.raw                       # one copy: `buf.raw` inside the comprehension would copy the whole buffer per digest
+        return [raw[i:i + 32] for i in range(0, self.length * 32, 32)]
 
     def __del__(self):
         try:
@@ -448,6 +450,22 @@ class MerkleTree:
         h = C.c_void_p()
         hash.ctx.check(hash._lib.gs_merkle_create(hash.ctx.handle, hash.alg, values.handle, C.byref(h)))
         return MerkleTree(hash.ctx, h, values.length.bit_length() - 1)
+
+    @staticmethod
+    def _commit(vectors: Sequence[Matrix], hash: GpuHash) -> 'MerkleTree':
+        """test hook: mergeVectorRows + create in the launches the prover uses for a commit (gs_debug_commit_columns)"""
+        arr = (C.c_void_p * len(vectors))(*[v.handle for v in vectors])
+        h = C.c_void_p()
+        hash.ctx.check(hash._lib.gs_debug_commit_columns(hash.ctx.handle, hash.alg, arr, len(vectors), C.byref(h)))
+        return MerkleTree(hash.ctx, h, vectors[0].length.bit_length() - 1)
+
+    def _nodes(self) -> List[bytes]:
+        """test hook: the 2n stored digests (slot 0 unused, [1] = root, leaves at [n, 2n))"""
+        count = 2 << self.depth
+        buf = C.create_string_buffer(32 * count)
+        self.ctx.check(self.ctx._lib.gs_debug_tree_nodes(self.ctx.handle, self.handle, buf, 32 * count))
+        raw = buf.raw
+        return [raw[32 * i: 32 * i + 32] for i in range(count)]
 
     @property
     def root(self) -> bytes:

@@ -233,6 +233,10 @@ int gs_debug_modmul_probe(gs_ctx* ctx, int blocks, int iters, float* ms_out);
 int gs_debug_sqr_probe(gs_ctx* ctx, int blocks, int iters, float* ms_out, int* mismatches);
 /* same for the NTT's instruction mix: blocks x 256 threads x 2 butterflies (u + v, (u - v) * w) x iters */
 int gs_debug_butterfly_probe(gs_ctx* ctx, int blocks, int iters, float* ms_out);
+/* test hooks for the commit kernels: mergeVectorRows + MerkleTree.create (Stark.ts:114-118) in the launches the prover
+ * uses for a commit (leaf hashing fused into the tree kernels), and the 2n stored digests of a tree (slot 0 unused) */
+int gs_debug_commit_columns(gs_ctx* ctx, int alg, const gs_mat* const* mats, int count, gs_tree** out);
+int gs_debug_tree_nodes(gs_ctx* ctx, const gs_tree* tree, void* out, size_t out_bytes);
 
 #ifdef __cplusplus
 }
