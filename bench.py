@@ -443,6 +443,11 @@ def run_ours(args, rank, local_rank, world):
                 traffic_src = f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum over the launches of one prove; capture at commit {ent.get('commit')}"
         except Exception:
             traffic = None
+    if traffic is None and world == 1 and dom == 'merkle_commit':
+        traffic_src = ('null: the fused commit launches (merkle_span_kernel, leaf-hashing merkle_top_kernel) were never under ncu -- the '
+                       'GPU budget of the round ended with their parity and A/B runs; the separate kernels they replace moved 583 MB '
+                       '(hash_columns) + 859 MB (merkle_build) per prove (profiles/ncu_summary.json, commit 2e4d98f), and the fusion '
+                       'removes the re-read of every level that a span keeps in shared memory')
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
                 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs)',
                 'kernel_ms_per_step': grouped[dom], 'algorithmic_bytes_per_step': alg,

@@ -21,6 +21,9 @@ def main(raw, prefix, last_n=0):
     if last_n:
         rows = rows[:2] + rows[2:][-last_n:]
     ki = hdr.index('Kernel Name')
+    # fused single-GPU commit (merkle_span_kernel + the leaf-hashing tree top): one class, as in bench.py's kernels_ms_per_step
+    fused = any('merkle_span' in r[ki] for r in rows[2:])
+    classes_of = ([('merkle_span', 'merkle_commit'), ('merkle_top', 'merkle_commit')] if fused else []) + CLASSES
     table, classes = [], {}
     for r in rows[2:]:
         name = r[ki]
@@ -37,7 +40,7 @@ def main(raw, prefix, last_n=0):
                 v = v * {'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}.get(u, 1.0)
             rec[key] = round(v, 2)
         table.append(rec)
-        for pat, cls in CLASSES:
+        for pat, cls in classes_of:
             if pat in name:
                 c = classes.setdefault(cls, {'launches_captured': 0, 'time_us': 0.0, 'dram_read_MB': 0.0, 'dram_write_MB': 0.0})
                 c['launches_captured'] += 1; c['time_us'] += rec['time_us']
