@@ -165,7 +165,9 @@ def fri_layers(n):
 def algorithmic_bytes(cls, log_t, log_e, r, s, n_boundary, fused=False):
     """SURVEY.md section 8d / App. A.9 per-unit figures x units of ONE prove, per kernel class.
     fused: the single-GPU commit (class merkle_commit) hashes leaves of at most four columns inside the tree launches --
-    every FRI layer, and the evaluation tree when r + s <= 4; its floor is columns read once + every digest written once."""
+    every FRI layer, and the evaluation tree when r + s <= 4.  Its figure is section 8d's for the work those launches do
+    (leaf hash N(16(R+S)+32) + Merkle build 64 B per node); 'merkle_commit_floor' is what a fused commit has to move at least
+    (columns read once, every digest written once) and is reported beside it."""
     T, N = 1 << log_t, 1 << (log_t + log_e)
     B, D = 16, 32
     fri = fri_layers(N)
@@ -178,6 +180,8 @@ def algorithmic_bytes(cls, log_t, log_e, r, s, n_boundary, fused=False):
     if cls == 'merkle_build':                                      # 64 B per tree node: read two digests, write one
         return (0 if ev_fused else 2 * N * D) + (0 if fused else sum(2 * (l // 4) * D for l in fri))
     if cls == 'merkle_commit':
+        return ((N * ((r + s) * B + D) + 2 * N * D) if ev_fused else 0) + sum((l // 4) * (4 * B + D) + 2 * (l // 4) * D for l in fri)
+    if cls == 'merkle_commit_floor':
         return (N * ((r + s) * B + 2 * D) if ev_fused else 0) + sum((l // 4) * (4 * B + 2 * D) for l in fri)
     if cls == 'compose':
         return N * B * (r + s + n_boundary + 1)
@@ -451,6 +455,10 @@ def run_ours(args, rank, local_rank, world):
     roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm, 'unit': 'GB/s', 'frac': achieved / hbm,
                 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': f'{peak_kind} (MEASURED_PEAKS.json hbm_gbs)',
                 'kernel_ms_per_step': grouped[dom], 'algorithmic_bytes_per_step': alg,
+                **({'fused_floor_bytes_per_step': algorithmic_bytes('merkle_commit_floor', log_t, log_e, n_reg, n_sec, n_boundary, fused) // world,
+                    'algorithmic_bytes_how': 'SURVEY 8d figures for the work these launches do: leaf hash N(16(R+S)+32) + 64 B per tree node, over the '
+                                             'evaluation tree and every FRI layer; fused_floor = columns read once + every digest written once'}
+                   if dom == 'merkle_commit' else {}),
                 'share_of_step': grouped[dom] / (sum(prof_dev) / len(prof_dev)),
                 'note': '128-bit modular arithmetic on 32-bit integer pipes: every kernel here is issue-bound, not HBM-bound'}
 
