@@ -31,3 +31,18 @@ def test_reference_arm_is_silent_on_other_ranks():
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--config', 'test', '--gpus', '2', '--steps', '1', '--warmup', '0'],
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == ''
+
+
+def test_algorithmic_bytes_of_the_fused_commit_are_the_sum_of_the_kernels_it_replaces():
+    """SURVEY 8d per-unit figures: leaf hash N(16(R+S)+32) + 64 B per tree node, whichever launches do the work."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for log_t, log_e, r, s in [(20, 3, 1, 0), (20, 3, 1, 1), (13, 3, 1, 1), (20, 4, 1, 0), (16, 5, 12, 4), (12, 4, 4, 4)]:
+        unfused = bench.algorithmic_bytes('hash_columns', log_t, log_e, r, s, 1) + bench.algorithmic_bytes('merkle_build', log_t, log_e, r, s, 1)
+        fused = sum(bench.algorithmic_bytes(c, log_t, log_e, r, s, 1, True) for c in ('hash_columns', 'merkle_build', 'merkle_commit'))
+        assert fused == unfused
+        wide = r + s > 4                         # leaves of more than one block keep the separate leaf kernel for the evaluation tree
+        assert (bench.algorithmic_bytes('hash_columns', log_t, log_e, r, s, 1, True) > 0) == wide
+        assert 0 < bench.algorithmic_bytes('merkle_commit_floor', log_t, log_e, r, s, 1, True) < bench.algorithmic_bytes('merkle_commit', log_t, log_e, r, s, 1, True)
+    # the north-star figure quoted in DESIGN.md section 5
+    assert bench.algorithmic_bytes('merkle_commit', 20, 3, 1, 0, 1, True) == 1386914816
