@@ -140,7 +140,20 @@ std::shared_ptr<TraceJit> jit_get(const HostProgram& pr, int R, int n_static);
 std::shared_ptr<TraceJit> jit_get(const HostProgram& pr, int R, int n_static) {
     static std::mutex mu;
     static std::map<std::string, std::shared_ptr<TraceJit>> cache;
-    auto interp = [](const std::string& why) { auto j = std::make_shared<TraceJit>(); j->status = "interpreter (" + why + ")"; return j; };
+    // the fallback is never silent: one line on stderr per program (GS_TRACE_JIT=0 is a request, not a failure), and
+    // gs_trace_backend() / bench.py's `backends.trace` say which generator ran
+    auto interp = [](const std::string& why) {
+        auto j = std::make_shared<TraceJit>(); j->status = "interpreter (" + why + ")";
+        if (why != "GS_TRACE_JIT=0") {
+            static std::mutex wmu; static std::map<std::string, bool> warned;
+            std::lock_guard<std::mutex> wl(wmu);
+            if (!warned[why]) {
+                warned[why] = true;
+                fprintf(stderr, "genstark_b200: execution-trace JIT unavailable (%s); using the interpreter (about 1.5x slower per step)\n", why.c_str());
+            }
+        }
+        return j;
+    };
     if (const char* e = getenv("GS_TRACE_JIT")) if (e[0] == '0') return interp("GS_TRACE_JIT=0");
     const std::string src = jit_emit_source(pr, R, n_static);
     if (src.empty()) return interp("program not supported by the code generator");
