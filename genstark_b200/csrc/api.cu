@@ -144,6 +144,9 @@ int gs_field_scalar_op(int op, const uint8_t a16[16], const uint8_t b16[16], uin
 // ---- matrices --------------------------------------------------------------------------------
 int gs_mat_alloc(gs_ctx* c, int64_t rows, int64_t cols, gs_mat** out) {
     if (!c || !out || rows <= 0 || cols <= 0) return c ? c->fail(GS_E_ARG, "bad matrix shape") : GS_E_ARG;
+    // rows * cols * 16 must not wrap: nothing on this path is larger than 2^36 elements (1 TiB), far beyond the device
+    if (rows > (1ll << 36) || cols > (1ll << 36) || (unsigned __int128)rows * (unsigned __int128)cols > ((unsigned __int128)1 << 36))
+        return c->fail(GS_E_ARG, "matrix of %lld x %lld elements is too large", (long long)rows, (long long)cols);
     cudaSetDevice(c->device);
     gs_mat* m = new gs_mat();
     m->ctx = c; m->rows = rows; m->cols = cols; m->owns = true; m->data = nullptr;
@@ -207,6 +210,7 @@ int gs_eval_polys_at_roots(gs_ctx* c, const gs_mat* polys, int log2_domain, gs_m
     const int log_t = ilog2_exact(polys->cols);
     if (log_t < 1) return c->fail(GS_E_ARG, "polynomial length must be a power of two >= 2");
     if (log2_domain < log_t) return c->fail(GS_E_ARG, "domain smaller than the polynomial");
+    if (log2_domain > c->log_g) return c->fail(GS_E_UNSUPPORTED, "domain 2^%d exceeds 2^%d", log2_domain, c->log_g);
     cudaSetDevice(c->device);
     const long long n = 1ll << log2_domain;
     int rc = gs_mat_alloc(c, polys->rows, n, evals);
@@ -281,6 +285,7 @@ int gs_vec_combine_many(gs_ctx* c, const gs_mat* const* vectors, int count, cons
     if (!c || !vectors || !coefficients16 || !out || count < 1 || count > 64) return c ? c->fail(GS_E_ARG, "1..64 vectors required") : GS_E_ARG;
     cudaSetDevice(c->device);
     CombineParams P; P.m = count;
+    if (!vectors[0]) return c->fail(GS_E_ARG, "null vector");
     const long long n = vectors[0]->rows * vectors[0]->cols;
     for (int m = 0; m < count; ++m) {
         if (!vectors[m] || vectors[m]->rows * vectors[m]->cols != n) return c->fail(GS_E_ARG, "shape mismatch");
@@ -290,10 +295,13 @@ int gs_vec_combine_many(gs_ctx* c, const gs_mat* const* vectors, int count, cons
     if (rc != GS_OK) return rc;
     rc = c->ensure_scratch(sizeof P);
     if (rc != GS_OK) { gs_mat_free(*out); *out = nullptr; return rc; }
-    GS_CUDA(c, cudaMemcpyAsync(c->scratch, &P, sizeof P, cudaMemcpyHostToDevice, c->stream));
-    combine_many_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>((const CombineParams*)c->scratch, (*out)->data, n);
-    c->launches++;
-    GS_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaError_t e = cudaMemcpyAsync(c->scratch, &P, sizeof P, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        combine_many_kernel<<<grid_for(c, n, 256), 256, 0, c->stream>>>((const CombineParams*)c->scratch, (*out)->data, n);
+        c->launches++;
+        e = cudaStreamSynchronize(c->stream);
+    }
+    if (e != cudaSuccess) { gs_mat_free(*out); *out = nullptr; return c->cuda_fail(e, "combine_many_kernel"); }
     return GS_OK;
 }
 
@@ -336,7 +344,8 @@ int gs_transpose_vector(gs_ctx* c, const gs_mat* v, int columns, int64_t step, g
 int gs_fri_fold(gs_ctx* c, const gs_mat* v, int log2_domain, int depth, const uint8_t special_x16[16], gs_mat** column) {
     if (!c || !v || !special_x16 || !column) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
     const long long L = v->rows * v->cols;
-    if (L < 4 || (L & 3) || (L << (2 * depth)) != (1ll << log2_domain) || log2_domain > c->log_g) return c->fail(GS_E_ARG, "layer length must be domain / 4^depth");
+    if (depth < 0 || depth > 30 || log2_domain < 2 || log2_domain > c->log_g) return c->fail(GS_E_ARG, "bad depth / domain");
+    if (L < 4 || (L & 3) || 2 * depth > log2_domain || L != (1ll << (log2_domain - 2 * depth))) return c->fail(GS_E_ARG, "layer length must be domain / 4^depth");
     cudaSetDevice(c->device);
     int rc = gs_mat_alloc(c, 1, L >> 2, column);
     if (rc != GS_OK) return rc;
@@ -495,6 +504,7 @@ void gs_tree_free(gs_tree* t) { if (!t) return; cudaSetDevice(t->ctx->device); c
 
 static int run_probe(gs_ctx* c, int kind, int blocks, int iters, float* ms_out) {
     if (!c || !ms_out) return GS_E_ARG;
+    if (blocks < 1 || blocks > (1 << 20) || iters < 1 || iters > (1 << 24)) return c->fail(GS_E_ARG, "probe shape out of range");
     cudaSetDevice(c->device);
     int rc = c->ensure_scratch(64);
     if (rc != GS_OK) return rc;
@@ -515,6 +525,7 @@ static int run_probe(gs_ctx* c, int kind, int blocks, int iters, float* ms_out) 
 /* blocks x 256 threads x 4 chains x iters squarings (fp_sqr); *mismatches = disagreements of fp_sqr with fp_mul(a, a) on edge and chain values */
 int gs_debug_sqr_probe(gs_ctx* c, int blocks, int iters, float* ms_out, int* mismatches) {
     if (!c || !ms_out || !mismatches) return GS_E_ARG;
+    if (blocks < 1 || blocks > (1 << 20) || iters < 1 || iters > (1 << 24)) return c->fail(GS_E_ARG, "probe shape out of range");
     cudaSetDevice(c->device);
     int rc = c->ensure_scratch(256);
     if (rc != GS_OK) return rc;
