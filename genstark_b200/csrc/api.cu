@@ -550,10 +550,17 @@ int gs_debug_modmul_probe(gs_ctx* c, int blocks, int iters, float* ms_out) { ret
 int gs_debug_butterfly_probe(gs_ctx* c, int blocks, int iters, float* ms_out) { return run_probe(c, 1, blocks, iters, ms_out); }
 
 // ---- fused prover ------------------------------------------------------------------------------
+static int stark_create_impl(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries, gs_stark** out);
 int gs_stark_create(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,
                     gs_stark** out) {
     if (!c || !air_blob || !out) return c ? c->fail(GS_E_ARG, "null argument") : GS_E_ARG;
     *out = nullptr;
+    // nothing may unwind through the C ABI (an AIR blob with absurd sizes ends in std::bad_alloc / std::length_error)
+    try { return stark_create_impl(c, air_blob, blob_len, hash_alg, exe_queries, fri_queries, out); }
+    catch (const std::exception& e) { *out = nullptr; return c->fail(GS_E_ARG, "instantiation failed: %s", e.what()); }
+}
+static int stark_create_impl(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,
+                             gs_stark** out) {
     if (hash_alg != HASH_SHA256 && hash_alg != HASH_BLAKE2S) return c->fail(GS_E_ARG, "Hash algorithm %d is not supported", hash_alg);
     if (exe_queries < 1 || exe_queries > 128) return c->fail(GS_E_ARG, "Execution sample size must be an integer between 1 and 128");
     if (fri_queries < 1 || fri_queries > 64) return c->fail(GS_E_ARG, "FRI sample size must be an integer between 1 and 64");
@@ -634,6 +641,7 @@ int gs_stark_create(gs_ctx* c, const uint8_t* air_blob, size_t blob_len, int has
 int gs_air_generate_trace(const uint8_t* air_blob, size_t blob_len, const uint8_t* init_state16, const uint8_t* input_traces,
                           uint8_t* out_trace) {
     if (!air_blob || !init_state16 || !out_trace) return GS_E_ARG;
+    try {
     Stark S; int code = GS_OK;
     const std::string err = parse_air(air_blob, blob_len, &S, &code);
     if (code != GS_OK) { g_null_error = err; return code; }
@@ -642,6 +650,7 @@ int gs_air_generate_trace(const uint8_t* air_blob, size_t blob_len, const uint8_
     for (int r = 0; r < S.R; ++r) { fp v; memcpy(&v, init_state16 + 16 * r, 16); init[r] = fp_to_u128(v); }
     generate_trace(&S, init.data(), (const fp*)input_traces, (fp*)out_trace);
     return GS_OK;
+    } catch (const std::exception& e) { g_null_error = std::string("trace generation failed: ") + e.what(); return GS_E_ARG; }
 }
 
 void gs_stark_destroy(gs_stark* s) {
@@ -669,6 +678,7 @@ int gs_stark_prove_ex(gs_stark* s, const uint8_t* assertions, int n_assertions, 
     if (!s || !assertions || !init_state16 || !proof_out || !proof_len) return s ? s->ctx->fail(GS_E_ARG, "null argument") : GS_E_ARG;
     Ctx* c = s->ctx;
     if ((s->n_secret + s->n_public) > 0 && !input_traces) return c->fail(GS_E_ARG, "input register traces required");
+    try {
     std::vector<Assertion> as(n_assertions > 0 ? n_assertions : 0);
     for (int i = 0; i < n_assertions; ++i) {
         const uint8_t* p = assertions + 24 * (size_t)i;
@@ -681,6 +691,7 @@ int gs_stark_prove_ex(gs_stark* s, const uint8_t* assertions, int n_assertions, 
     if (rc != GS_OK) return rc;
     *proof_out = s->proof.data(); *proof_len = s->proof.size();
     return GS_OK;
+    } catch (const std::exception& e) { cudaStreamSynchronize(c->stream); return c->fail(GS_E_CUDA, "prove failed: %s", e.what()); }
 }
 
 int gs_stark_last_timing(gs_stark* s, float* device_ms, double* host_ms) {

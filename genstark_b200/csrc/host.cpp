@@ -11,6 +11,7 @@ extern "C" int gs_stark_verify(const uint8_t* air_blob, size_t blob_len, int has
     using namespace gs;
     auto fail = [&](int code, const std::string& m) { if (err_buf && err_cap) { snprintf(err_buf, err_cap, "%s", m.c_str()); } return code; };
     if (!air_blob || !assertions || !proof) return fail(GS_E_ARG, "null argument");
+    try {
     AirHost A; int code = GS_OK;
     const std::string perr = parse_air(air_blob, blob_len, &A, &code);
     if (code != GS_OK) return fail(code, perr);
@@ -24,6 +25,7 @@ extern "C" int gs_stark_verify(const uint8_t* air_blob, size_t blob_len, int has
     if (!err.empty()) return fail(GS_E_STARK, err);
     if (err_buf && err_cap) err_buf[0] = 0;
     return GS_OK;
+    } catch (const std::exception& e) { return fail(GS_E_STARK, std::string("Verification failed: ") + e.what()); }
 }
 
 /* which trace generator the last generate_trace of this thread used: "jit <hash>" or "interpreter (<reason>)" */
@@ -48,6 +50,10 @@ extern "C" int gs_merkle_verify_batch(int alg, const uint8_t root32[32], const u
     if ((int)nv != count || depth > 32) return 0;
     size_t off = 12;
     if (proof_len < off + (size_t)nv * 32) return GS_E_ARG;
+    // the column count comes from the blob: every column costs at least its 4-byte length, so a count the remaining bytes
+    // cannot hold is malformed (and must not size an allocation: 2^32 - 1 columns used to end in std::bad_alloc)
+    if ((size_t)nc > (proof_len - off - (size_t)nv * 32) / 4) return GS_E_ARG;
+    try {
     std::vector<Digest> values(nv);
     for (uint32_t i = 0; i < nv; ++i) { memcpy(values[i].data(), proof + off, 32); off += 32; }
     std::vector<std::vector<Digest>> nodes(nc);
@@ -61,6 +67,7 @@ extern "C" int gs_merkle_verify_batch(int alg, const uint8_t root32[32], const u
     Digest root; memcpy(root.data(), root32, 32);
     HostHash H{alg};
     return verify_batch(root, std::vector<uint32_t>(indexes, indexes + count), values, nodes, (int)depth, H) ? 1 : 0;
+    } catch (const std::exception&) { return GS_E_ARG; }          // nothing may unwind through the C ABI
 }
 
 // ---- prime fields of at most 64 bits: Stark.prove / Stark.verify on the host (hoststark64.h).  Elements cross the ABI as the same
@@ -102,6 +109,7 @@ extern "C" int gs_host_stark_prove(const uint8_t* air_blob, size_t blob_len, int
     auto fail = [&](int code, const std::string& m) { if (err_buf && err_cap) snprintf(err_buf, err_cap, "%s", m.c_str()); return code; };
     if (!air_blob || !assertions || !init_state16 || !proof_out || !proof_len) return fail(GS_E_ARG, "null argument");
     if ((hash_alg != 0 && hash_alg != 1) || exe_queries < 1 || exe_queries > 128 || fri_queries < 1 || fri_queries > 64) return fail(GS_E_ARG, "bad security options");
+    try {
     small::Air A; std::vector<small::Assertion64> as; std::string err;
     int rc = small_setup(air_blob, blob_len, assertions, n_assertions, A, as, err);
     if (rc != GS_OK) return fail(rc, err);
@@ -115,6 +123,7 @@ extern "C" int gs_host_stark_prove(const uint8_t* air_blob, size_t blob_len, int
     *proof_out = g_small_proof.data(); *proof_len = g_small_proof.size();
     if (err_buf && err_cap) err_buf[0] = 0;
     return GS_OK;
+    } catch (const std::exception& e) { return fail(GS_E_STARK, std::string("prove failed: ") + e.what()); }
 }
 
 extern "C" int gs_host_stark_verify(const uint8_t* air_blob, size_t blob_len, int hash_alg, int exe_queries, int fri_queries,
@@ -123,6 +132,7 @@ extern "C" int gs_host_stark_verify(const uint8_t* air_blob, size_t blob_len, in
     using namespace gs;
     auto fail = [&](int code, const std::string& m) { if (err_buf && err_cap) snprintf(err_buf, err_cap, "%s", m.c_str()); return code; };
     if (!air_blob || !assertions || !proof) return fail(GS_E_ARG, "null argument");
+    try {
     small::Air A; std::vector<small::Assertion64> as; std::string err;
     int rc = small_setup(air_blob, blob_len, assertions, n_assertions, A, as, err);
     if (rc != GS_OK) return fail(rc, err);
@@ -132,4 +142,5 @@ extern "C" int gs_host_stark_verify(const uint8_t* air_blob, size_t blob_len, in
     if (!err.empty()) return fail(GS_E_STARK, err);
     if (err_buf && err_cap) err_buf[0] = 0;
     return GS_OK;
+    } catch (const std::exception& e) { return fail(GS_E_STARK, std::string("Verification failed: ") + e.what()); }
 }

@@ -90,3 +90,29 @@ def test_digest_and_verify_batch(alg):
         wrong_root = bytes(32)
         assert L.gs_merkle_verify_batch(a, wrong_root, arr, len(idx), bytes(blob), len(blob)) == 0
     assert L.gs_merkle_verify_batch(a, tree.root, arr, len(idx), bytes(blob[:20]), 20) < 0
+
+
+def test_verify_batch_counts_in_the_blob_never_size_an_allocation():
+    """column / node counts are attacker-controlled 32-bit words: 2^32 - 1 columns used to end the process in std::bad_alloc
+    (found by fuzzing the blob); every count the remaining bytes cannot hold is a malformed proof (negative status), never a crash"""
+    L = _native.lib()
+    oh = OHash('blake2s256')
+    r = random.Random(9)
+    leaves = [oh.digest(r.randbytes(16)) for _ in range(32)]
+    tree = OTree.create(leaves, oh)
+    idx = [3, 9, 20]
+    proof = tree.prove_batch(idx)
+    blob = bytearray(len(proof.values).to_bytes(4, 'little') + len(proof.nodes).to_bytes(4, 'little') + proof.depth.to_bytes(4, 'little'))
+    for v in proof.values:
+        blob += v
+    first_len = len(blob)                             # offset of the first column's length word
+    for col in proof.nodes:
+        blob += len(col).to_bytes(4, 'little') + b''.join(col)
+    arr = (C.c_uint32 * len(idx))(*idx)
+    assert L.gs_merkle_verify_batch(1, tree.root, arr, len(idx), bytes(blob), len(blob)) == 1
+    for off in (4, first_len):                        # the column count, a column's node count
+        for v in (0xFFFFFFFF, 0x80000000, 0x7FFFFFFF, 0x10000000, len(blob)):
+            t = bytearray(blob); t[off:off + 4] = v.to_bytes(4, 'little')
+            assert L.gs_merkle_verify_batch(1, tree.root, arr, len(idx), bytes(t), len(t)) <= 0
+    t = bytearray(blob); t[8:12] = (200).to_bytes(4, 'little')        # depth beyond 32
+    assert L.gs_merkle_verify_batch(1, tree.root, arr, len(idx), bytes(t), len(t)) == 0
