@@ -55,6 +55,44 @@ static inline bool read_program(BlobReader& r, HostProgram& pr) {
     return r.ok;
 }
 
+// Every index an instruction carries is checked once, here, so that neither the host interpreter / code generator nor the
+// device evaluator (interpreting kernel, NVRTC source) ever indexes with a value taken from the blob unchecked: value slots
+// 0 .. n_slots-1 (reused, so "defined before it is read" is tracked per slot), constants, trace registers, static registers,
+// outputs (each written at least once).  `next` values exist in the constraint evaluator only.
+static inline const char* validate_instrs(const std::vector<std::array<uint32_t, 4>>& instrs, size_t n_consts, int n_slots, int n_out,
+                                          int R, int n_static, bool is_transition) {
+    if (n_slots < 1 || n_slots > (1 << 20)) return "program: value-slot count out of range";
+    if (n_out < 1 || n_out > GS_MAX_CONSTRAINTS) return "program: output count out of range";
+    std::vector<char> defined((size_t)n_slots, 0), written((size_t)n_out, 0);
+    const uint32_t ns = (uint32_t)n_slots, nc = (uint32_t)n_consts;
+    for (const auto& ins : instrs) {
+        const uint32_t op = ins[0], d = ins[1], x = ins[2], y = ins[3];
+        auto readable = [&](uint32_t slot) { return slot < ns && defined[slot]; };
+        switch (op) {
+            case OP_CONST: if (x >= nc) return "program: constant index out of range"; break;
+            case OP_NEXT: if (is_transition) return "program: a transition function cannot read the next state";   /* fall through */
+            case OP_CUR: if (x >= (uint32_t)R) return "program: trace register index out of range"; break;
+            case OP_STATIC: if (x >= (uint32_t)n_static) return "program: static register index out of range"; break;
+            case OP_ADD: case OP_SUB: case OP_MUL: if (!readable(x) || !readable(y)) return "program: operand slot read before it is written"; break;
+            case OP_NEG: case OP_INV: if (!readable(x)) return "program: operand slot read before it is written"; break;
+            case OP_EXP: if (!readable(x)) return "program: operand slot read before it is written"; if (y >= nc) return "program: exponent index out of range"; break;
+            case OP_OUT:
+                if (d >= (uint32_t)n_out) return "program: output index out of range";
+                if (!readable(x)) return "program: output reads a slot that was never written";
+                written[d] = 1;
+                continue;
+            default: return "program: unknown opcode";
+        }
+        if (d >= ns) return "program: destination slot out of range";
+        defined[d] = 1;
+    }
+    for (char w : written) if (!w) return "program: an output is never written";
+    return nullptr;
+}
+static inline const char* validate_program(const HostProgram& pr, int R, int n_static, bool is_transition) {
+    return validate_instrs(pr.instrs, pr.consts.size(), pr.n_slots, pr.n_out, R, n_static, is_transition);
+}
+
 // parse the AIR blob (air.py: pack_air) into the host part of a Stark; returns "" or an error message
 std::string parse_air(const uint8_t* air_blob, size_t blob_len, AirHost* S, int* code);
 #ifdef GS_HOSTAIR_IMPL
@@ -74,7 +112,7 @@ std::string parse_air(const uint8_t* air_blob, size_t blob_len, AirHost* S, int*
     for (auto& sr : S->statics) {
         sr.kind = (int)r.u32();
         const uint32_t len = r.u32();
-        if (!r.ok || len > (1u << 24)) return "bad static register";
+        if (!r.ok || len > (1u << 24) || sr.kind < 0 || sr.kind > 2 || (sr.kind != 0 && len != 0)) return "bad static register";
         sr.values.resize(len);
         for (auto& v : sr.values) v = r.elem();
         if (sr.kind == 0 && (len == 0 || (len & (len - 1)) || len > (1u << S->log_t))) return "cycle length must be a power of two <= steps";
@@ -85,6 +123,9 @@ std::string parse_air(const uint8_t* air_blob, size_t blob_len, AirHost* S, int*
     for (auto& d : S->degrees) d = (int)r.u32();
     if (!read_program(r, S->transition) || !read_program(r, S->evaluation)) return "bad AIR program";
     if (S->transition.n_out != S->R || S->evaluation.n_out != S->K) return "program outputs do not match the register / constraint counts";
+    if (const char* bad = validate_program(S->transition, S->R, (int)n_static, true)) return std::string("transition ") + bad;
+    if (const char* bad = validate_program(S->evaluation, S->R, (int)n_static, false)) return std::string("evaluation ") + bad;
+    for (int d : S->degrees) if (d < 0 || d > 256) return "constraint degree out of range";
     for (auto& ins : S->evaluation.instrs) if (ins[0] == OP_EXP) { *code = GS_E_UNSUPPORTED; return "exp with a large exponent in a constraint"; }
     *code = GS_OK;
     return "";

@@ -33,6 +33,22 @@ struct Field {
         }
         return 0;
     }
+    // Miller-Rabin with the first twelve primes as bases: deterministic below 3.3 * 10^24, so for every 64-bit modulus.
+    // A composite "modulus" would not only make the arithmetic meaningless, it has no element of the required order and the
+    // generator search above would walk the whole range (found by fuzzing the AIR blob: a one-bit change of p32).
+    bool is_prime() const {
+        if (p < 2) return false;
+        for (u64 q : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) if (p % q == 0) return p == q;
+        u64 d = p - 1; int sft = 0; while ((d & 1) == 0) { d >>= 1; ++sft; }
+        for (u64 a : {2ull, 3ull, 5ull, 7ull, 11ull, 13ull, 17ull, 19ull, 23ull, 29ull, 31ull, 37ull}) {
+            u64 x = pow(a % p, d);
+            if (x == 1 || x == p - 1) continue;
+            bool comp = true;
+            for (int r = 1; r < sft && comp; ++r) { x = mul(x, x); if (x == p - 1) comp = false; }
+            if (comp) return false;
+        }
+        return true;
+    }
     u64 digest_mod(const uint8_t d[32]) const { u128 r = 0; for (int k = 0; k < 32; ++k) r = ((r << 8) | d[k]) % p; return (u64)r; }
     u64 prng_one(const uint8_t* seed, size_t n) const { uint8_t d[32]; sha256_bytes(seed, n, d); return digest_mod(d); }
     std::vector<u64> prng_many(const uint8_t* seed, size_t n, int count) const {
@@ -112,6 +128,7 @@ static inline std::string parse_air64(const uint8_t* blob, size_t len, Air& A, i
     if (!ok || mod < 3 || (mod >> 64) != 0) { *code = GS_E_UNSUPPORTED; return "the host path takes prime fields of at most 64 bits"; }
     A.F.p = (u64)mod; int bits = 0; while (bits < 64 && (mod >> bits)) ++bits;
     A.F.es = std::max(8, (bits + 7) / 8);
+    if (!A.F.is_prime()) { *code = GS_E_UNSUPPORTED; return "the modulus is not prime"; }
     A.R = (int)u32(); A.K = (int)u32(); A.log_t = (int)u32(); A.log_e = (int)u32();
     const uint32_t ns = u32();
     if (!ok || A.R < 1 || A.R > GS_MAX_COLS || A.K < 1 || A.K > GS_MAX_CONSTRAINTS || ns > GS_MAX_COLS) { *code = GS_E_UNSUPPORTED; return "AIR shape out of range"; }
@@ -120,7 +137,7 @@ static inline std::string parse_air64(const uint8_t* blob, size_t len, Air& A, i
     A.statics.resize(ns);
     for (auto& s : A.statics) {
         s.kind = (int)u32(); const uint32_t l = u32();
-        if (!ok || l > (1u << 20)) return "bad static register";
+        if (!ok || l > (1u << 20) || s.kind < 0 || s.kind > 2 || (s.kind != 0 && l != 0)) return "bad static register";
         s.values.resize(l);
         for (auto& v : s.values) { const u128 w = wide(); if (w >= A.F.p) ok = false; v = (u64)w; }
         if (s.kind == 0 && (l == 0 || (l & (l - 1)) || l > (1u << A.log_t))) return "cycle length must be a power of two <= steps";
@@ -139,6 +156,9 @@ static inline std::string parse_air64(const uint8_t* blob, size_t len, Air& A, i
     }
     if (!ok) return "truncated AIR blob";
     if (A.transition.n_out != A.R || A.evaluation.n_out != A.K) return "program outputs do not match the register / constraint counts";
+    if (const char* bad = validate_instrs(A.transition.ins, A.transition.consts.size(), A.transition.n_slots, A.transition.n_out, A.R, (int)ns, true)) return std::string("transition ") + bad;
+    if (const char* bad = validate_instrs(A.evaluation.ins, A.evaluation.consts.size(), A.evaluation.n_slots, A.evaluation.n_out, A.R, (int)ns, false)) return std::string("evaluation ") + bad;
+    for (int d : A.degrees) if (d < 0 || d > 256) return "constraint degree out of range";
     *code = GS_OK;
     return "";
 }
