@@ -16,6 +16,13 @@ from genstark_b200.stark import input_blob
 HDR = 4 + 16 + 20            # magic, modulus, R K log_t log_e n_static
 
 
+@pytest.fixture(autouse=True)
+def _interpreter_only(monkeypatch):
+    """mutants would each be compiled by the trace JIT, and compiling the unmutated programs here would pre-fill the in-process
+    cache that tests/test_trace_jit.py inspects"""
+    monkeypatch.setenv('GS_TRACE_JIT', '0')
+
+
 def _trace_rc(blob, air, inputs, seed):
     L = _native.lib()
     p = air.modulus
@@ -78,10 +85,7 @@ def test_slot_counts_registers_and_static_kinds_are_checked():
 
 def test_random_mutations_of_the_blob_never_crash_the_host_paths():
     """2000 mutants per AIR family through parse + trace generation (interpreter) -- the in-suite slice of the campaign"""
-    import os
-    old = os.environ.get('GS_TRACE_JIT')
-    os.environ['GS_TRACE_JIT'] = '0'
-    try:
+    if True:
         for name, mk in (('mimc', lambda: cases.mimc(64, 8)), ('poseidon', lambda: cases.poseidon(2, 1, e=16)), ('rescue', lambda: cases.rescue(2))):
             air, opts, a, inputs, seed = mk()
             blob = pack_air(air)
@@ -111,11 +115,6 @@ def test_random_mutations_of_the_blob_never_crash_the_host_paths():
                     if log_t > 8 or log_e > 5 or regs > 4 * air.trace_register_count:
                         continue                        # a legitimate but much larger trace than the output buffer of this test
                 _trace_rc(t, air, inputs, seed)
-    finally:
-        if old is None:
-            os.environ.pop('GS_TRACE_JIT', None)
-        else:
-            os.environ['GS_TRACE_JIT'] = old
 
 
 def test_small_field_path_refuses_a_composite_modulus_instead_of_searching_for_a_generator():
