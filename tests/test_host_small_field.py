@@ -246,6 +246,14 @@ def test_small_field_verifier_rejects_mutations_without_crashing(data):
         t[i:i + n] = bytes(len(t[i:i + n]))
     if bytes(t) == buf:
         return
+    try:
+        # the wire format's one non-canonical spot (serialization.ts:25-124): the "first node is a raw leaf" bit of a node column
+        # changes nothing when a row is as long as a digest (4 x 8-byte elements = 32 bytes here), nor for an empty column; a
+        # mutant that parses to the same proof is the same proof, not a forgery (seen 4 times in 40 000 mutations)
+        if st.serialize(st.parse(bytes(t))) == buf:
+            return
+    except Exception:
+        pass
     with pytest.raises(StarkError):
         st.verify(a, bytes(t))
 
