@@ -296,8 +296,32 @@ class AirModule:
 def gather_column_blob(values: Sequence[int], index, modulus: int) -> bytes:
     """column[t] = values[index[t]] as 16-byte little-endian elements; ``index`` is a numpy integer array"""
     import numpy as np
-    table = np.frombuffer(b''.join((int(v) % modulus).to_bytes(16, 'little') for v in values), dtype=np.uint8).reshape(-1, 16)
-    return table[np.asarray(index)].tobytes()
+    # 16-byte elements are moved as one complex128 item each (a typed take: ~0.1 ms per 2^16 rows; indexing rows of a
+    # (n, 16) uint8 table, or the default bounds-checking mode of take, costs 2 ms) -- the range is checked once up front
+    table = np.frombuffer(b''.join((int(v) % modulus).to_bytes(16, 'little') for v in values), dtype=np.complex128)
+    idx = np.asarray(index).astype(np.intp, copy=False)
+    if idx.size and (int(idx.min()) < 0 or int(idx.max()) >= table.shape[0]):
+        raise IndexError('input register index outside the input values')
+    return np.take(table, idx, mode='clip').tobytes()
+
+
+def gather_columns_blob(columns, modulus: int) -> bytes:
+    """several gather_column_blob columns ([(values, index), ...], all of one length) back to back, written straight into one
+    buffer: one copy at the end instead of one per column plus a join (5 MB for the Poseidon Merkle-proof inputs)"""
+    import numpy as np
+    if not columns:
+        return b''
+    n = len(np.asarray(columns[0][1]))
+    out = np.empty(len(columns) * n, dtype=np.complex128)
+    for k, (values, index) in enumerate(columns):
+        table = np.frombuffer(b''.join((int(v) % modulus).to_bytes(16, 'little') for v in values), dtype=np.complex128)
+        idx = np.asarray(index).astype(np.intp, copy=False)
+        if idx.shape != (n,):
+            raise ValueError('input register columns must have one length')
+        if n and (int(idx.min()) < 0 or int(idx.max()) >= table.shape[0]):
+            raise IndexError('input register index outside the input values')
+        np.take(table, idx, mode='clip', out=out[k * n:(k + 1) * n])
+    return out.tobytes()
 
 
 def input_blob(air: 'AirModule', inputs) -> Optional[bytes]:

@@ -9,7 +9,7 @@ from __future__ import annotations
 import hashlib
 from typing import List, Sequence
 
-from .air import (AirModule, ProgramBuilder, StaticRegister, P128, P32, gather_column_blob, prng_sha256)
+from .air import (AirModule, ProgramBuilder, StaticRegister, P128, P32, gather_column_blob, gather_columns_blob, prng_sha256)
 
 MIMC_SEED = bytes.fromhex('4d694d43')       # examples/mimc/mimc128.ts:15,36
 
@@ -191,11 +191,19 @@ def rescue4x128(instances: int = 1, extension_factor: int = None) -> AirModule:
             out.append([vals[((step + 1) // RESCUE_STEPS) % instances] for step in range(steps)])
         return out
 
+    def expand_blob(inputs):
+        """same columns as expand(), gathered with numpy (prove path: 16 384 Python integers cost more than the device part)"""
+        import numpy as np
+        for reg in range(4):
+            assert len(inputs[reg]) == instances
+        idx = ((np.arange(steps, dtype=np.int64) + 1) // RESCUE_STEPS) % instances
+        return gather_columns_blob([(inputs[reg], idx) for reg in range(4)], p)
+
     return AirModule(
         name='rescue4x128', modulus=p, trace_register_count=4, trace_length=steps,
         transition=t.build(), evaluation=e.build(), static_registers=statics, extension_factor=extension_factor,
         init=lambda inputs, seed: [int(inputs[reg][0]) % p for reg in range(4)],
-        expand_inputs=expand, input_shapes=lambda inputs: [[instances] for _ in range(4)])
+        expand_inputs=expand, expand_inputs_blob=expand_blob, input_shapes=lambda inputs: [[instances] for _ in range(4)])
 
 
 # -------------------------------------------------------------------------------------------- Poseidon
@@ -314,9 +322,8 @@ def poseidon_merkle_proof(depth: int = 8, proofs: int = 1, extension_factor: int
         nxt = (np.arange(steps, dtype=np.int64) + 1) % steps
         pr, lv = nxt // period, (nxt % period) // cyc
         flat = lambda m: [x for row in m for x in row]
-        return b''.join([gather_column_blob(leaf0, pr, p), gather_column_blob(leaf1, pr, p),
-                         gather_column_blob(flat(node0), pr * depth + lv, p), gather_column_blob(flat(node1), pr * depth + lv, p),
-                         gather_column_blob(flat(bits), pr * depth + lv, p)])
+        at = pr * depth + lv
+        return gather_columns_blob([(leaf0, pr), (leaf1, pr), (flat(node0), at), (flat(node1), at), (flat(bits), at)], p)
 
     def expand_public(public_inputs):
         (bits,) = public_inputs

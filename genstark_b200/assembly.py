@@ -41,7 +41,7 @@ import os
 import re
 from typing import Dict, List, Optional, Sequence
 
-from .air import AirModule, Program, ProgramBuilder, StaticRegister, gather_column_blob, prng_sha256, _Node
+from .air import AirModule, Program, ProgramBuilder, StaticRegister, gather_column_blob, gather_columns_blob, prng_sha256, _Node
 
 
 class AssemblyError(Exception):
@@ -621,8 +621,8 @@ class AirComponent:
                     raise AssemblyError(f'input {k} is declared binary')
                 if k not in index_cache:
                     index_cache[k] = ((np.arange(T, dtype=np.int64) - shifts[k]) % T) // span[k]
-                out.append(gather_column_blob(flat, index_cache[k], p))
-            return b''.join(out)
+                out.append((flat, index_cache[k]))
+            return gather_columns_blob(out, p)
 
         def expand_public(public_inputs):
             if len(public_inputs or []) != len(public): raise AssemblyError(f'{len(public)} public inputs expected')
