@@ -305,14 +305,16 @@ def gather_column_blob(values: Sequence[int], index, modulus: int) -> bytes:
     return np.take(table, idx, mode='clip').tobytes()
 
 
-def gather_columns_blob(columns, modulus: int) -> bytes:
+def gather_columns_blob(columns, modulus: int, as_buffer: bool = False):
     """several gather_column_blob columns ([(values, index), ...], all of one length) back to back, written straight into one
-    buffer: one copy at the end instead of one per column plus a join (5 MB for the Poseidon Merkle-proof inputs)"""
+    buffer: one copy at the end instead of one per column plus a join (5 MB for the Poseidon Merkle-proof inputs).
+    as_buffer: return the bytearray the columns were gathered into (no copy at all; input_cbuf hands it to the C ABI)."""
     import numpy as np
     if not columns:
-        return b''
+        return bytearray() if as_buffer else b''
     n = len(np.asarray(columns[0][1]))
-    out = np.empty(len(columns) * n, dtype=np.complex128)
+    buf = bytearray(16 * len(columns) * n)
+    out = np.frombuffer(buf, dtype=np.complex128)
     for k, (values, index) in enumerate(columns):
         table = np.frombuffer(b''.join((int(v) % modulus).to_bytes(16, 'little') for v in values), dtype=np.complex128)
         idx = np.asarray(index).astype(np.intp, copy=False)
@@ -321,7 +323,8 @@ def gather_columns_blob(columns, modulus: int) -> bytes:
         if n and (int(idx.min()) < 0 or int(idx.max()) >= table.shape[0]):
             raise IndexError('input register index outside the input values')
         np.take(table, idx, mode='clip', out=out[k * n:(k + 1) * n])
-    return out.tobytes()
+    del out                                  # release the export so the bytearray can be handed on (or resized) freely
+    return buf if as_buffer else bytes(buf)
 
 
 def input_blob(air: 'AirModule', inputs) -> Optional[bytes]:
@@ -333,6 +336,20 @@ def input_blob(air: 'AirModule', inputs) -> Optional[bytes]:
         return None
     p = air.modulus
     return b''.join((int(v) % p).to_bytes(16, 'little') for t in traces for v in t)
+
+
+def input_cbuf(air: 'AirModule', inputs):
+    """input_blob for the C ABI without the last copy: a ctypes char array over the buffer the columns were gathered into
+    (accepted wherever the binding declares c_char_p), or bytes / None when the AIR has no buffer-returning expansion"""
+    import ctypes as C
+    if air.expand_inputs_blob is not None:
+        try:
+            buf = air.expand_inputs_blob(inputs or [], as_buffer=True)
+        except TypeError:                    # an expansion function that only takes the inputs
+            buf = None
+        if isinstance(buf, bytearray):
+            return (C.c_char * len(buf)).from_buffer(buf) if len(buf) else None
+    return input_blob(air, inputs)
 
 
 AIR_BLOB_MAGIC = 0x52494147      # 'GAIR'

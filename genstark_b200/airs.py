@@ -191,13 +191,13 @@ def rescue4x128(instances: int = 1, extension_factor: int = None) -> AirModule:
             out.append([vals[((step + 1) // RESCUE_STEPS) % instances] for step in range(steps)])
         return out
 
-    def expand_blob(inputs):
+    def expand_blob(inputs, as_buffer=False):
         """same columns as expand(), gathered with numpy (prove path: 16 384 Python integers cost more than the device part)"""
         import numpy as np
         for reg in range(4):
             assert len(inputs[reg]) == instances
         idx = ((np.arange(steps, dtype=np.int64) + 1) // RESCUE_STEPS) % instances
-        return gather_columns_blob([(inputs[reg], idx) for reg in range(4)], p)
+        return gather_columns_blob([(inputs[reg], idx) for reg in range(4)], p, as_buffer)
 
     return AirModule(
         name='rescue4x128', modulus=p, trace_register_count=4, trace_length=steps,
@@ -315,7 +315,7 @@ def poseidon_merkle_proof(depth: int = 8, proofs: int = 1, extension_factor: int
             regs[4][s] = int(bits[pr][lv]) % p
         return regs
 
-    def expand_blob(inputs):
+    def expand_blob(inputs, as_buffer=False):
         """same columns as expand(), gathered with numpy"""
         import numpy as np
         leaf0, leaf1, node0, node1, bits = inputs
@@ -323,7 +323,7 @@ def poseidon_merkle_proof(depth: int = 8, proofs: int = 1, extension_factor: int
         pr, lv = nxt // period, (nxt % period) // cyc
         flat = lambda m: [x for row in m for x in row]
         at = pr * depth + lv
-        return gather_columns_blob([(leaf0, pr), (leaf1, pr), (flat(node0), at), (flat(node1), at), (flat(bits), at)], p)
+        return gather_columns_blob([(leaf0, pr), (leaf1, pr), (flat(node0), at), (flat(node1), at), (flat(bits), at)], p, as_buffer)
 
     def expand_public(public_inputs):
         (bits,) = public_inputs

@@ -608,7 +608,7 @@ class AirComponent:
 
         index_cache = {}
 
-        def expand_blob(inputs):
+        def expand_blob(inputs, as_buffer=False):
             """the columns of expand() as bytes, gathered with numpy (prove path)"""
             import numpy as np
             if len(inputs or []) != len(regs): raise AssemblyError(f'{len(regs)} inputs expected')
@@ -622,7 +622,7 @@ class AirComponent:
                 if k not in index_cache:
                     index_cache[k] = ((np.arange(T, dtype=np.int64) - shifts[k]) % T) // span[k]
                 out.append((flat, index_cache[k]))
-            return gather_columns_blob(out, p)
+            return gather_columns_blob(out, p, as_buffer)
 
         def expand_public(public_inputs):
             if len(public_inputs or []) != len(public): raise AssemblyError(f'{len(public)} public inputs expected')

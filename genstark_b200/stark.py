@@ -15,7 +15,7 @@ import struct
 from typing import Dict, List, Optional, Sequence
 
 from . import _native
-from .air import AirModule, input_blob, pack_air
+from .air import AirModule, input_blob, input_cbuf, pack_air
 from .field import Context
 
 DEFAULT_EXE_QUERY_COUNT, DEFAULT_FRI_QUERY_COUNT = 80, 40          # Stark.ts:13-14
@@ -108,7 +108,7 @@ class Stark:
         a_blob = b''.join(struct.pack('<II', int(a['register']), int(a['step'])) + (int(a['value']) % p).to_bytes(16, 'little')
                           for a in assertions)
         init_blob = b''.join(v.to_bytes(16, 'little') for v in init)
-        in_blob = input_blob(air, inputs)
+        in_blob = input_cbuf(air, inputs)          # zero-copy columns of the input registers
         shapes = air.input_shapes(inputs or [])
         s_blob = bytes([len(shapes)]) + b''.join(bytes([len(s)]) + b''.join(struct.pack('<I', x) for x in s) for s in shapes)
         out_p, out_n = C.POINTER(C.c_uint8)(), C.c_size_t()
@@ -331,7 +331,7 @@ class HostStark(Stark):
             raise StarkError('Failed to generate the execution trace: initial state has the wrong width')
         a_blob = b''.join(struct.pack('<II', int(a['register']), int(a['step'])) + (int(a['value']) % p).to_bytes(16, 'little')
                           for a in assertions)
-        in_blob = input_blob(air, inputs)
+        in_blob = input_cbuf(air, inputs)          # zero-copy columns of the input registers
         shapes = air.input_shapes(inputs or [])
         s_blob = bytes([len(shapes)]) + b''.join(bytes([len(s)]) + b''.join(struct.pack('<I', x) for x in s) for s in shapes)
         blob = pack_air(air)
@@ -433,7 +433,7 @@ def generate_execution_trace(air: AirModule, inputs=None, seed=None) -> List[Lis
     init = [int(v) % p for v in air.init(inputs or [], seed or [])]
     if len(init) != air.trace_register_count:
         raise StarkError('Failed to generate the execution trace: initial state has the wrong width')
-    in_blob = input_blob(air, inputs)
+    in_blob = input_cbuf(air, inputs)
     blob = pack_air(air)
     r, t = air.trace_register_count, air.trace_length
     out = C.create_string_buffer(16 * r * t)
