@@ -48,19 +48,164 @@ struct TraceJit {
 
 static inline std::string jit_hex_u64(u64_t v) { char b[32]; snprintf(b, sizeof b, "0x%llxull", v); return b; }
 
-// C++ source of the block function for this transition program.  Straight-line SSA over the flat program; products
+// ---- mask specialisation -------------------------------------------------------------------------------------------
+// Multi-instance AIRs select between sub-computations with 0/1 cyclic registers: next = m * A + (1 - m) * B (the full /
+// partial round of Poseidon, "first step of a segment" masks).  Evaluated as written, every step pays for both A and B.
+// The masks are static registers whose cycle values are all 0 or 1 -- known when the code is generated -- so the transition
+// is specialised once per combination of mask values that occurs: the mask becomes a constant, x * 0 / x * 1 / x + 0 fold
+// away and what only fed the dead branch is dropped; the step loop switches on the mask values of the step.  Same values
+// (the folds are exact field identities), ~2.5x fewer multiplications per Poseidon step.
+struct JitVariant { unsigned combo; HostProgram prog; };
+
+// pr with static register mask_regs[j] fixed to bit j of `bits`: constants folded, identities aliased, dead code dropped.
+// Result in SSA form (a fresh slot per value).  false: a shape this pass does not handle (the generic body is used).
+static inline bool jit_specialise(const HostProgram& pr, const std::vector<int>& mask_regs, unsigned bits, HostProgram& out) {
+    const size_t n = pr.instrs.size();
+    struct Val { int kind = -1; u128 k = 0; int node = -1; };            // kind 0: node (instruction index), 1: known constant
+    std::vector<Val> val(n);
+    std::vector<int> def_of_slot(pr.n_slots + 1, -1);
+    struct Node { uint32_t op; Val a, b; uint32_t aux; };                   // aux: register / static index, or the exponent's constant index
+    std::vector<Node> node(n);
+    std::vector<Val> outs(pr.n_out);
+    auto known = [](const Val& v, u128 x) { return v.kind == 1 && v.k == x; };
+    auto K = [](u128 x) { Val v; v.kind = 1; v.k = x; return v; };
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t op = pr.instrs[i][0], d = pr.instrs[i][1], x = pr.instrs[i][2], y = pr.instrs[i][3];
+        Val A, B;
+        const bool bin = (op == OP_ADD || op == OP_SUB || op == OP_MUL), un = (op == OP_NEG || op == OP_INV || op == OP_EXP || op == OP_OUT);
+        if (bin || un) { if (x > (uint32_t)pr.n_slots || def_of_slot[x] < 0) return false; A = val[def_of_slot[x]]; }
+        if (bin) { if (y > (uint32_t)pr.n_slots || def_of_slot[y] < 0) return false; B = val[def_of_slot[y]]; }
+        Val r; r.kind = 0; r.node = (int)i;
+        node[i] = Node{op, A, B, 0};
+        switch (op) {
+            case OP_CONST: if (x >= pr.consts.size()) return false; r = K(pr.consts[x]); break;
+            case OP_CUR: node[i].aux = x; break;
+            case OP_STATIC: {
+                node[i].aux = x;
+                for (size_t j = 0; j < mask_regs.size(); ++j) if ((uint32_t)mask_regs[j] == x) r = K((bits >> j) & 1u);
+                break;
+            }
+            case OP_ADD:
+                if (A.kind == 1 && B.kind == 1) r = K(h_add(A.k, B.k));
+                else if (known(A, 0)) r = B;
+                else if (known(B, 0)) r = A;
+                break;
+            case OP_SUB:
+                if (A.kind == 1 && B.kind == 1) r = K(h_sub(A.k, B.k));
+                else if (known(B, 0)) r = A;
+                break;
+            case OP_MUL:
+                if (known(A, 0) || known(B, 0)) r = K(0);
+                else if (A.kind == 1 && B.kind == 1) r = K(h_mul(A.k, B.k));
+                else if (known(A, 1)) r = B;
+                else if (known(B, 1)) r = A;
+                break;
+            case OP_NEG: if (A.kind == 1) r = K(h_sub(0, A.k)); break;
+            case OP_INV: if (A.kind == 1) r = K(h_inv(A.k)); break;
+            case OP_EXP: if (y >= pr.consts.size()) return false; node[i].aux = y; if (A.kind == 1) r = K(h_pow(A.k, pr.consts[y])); break;
+            case OP_OUT: if (d >= (uint32_t)pr.n_out) return false; outs[d] = A; continue;
+            default: return false;
+        }
+        if (d > (uint32_t)pr.n_slots) return false;
+        val[i] = r;
+        def_of_slot[d] = (int)i;
+    }
+    for (const Val& v : outs) if (v.kind < 0) return false;
+    // liveness from the outputs
+    std::vector<char> live(n, 0);
+    std::vector<int> stack;
+    for (const Val& v : outs) if (v.kind == 0 && !live[v.node]) { live[v.node] = 1; stack.push_back(v.node); }
+    while (!stack.empty()) {
+        const int i = stack.back(); stack.pop_back();
+        for (const Val* v : {&node[i].a, &node[i].b}) if (v->kind == 0 && !live[v->node]) { live[v->node] = 1; stack.push_back(v->node); }
+    }
+    // re-emit in SSA form
+    out = HostProgram(); out.n_out = pr.n_out;
+    std::map<u128, uint32_t> const_idx;
+    auto cidx = [&](u128 x) { auto it = const_idx.find(x); if (it != const_idx.end()) return it->second; const uint32_t k = (uint32_t)out.consts.size(); out.consts.push_back(x); const_idx[x] = k; return k; };
+    std::vector<int> slot_of(n, -1);
+    uint32_t next_slot = 0;
+    auto operand = [&](const Val& v) -> uint32_t {                       // slot holding the operand (constants get a slot of their own)
+        if (v.kind == 0) return (uint32_t)slot_of[v.node];
+        const uint32_t sl = next_slot++;
+        out.instrs.push_back({(uint32_t)OP_CONST, sl, cidx(v.k), 0u});
+        return sl;
+    };
+    for (size_t i = 0; i < n; ++i) {
+        if (!live[i]) continue;
+        const Node& nd = node[i];
+        uint32_t a = 0, b = 0;
+        switch (nd.op) {
+            case OP_CUR: case OP_STATIC: a = nd.aux; break;
+            case OP_ADD: case OP_SUB: case OP_MUL: a = operand(nd.a); b = operand(nd.b); break;
+            case OP_NEG: case OP_INV: a = operand(nd.a); break;
+            case OP_EXP: a = operand(nd.a); b = cidx(pr.consts[nd.aux]); break;
+            default: return false;
+        }
+        slot_of[i] = (int)next_slot++;
+        out.instrs.push_back({nd.op, (uint32_t)slot_of[i], a, b});
+    }
+    for (int r = 0; r < pr.n_out; ++r) out.instrs.push_back({(uint32_t)OP_OUT, (uint32_t)r, operand(outs[r]), 0u});
+    out.n_slots = (int)std::max<uint32_t>(next_slot, 1u);
+    return true;
+}
+
+// the static registers that are 0/1 cycles (at most four are used), and the combinations of their values that occur
+static inline void jit_find_masks(const AirHost* S, std::vector<int>& mask_regs, std::vector<unsigned>& combos, std::vector<size_t>* counts = nullptr) {
+    mask_regs.clear(); combos.clear(); if (counts) counts->clear();
+    if (const char* e = getenv("GS_TRACE_SPECIALISE")) if (e[0] == '0') return;
+    size_t period = 1;
+    for (size_t k = 0; k < S->statics.size() && mask_regs.size() < 4; ++k) {
+        const StaticReg& sr = S->statics[k];
+        if (sr.kind != 0 || sr.values.empty() || (sr.values.size() & (sr.values.size() - 1))) continue;
+        bool binary = true;
+        for (u128 v : sr.values) if (v > 1) { binary = false; break; }
+        if (!binary) continue;
+        bool used = false;
+        for (const auto& ins : S->transition.instrs) if (ins[0] == OP_STATIC && ins[2] == (uint32_t)k) { used = true; break; }
+        if (!used) continue;
+        mask_regs.push_back((int)k);
+        period = std::max(period, sr.values.size());
+    }
+    if (mask_regs.empty()) return;
+    std::vector<int> seen(1u << mask_regs.size(), -1);
+    for (size_t s = 0; s < period; ++s) {
+        unsigned c = 0;
+        for (size_t j = 0; j < mask_regs.size(); ++j) { const auto& v = S->statics[mask_regs[j]].values; c |= (unsigned)(v[s & (v.size() - 1)] & 1) << j; }
+        if (seen[c] < 0) { seen[c] = (int)combos.size(); combos.push_back(c); if (counts) counts->push_back(0); }
+        if (counts) (*counts)[seen[c]]++;
+    }
+}
+// rough cost of one step of a program in multiplications (an exponentiation or an inversion is a long chain of them)
+static inline double jit_program_cost(const HostProgram& pr) {
+    double c = 0;
+    for (const auto& ins : pr.instrs) {
+        if (ins[0] == OP_MUL) c += 1;
+        else if (ins[0] == OP_EXP) { u128 e = ins[3] < pr.consts.size() ? pr.consts[ins[3]] : 0; int bits = 0; while (e) { ++bits; e >>= 1; } c += 1.5 * bits; }
+        else if (ins[0] == OP_INV) c += 190;
+        else if (ins[0] == OP_ADD || ins[0] == OP_SUB || ins[0] == OP_NEG) c += 0.1;
+    }
+    return c;
+}
+
+static inline void jit_emit_consts(std::ostringstream& o, const HostProgram& pr, const std::string& kp) {
+    for (size_t i = 0; i < pr.consts.size(); ++i)
+        o << "static const w128 " << kp << i << " = {" << jit_hex_u64((u64_t)pr.consts[i]) << ", " << jit_hex_u64((u64_t)(pr.consts[i] >> 64)) << "};\n";
+}
+
+// One step of a transition program as straight-line SSA (state s<r> -> s<r>); constants are named <kp><index>.  Products
 // that feed exactly one further multiplication or addition are fused with it (f_mul3_add / f_mul_add,
 // hostfield_fast.h), which removes a modular reduction from the dependency chain of S-boxes such as x^3 + k.
-static inline std::string jit_emit_source(const HostProgram& pr, int R, int n_static) {
+static inline bool jit_emit_body(std::ostringstream& o, const HostProgram& pr, int R, int n_static, const std::string& kp, const std::string& ind) {
     const size_t n = pr.instrs.size();
     // definitions: which instruction defines each operand, and how often each definition is read
     std::vector<int> def_of_slot(pr.n_slots + 1, -1), da(n, -1), db(n, -1), uses(n, 0);
     for (size_t i = 0; i < n; ++i) {
         const uint32_t op = pr.instrs[i][0];
         const bool bin = (op == OP_ADD || op == OP_SUB || op == OP_MUL), un = (op == OP_NEG || op == OP_INV || op == OP_EXP || op == OP_OUT);
-        if (bin) { da[i] = def_of_slot[pr.instrs[i][2]]; db[i] = def_of_slot[pr.instrs[i][3]]; if (da[i] < 0 || db[i] < 0) return ""; uses[da[i]]++; uses[db[i]]++; }
-        if (un) { da[i] = def_of_slot[pr.instrs[i][2]]; if (da[i] < 0) return ""; uses[da[i]]++; }
-        if (op == OP_NEXT || op > OP_OUT) return "";
+        if (bin) { da[i] = def_of_slot[pr.instrs[i][2]]; db[i] = def_of_slot[pr.instrs[i][3]]; if (da[i] < 0 || db[i] < 0) return false; uses[da[i]]++; uses[db[i]]++; }
+        if (un) { da[i] = def_of_slot[pr.instrs[i][2]]; if (da[i] < 0) return false; uses[da[i]]++; }
+        if (op == OP_NEXT || op > OP_OUT) return false;
         if (op != OP_OUT) def_of_slot[pr.instrs[i][1]] = (int)i;
     }
     // fusion: child[j] = the product folded into instruction j; that product is not emitted on its own
@@ -71,18 +216,64 @@ static inline std::string jit_emit_source(const HostProgram& pr, int R, int n_st
         if (op != OP_MUL && op != OP_ADD) continue;
         if (da[j] == db[j]) continue;                                       // x*x, x+x: nothing to fold
         for (int side = 0; side < 2 && child[j] < 0; ++side) {
-            const int d = side ? db[j] : da[j], o = side ? da[j] : db[j];
+            const int d = side ? db[j] : da[j], o2 = side ? da[j] : db[j];
             if (!is_mul(d) || uses[d] != 1 || deferred[d]) continue;
             if (op == OP_MUL && child[d] >= 0) continue;                     // a product of at most three factors
-            child[j] = d; other[j] = o; deferred[d] = 1;
+            child[j] = d; other[j] = o2; deferred[d] = 1;
         }
     }
+    std::vector<std::string> name(n);            // expression naming each definition's value
+    std::vector<std::string> nxt(R);
+    auto operands = [&](int d) { return name[da[d]] + ", " + name[db[d]]; };      // of a product
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t op = pr.instrs[i][0], d = pr.instrs[i][1], x = pr.instrs[i][2], y = pr.instrs[i][3];
+        const std::string v = "v" + std::to_string(i);
+        if (deferred[i]) continue;
+        switch (op) {
+            case OP_CONST: if (x >= pr.consts.size()) return false; name[i] = kp + std::to_string(x); break;
+            case OP_CUR: if ((int)x >= R) return false; name[i] = "s" + std::to_string(x); break;
+            case OP_STATIC: if ((int)x >= n_static) return false; o << ind << "const w128 " << v << " = st" << x << "[(u64_t)s & m" << x << "];\n"; name[i] = v; break;
+            case OP_ADD:
+                if (child[i] >= 0) {
+                    const int m = child[i];
+                    if (child[m] >= 0) o << ind << "const w128 " << v << " = f_mul3_add(" << operands(child[m]) << ", " << name[other[m]] << ", " << name[other[i]] << ");\n";
+                    else o << ind << "const w128 " << v << " = f_mul_add(" << operands(m) << ", " << name[other[i]] << ");\n";
+                } else o << ind << "const w128 " << v << " = w_add(" << name[da[i]] << ", " << name[db[i]] << ");\n";
+                name[i] = v; break;
+            case OP_MUL:
+                if (child[i] >= 0) o << ind << "const w128 " << v << " = f_mul3_add(" << operands(child[i]) << ", " << name[other[i]] << ", k_zero);\n";
+                else o << ind << "const w128 " << v << " = f_mul_add(" << name[da[i]] << ", " << name[db[i]] << ", k_zero);\n";
+                name[i] = v; break;
+            case OP_SUB: o << ind << "const w128 " << v << " = w_sub(" << name[da[i]] << ", " << name[db[i]] << ");\n"; name[i] = v; break;
+            case OP_NEG: o << ind << "const w128 " << v << " = w_sub(k_zero, " << name[da[i]] << ");\n"; name[i] = v; break;
+            case OP_INV: o << ind << "const w128 " << v << " = w_inv(" << name[da[i]] << ");\n"; name[i] = v; break;
+            case OP_EXP: {
+                if (y >= pr.consts.size()) return false;
+                const u128 e = pr.consts[y];
+                o << ind << "const w128 " << v << " = w_pow(" << name[da[i]] << ", " << jit_hex_u64((u64_t)e) << ", " << jit_hex_u64((u64_t)(e >> 64)) << ");\n";
+                name[i] = v; break;
+            }
+            case OP_OUT: if ((int)d < R) nxt[d] = name[da[i]]; break;
+            default: return false;
+        }
+    }
+    for (int r = 0; r < R; ++r) if (nxt[r].empty()) return false;
+    // the new state is assigned after every output is computed (outputs may read the old state)
+    for (int r = 0; r < R; ++r) o << ind << "const w128 n" << r << " = " << nxt[r] << ";\n";
+    for (int r = 0; r < R; ++r) o << ind << "s" << r << " = n" << r << ";\n";
+    return true;
+}
+
+// C++ source of the block function for this transition program: the generic step, and one specialised step per combination
+// of mask values (variants; mask_regs[j] = static register whose value is bit j of a combination)
+static inline std::string jit_emit_source(const HostProgram& pr, int R, int n_static, const std::vector<int>& mask_regs = {},
+                                          const std::vector<JitVariant>& variants = {}) {
     std::ostringstream o;
     o << "#include <x86intrin.h>\n" << GS_HOSTFIELD_SRC << "\n" << GS_HOSTFIELD_FAST_SRC << "\n";
     o << "struct JitArgs { w128* state; const w128* const* stat; const u64_t* stat_mask; w128* trace; long long T, s0, s1, w0; };\n";
     o << "static const w128 k_zero = {0, 0};\n";
-    for (size_t i = 0; i < pr.consts.size(); ++i)
-        o << "static const w128 k" << i << " = {" << jit_hex_u64((u64_t)pr.consts[i]) << ", " << jit_hex_u64((u64_t)(pr.consts[i] >> 64)) << "};\n";
+    jit_emit_consts(o, pr, "k");
+    for (size_t v = 0; v < variants.size(); ++v) jit_emit_consts(o, variants[v].prog, "q" + std::to_string(v) + "_");
     o << "extern \"C\" void gs_trace_block(const JitArgs* a) {\n";
     o << "  const long long T = a->T, w0 = a->w0; w128* const tr = a->trace;\n";
     for (int r = 0; r < R; ++r) o << "  w128 s" << r << " = a->state[" << r << "];\n";
@@ -92,45 +283,28 @@ static inline std::string jit_emit_source(const HostProgram& pr, int R, int n_st
     for (int r = 0; r < R; ++r) o << "      tr[" << r << " * T + s] = w_from(w_canon(s" << r << "));\n";
     o << "    }\n";
     o << "    if (s + 1 == T) break;\n";
-    std::vector<std::string> name(n);            // expression naming each definition's value
-    std::vector<std::string> nxt(R);
-    auto operands = [&](int d) { return name[da[d]] + ", " + name[db[d]]; };      // of a product
-    for (size_t i = 0; i < n; ++i) {
-        const uint32_t op = pr.instrs[i][0], d = pr.instrs[i][1], x = pr.instrs[i][2], y = pr.instrs[i][3];
-        const std::string v = "v" + std::to_string(i);
-        if (deferred[i]) continue;
-        switch (op) {
-            case OP_CONST: if (x >= pr.consts.size()) return ""; name[i] = "k" + std::to_string(x); break;
-            case OP_CUR: if ((int)x >= R) return ""; name[i] = "s" + std::to_string(x); break;
-            case OP_STATIC: if ((int)x >= n_static) return ""; o << "    const w128 " << v << " = st" << x << "[(u64_t)s & m" << x << "];\n"; name[i] = v; break;
-            case OP_ADD:
-                if (child[i] >= 0) {
-                    const int m = child[i];
-                    if (child[m] >= 0) o << "    const w128 " << v << " = f_mul3_add(" << operands(child[m]) << ", " << name[other[m]] << ", " << name[other[i]] << ");\n";
-                    else o << "    const w128 " << v << " = f_mul_add(" << operands(m) << ", " << name[other[i]] << ");\n";
-                } else o << "    const w128 " << v << " = w_add(" << name[da[i]] << ", " << name[db[i]] << ");\n";
-                name[i] = v; break;
-            case OP_MUL:
-                if (child[i] >= 0) o << "    const w128 " << v << " = f_mul3_add(" << operands(child[i]) << ", " << name[other[i]] << ", k_zero);\n";
-                else o << "    const w128 " << v << " = f_mul_add(" << name[da[i]] << ", " << name[db[i]] << ", k_zero);\n";
-                name[i] = v; break;
-            case OP_SUB: o << "    const w128 " << v << " = w_sub(" << name[da[i]] << ", " << name[db[i]] << ");\n"; name[i] = v; break;
-            case OP_NEG: o << "    const w128 " << v << " = w_sub(k_zero, " << name[da[i]] << ");\n"; name[i] = v; break;
-            case OP_INV: o << "    const w128 " << v << " = w_inv(" << name[da[i]] << ");\n"; name[i] = v; break;
-            case OP_EXP: {
-                if (y >= pr.consts.size()) return "";
-                const u128 e = pr.consts[y];
-                o << "    const w128 " << v << " = w_pow(" << name[da[i]] << ", " << jit_hex_u64((u64_t)e) << ", " << jit_hex_u64((u64_t)(e >> 64)) << ");\n";
-                name[i] = v; break;
-            }
-            case OP_OUT: if ((int)d < R) nxt[d] = name[da[i]]; break;
-            default: return "";
+    if (variants.empty()) {
+        if (!jit_emit_body(o, pr, R, n_static, "k", "    ")) return "";
+    } else {
+        // the mask values of this step select the specialised step; any other value (a mask that is not 0 / 1 after all)
+        // takes the generic one
+        o << "    unsigned combo = 0, exact = 1;\n";
+        for (size_t j = 0; j < mask_regs.size(); ++j) {
+            const int k = mask_regs[j];
+            if (k < 0 || k >= n_static) return "";
+            o << "    { const w128 mv = st" << k << "[(u64_t)s & m" << k << "]; combo |= (unsigned)(mv.lo & 1) << " << j << "; exact &= (unsigned)(mv.hi == 0 && mv.lo <= 1); }\n";
         }
+        o << "    switch (exact ? combo : ~0u) {\n";
+        for (size_t v = 0; v < variants.size(); ++v) {
+            o << "      case " << variants[v].combo << "u: {\n";
+            if (!jit_emit_body(o, variants[v].prog, R, n_static, "q" + std::to_string(v) + "_", "        ")) return "";
+            o << "      } break;\n";
+        }
+        o << "      default: {\n";
+        if (!jit_emit_body(o, pr, R, n_static, "k", "        ")) return "";
+        o << "      } break;\n";
+        o << "    }\n";
     }
-    for (int r = 0; r < R; ++r) if (nxt[r].empty()) return "";
-    // the new state is assigned after every output is computed (outputs may read the old state)
-    for (int r = 0; r < R; ++r) o << "    const w128 n" << r << " = " << nxt[r] << ";\n";
-    for (int r = 0; r < R; ++r) o << "    s" << r << " = n" << r << ";\n";
     o << "  }\n";
     for (int r = 0; r < R; ++r) o << "  a->state[" << r << "] = s" << r << ";\n";
     o << "}\n";
@@ -138,9 +312,10 @@ static inline std::string jit_emit_source(const HostProgram& pr, int R, int n_st
 }
 
 // compile (or reuse) the block function of a transition program; never throws, never fails the prove
-std::shared_ptr<TraceJit> jit_get(const HostProgram& pr, int R, int n_static);
+std::shared_ptr<TraceJit> jit_get(const AirHost* S);
 #ifdef GS_HOSTAIR_IMPL
-std::shared_ptr<TraceJit> jit_get(const HostProgram& pr, int R, int n_static) {
+std::shared_ptr<TraceJit> jit_get(const AirHost* S) {
+    const HostProgram& pr = S->transition; const int R = S->R, n_static = (int)S->statics.size();
     static std::mutex mu;
     static std::map<std::string, std::shared_ptr<TraceJit>> cache;
     // the fallback is never silent: one line on stderr per program (GS_TRACE_JIT=0 is a request, not a failure), and
@@ -158,8 +333,23 @@ std::shared_ptr<TraceJit> jit_get(const HostProgram& pr, int R, int n_static) {
         return j;
     };
     if (const char* e = getenv("GS_TRACE_JIT")) if (e[0] == '0') return interp("GS_TRACE_JIT=0");
-    const std::string src = jit_emit_source(pr, R, n_static);
+    std::vector<int> mask_regs; std::vector<unsigned> combos; std::vector<size_t> counts; std::vector<JitVariant> variants;
+    jit_find_masks(S, mask_regs, combos, &counts);
+    double weighted = 0, total = 0;
+    for (size_t ci = 0; ci < combos.size(); ++ci) {
+        JitVariant v; v.combo = combos[ci];
+        if (!jit_specialise(pr, mask_regs, combos[ci], v.prog) || validate_program(v.prog, R, n_static, true) != nullptr) { variants.clear(); break; }
+        weighted += (double)counts[ci] * jit_program_cost(v.prog); total += (double)counts[ci];
+        variants.push_back(std::move(v));
+    }
+    // worth it only when the average step gets markedly cheaper (Poseidon: 0.4x); a select that guards a few multiplications
+    // next to two 128-bit exponentiations (Rescue) only adds a switch and code
+    const char* force = getenv("GS_TRACE_SPECIALISE");                       // "2": specialise whatever the estimate says (tests)
+    if (!variants.empty() && !(force && force[0] == '2') && weighted / total > 0.8 * jit_program_cost(pr)) variants.clear();
+    if (variants.empty()) mask_regs.clear();
+    const std::string src = jit_emit_source(pr, R, n_static, mask_regs, variants);
     if (src.empty()) return interp("program not supported by the code generator");
+    if (const char* dump = getenv("GS_JIT_DUMP")) { if (FILE* f = fopen(dump, "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); } }   // the generated source, for inspection
     const char* cxx = getenv("GS_JIT_CXX"); if (!cxx) cxx = getenv("CXX"); if (!cxx) cxx = "g++";
     // -march=native: the code runs on the machine that compiles it (mulx / adx shorten the carry chains); compiler, flags
     // and CPU model are part of the key, so a cache on a shared home never serves another machine's object
@@ -255,12 +445,12 @@ public:
 static thread_local std::string g_trace_backend = "not run";
 const char* trace_backend_status() { return g_trace_backend.c_str(); }
 
-void trace_prepare(const AirHost* S) { g_trace_backend = jit_get(S->transition, S->R, (int)S->statics.size())->status; }
+void trace_prepare(const AirHost* S) { g_trace_backend = jit_get(S)->status; }
 
 void generate_trace(const AirHost* S, const u128* init_state, const fp* input_traces, fp* tr, const TraceChunkFn* on_chunk) {
     const int R = S->R; const long long T = 1ll << S->log_t;
     const size_t n_stat = S->statics.size();
-    const std::shared_ptr<TraceJit> jit = jit_get(S->transition, R, (int)n_stat);
+    const std::shared_ptr<TraceJit> jit = jit_get(S);
     g_trace_backend = jit->status;
     if (jit->fn) {
         std::vector<w128> state(R);
