@@ -474,8 +474,10 @@ void generate_trace(const AirHost* S, const u128* init_state, const fp* input_tr
         int threads = (int)std::thread::hardware_concurrency(); if (threads > 16) threads = 16;
         if (const char* e = getenv("GS_TRACE_THREADS")) threads = atoi(e);
         std::vector<long long> cut;                     // cut[k]: first row of chunk k
-        if (threads >= 2 && T >= 4096 && R <= 64) {
-            int P = 1; while (2 * P <= threads && T / (2 * P) >= 1024) P *= 2;
+        // chunks of at least 256 steps: a chunk is handed to a waiting worker in a few microseconds (TracePool), and 256 steps
+        // of a hash round are >= 100 us of work (2^12 steps of the Rescue chain: 16 chunks instead of 4)
+        if (threads >= 2 && T >= 1024 && R <= 64) {
+            int P = 1; while (2 * P <= threads && T / (2 * P) >= 256) P *= 2;
             const long long chunk = T / P;
             auto state_free = [&](long long s) {        // transition at step s ignores the current state?
                 w128 sa[64], sb[64];
