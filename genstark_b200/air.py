@@ -256,6 +256,8 @@ class AirModule:
     # optional fast path of expand_inputs: inputs -> the same columns as one bytes object (16-byte little-endian elements,
     # register after register); used on the prove path, where a Python list of T integers per register costs more than the proof
     expand_inputs_blob: Optional[Callable] = None
+    # the same for expand_public_inputs (verify path): public_inputs -> the columns as bytes
+    expand_public_inputs_blob: Optional[Callable] = None
 
     def __post_init__(self):
         if self.constraint_degrees is None:
@@ -336,6 +338,17 @@ def input_blob(air: 'AirModule', inputs) -> Optional[bytes]:
         return None
     p = air.modulus
     return b''.join((int(v) % p).to_bytes(16, 'little') for t in traces for v in t)
+
+
+def public_blob(air: 'AirModule', public_inputs) -> Optional[bytes]:
+    """T-length columns of the public input registers as gs_stark_verify takes them (public_traces)"""
+    if air.expand_public_inputs_blob is not None:
+        return air.expand_public_inputs_blob(public_inputs or []) or None
+    pub = air.expand_public_inputs(public_inputs or [])
+    if not pub:
+        return None
+    p = air.modulus
+    return b''.join((int(v) % p).to_bytes(16, 'little') for t in pub for v in t)
 
 
 def input_cbuf(air: 'AirModule', inputs):

@@ -333,6 +333,14 @@ def poseidon_merkle_proof(depth: int = 8, proofs: int = 1, extension_factor: int
             out[s] = int(bits[nxt // period][(nxt % period) // cyc]) % p
         return [out]
 
+    def expand_public_blob(public_inputs):
+        """the column of expand_public(), gathered with numpy (verify path)"""
+        import numpy as np
+        (bits,) = public_inputs
+        nxt = (np.arange(steps, dtype=np.int64) + 1) % steps
+        at = (nxt // period) * depth + (nxt % period) // cyc
+        return gather_columns_blob([([x for row in bits for x in row], at)], p)
+
     def init(inputs, seed):
         leaf0, leaf1, node0, node1, _ = inputs
         lf, nd = [int(leaf0[0]) % p, int(leaf1[0]) % p], [int(node0[0][0]) % p, int(node1[0][0]) % p]
@@ -342,6 +350,7 @@ def poseidon_merkle_proof(depth: int = 8, proofs: int = 1, extension_factor: int
         name='poseidon_mp', modulus=p, trace_register_count=12, trace_length=steps,
         transition=t.build(), evaluation=e.build(), static_registers=statics, extension_factor=extension_factor,
         init=init, expand_inputs=expand, expand_public_inputs=expand_public, expand_inputs_blob=expand_blob,
+        expand_public_inputs_blob=expand_public_blob,
         input_shapes=lambda inputs: [[proofs], [proofs], [proofs, depth], [proofs, depth], [proofs, depth]])
 
 

@@ -15,7 +15,7 @@ import struct
 from typing import Dict, List, Optional, Sequence
 
 from . import _native
-from .air import AirModule, input_blob, input_cbuf, pack_air
+from .air import AirModule, input_blob, input_cbuf, pack_air, public_blob
 from .field import Context
 
 DEFAULT_EXE_QUERY_COUNT, DEFAULT_FRI_QUERY_COUNT = 80, 40          # Stark.ts:13-14
@@ -413,8 +413,7 @@ def verify_proof(air: AirModule, options: dict, assertions: Sequence[dict], proo
         expected = None
     if expected is not None and [list(x) for x in claimed] != expected:
         raise StarkError(f'Verification failed: the proof was generated for input shapes {claimed}, this instance is built for {expected}')
-    pub = air.expand_public_inputs(publicInputs or [])
-    pub_blob = b''.join((int(v) % p).to_bytes(16, 'little') for t in pub for v in t) if pub else None
+    pub_blob = public_blob(air, publicInputs)
     blob = pack_air(air)
     err = C.create_string_buffer(512)
     rc = lib.gs_stark_verify(blob, len(blob), HASH_ALGORITHMS.index(alg), int(options.get('exeQueryCount') or DEFAULT_EXE_QUERY_COUNT),

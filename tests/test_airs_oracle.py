@@ -53,3 +53,9 @@ def test_numpy_input_expansion_equals_the_list_based_one():
         slow = b''.join((int(v) % p).to_bytes(16, 'little') for t in air.expand_inputs(inputs) for v in t)
         assert input_blob(air, inputs) == slow
         assert len(slow) == 16 * air.trace_length * sum(1 for s in air.static_registers if s.kind == 'input')
+    # verify path: the public-input columns, numpy against the list-based expansion
+    from genstark_b200.air import public_blob
+    for air, _, _, inputs, _ in (cases.poseidon(2, 1, e=16), cases.poseidon(4, 8)):
+        p, pub = air.modulus, inputs[4:]
+        assert air.expand_public_inputs_blob is not None
+        assert public_blob(air, pub) == b''.join((int(v) % p).to_bytes(16, 'little') for t in air.expand_public_inputs(pub) for v in t)
